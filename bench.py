@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the CPPF hot path (point pairs -> pair MLP -> votes -> pose).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): synthetic NOCS-bottle clouds, N = 4096 points,
+bottle constants, ALL N^2 = 16 777 216 ordered point pairs per object ("dense pairs"),
+random-init weights of the reference architecture.  One step = one object per rank through
+the whole per-object pipeline (point encoder -> pair MLP -> sampling -> centre vote ->
+argmax -> back-vote -> second pass -> orientation vote -> pose).  Objects shard over
+ranks (weak scaling); the 17-float pose records are gathered once over NCCL at the end of
+the timed region.
+
+  value : point-pairs / second, whole job, inputs resident in HBM.
+  e2e   : same metric through the public API with HOST buffers: the pinned cloud is copied
+          host->device and the pose record device->host inside every timed step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "point_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-points", type=int, default=4096)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=400_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {"workload": f"synthetic NOCS bottle, N={args.n_points} points, dense N^2={args.n_points ** 2} pairs/object, "
+                        "bottle constants (res 4e-3, 32 tr bins, 36 rot bins, 72 rots, adaptive), 1 object/rank/step",
+            "n_points": args.n_points, "pairs_per_object": args.n_points ** 2, "objects_per_step_per_rank": 1,
+            "out_dim": 141, "parallelism": f"objects sharded over {args.gpus} rank(s), one NCCL all_gather of pose records",
+            "l2_policy": "per-step working set (pair table + mu/nu + logits of 16.7M pairs, >4 GB) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if "Active" in cell and "Not" not in cell:
+                    reasons.add(name)
+        if sm:
+            hi = [v for v in sm if v >= 0.5 * max(sm)]
+            out = {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------ CPU reference path
+def cpu_reference_step(pc, nrm, sd_pe, sd_ppf, idxs, cfg, sphere, seed):
+    """The reference's own per-object path on the CPU for a bounded pair sample: oracle
+    restatement of the torch modules (reference models/model.py, run by torch CPU with all
+    threads) + the reference's CUDA-C voting strings compiled for the CPU with OpenMP
+    (oracle/_ref/libref_voting_cpu.so; falls back to the plain-C port if it did not travel)."""
+    from oracle import clib, ref_model
+    impl = "ref_cpu" if clib.have_ref_cpu() else "oracle"
+    n = pc.shape[0]
+    tpc, tn = torch.from_numpy(pc), torch.from_numpy(nrm)
+    dist = torch.cdist(tpc[None], tpc[None])[0]
+    feat = ref_model.point_encode(tpc, tn, dist, sd_pe, cfg["knn"])
+    logits = ref_model.ppf_encode_idx(tpc, tn, feat, idxs, sd_ppf)
+    B = cfg["tr_num_bins"]
+    g = torch.Generator().manual_seed(seed)
+    pr = torch.softmax(logits[:, :2 * B].reshape(-1, 2, B), -1)
+    bins = torch.cat([torch.multinomial(pr[:, 0], 1, generator=g), torch.multinomial(pr[:, 1], 1, generator=g)], -1)
+    tr = ref_model.decode_tr(bins[:, 0], bins[:, 1], B, cfg["vote_range"]).numpy()
+    lo, hi = pc.min(0), pc.max(0)
+    dims = ((hi - lo) / cfg["res"]).astype(np.int32) + 1
+    idx32 = idxs.astype(np.int32)
+    grid = clib.ppf_voting(pc, tr, np.ones(n, np.float32), idx32, dims, lo, cfg["res"], 72, True, impl=impl)
+    flat, centre = ref_model.centre_from_grid(grid, lo, cfg["res"])
+    oc = clib.backvote(pc, tr, idx32, dims, lo, cfg["res"], centre.astype(np.float32), 3 * cfg["res"], 72, impl=impl)
+    kept = idxs[np.any(oc != 0, -1)]
+    if len(kept):
+        l2 = ref_model.ppf_encode_idx(tpc, tn, feat, kept, sd_ppf)
+        up = torch.multinomial(torch.softmax(l2[:, 2 * B:2 * B + cfg["rot_num_bins"]], -1), 1, generator=g)[:, 0]
+        rot = ref_model.decode_rot(up, cfg["rot_num_bins"]).numpy().astype(np.float32)
+        sub = np.random.default_rng(seed).permutation(len(kept))[:10000]
+        cand = clib.rot_voting(pc, rot[sub], kept[sub].astype(np.int32), 72, impl=impl)
+        counts = ((torch.from_numpy(cand.reshape(-1, 3)) @ torch.from_numpy(sphere.T.astype(np.float32))) >
+                  float(np.cos(1.5 / 180 * np.pi))).sum(0)
+        best = sphere[int(torch.argmax(counts))]
+        ref_model.aux_sign(pc, nrm, kept, best, l2[:, -5].numpy())
+    return int(flat), impl
+
+
+def run_cpu_reference(args, steps, warmup, sample_pairs):
+    from cppf_b200 import model, synth
+    from oracle import ref_model
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = synth.BOTTLE
+    torch.manual_seed(0)
+    sd_pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).state_dict()
+    sd_ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).state_dict()
+    sphere = ref_model.fibonacci_sphere(480)
+    n = args.n_points
+    times, impl = [], "oracle"
+    for s in range(warmup + steps):
+        pc, nrm = synth.synth_bottle(n, s)
+        idxs = synth.sample_pairs(n, sample_pairs, s)
+        t0 = time.perf_counter()
+        _, impl = cpu_reference_step(pc, nrm, sd_pe, sd_ppf, idxs, cfg, sphere, s)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": sample_pairs * len(times) / total, "ms_per_step": 1e3 * total / len(times), "impl": impl,
+            "cores": torch.get_num_threads(),
+            "sample": f"{sample_pairs} random pairs of the N={n} object per step ({len(times)} steps): point encoder + "
+                      "pair MLP (torch CPU, all threads) + multinomial + vote/back-vote/rot-vote "
+                      f"({'reference CUDA-C strings built for CPU, OpenMP' if impl == 'ref_cpu' else 'plain-C oracle port'})"}
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    cfgj = workload_config(args)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_cpu_reference(args, max(1, args.steps), max(0, min(args.warmup, 1)), args.cpu_sample_pairs)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgj,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"],
+                                 "kind": "reference" if r["impl"] == "ref_cpu" else "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    from cppf_b200 import _lib, model, synth
+    from cppf_b200.pipeline import PoseConfig, PoseEstimator
+
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(dev).eval()
+    ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).to(dev).eval()
+    pcfg = PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=0))        # 0 = all N^2 ordered pairs
+    est = PoseEstimator(pe, ppf, pcfg, dev)
+    n = args.n_points
+    pairs_per_obj = n * n
+    n_obj = args.warmup + args.steps
+    clouds = [synth.synth_bottle(n, 1000 * rank + s) for s in range(n_obj)]
+    pinned = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(q).pin_memory()) for p, q in clouds]
+    h2d = 2 * n * 3 * 4 + 12
+    d2h = 8 * 8 + 8
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(leg):
+        """leg 'hbm': clouds already on the device; leg 'e2e': pinned host buffers in, pose record out."""
+        records = []
+        resident = [(p.to(dev), q.to(dev)) for p, q in pinned] if leg == "hbm" else None
+        timers = {}
+        est.timers = timers
+        for s in range(args.warmup):
+            src = resident[s] if leg == "hbm" else pinned[s]
+            est.estimate(src[0], src[1], seed=s)
+        timers.clear()
+        barrier()
+        l0 = _lib.launch_count()
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(args.warmup, n_obj):
+            src = resident[s] if leg == "hbm" else pinned[s]
+            records.append(est.estimate(src[0], src[1], seed=s)["record"])
+        rec = torch.from_numpy(np.stack(records)).to(dev)
+        if dist_on:
+            allrec = [torch.empty_like(rec) for _ in range(world)]
+            dist.all_gather(allrec, rec)                                  # the one collective: pose hypotheses
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        launches = _lib.launch_count() - l0
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist_on:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        est.timers = None
+        return float(t.item()), launches, clocks, timers
+
+    ms_hbm, launches, clocks, timers = run("hbm")
+    ms_e2e, _, _, _ = run("e2e")
+    total_pairs = world * args.steps * pairs_per_obj
+    value = total_pairs / (ms_hbm * 1e-3)
+    e2e = total_pairs / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        kern = {}
+        for name, evs in timers.items():
+            durs = [a.elapsed_time(b) for a, b in evs]
+            if durs:
+                kern[name] = {"avg_ms": sum(durs) / len(durs), "launches": len(durs)}
+        # algorithmic HBM bytes per launch: first-pass encode writes 64 fp32 logits
+        # per pair (dense pairs: no index read); vote reads 8 B (mu,nu) per pair and owns the grid.
+        algo = {"ppf_encode_pass1": pairs_per_obj * 64 * 4, "ppf_vote": pairs_per_obj * 8}
+        roof = None
+        if kern:
+            dom = max(kern, key=lambda k: kern[k]["avg_ms"])
+            for k in kern:
+                if k in algo:
+                    kern[k]["achieved_gbs"] = algo[k] / (kern[k]["avg_ms"] * 1e-3) / 1e9
+                    kern[k]["pairs_per_s"] = pairs_per_obj / (kern[k]["avg_ms"] * 1e-3)
+            if dom in algo:
+                a = kern[dom]["achieved_gbs"]
+                roof = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                        "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                        "algorithmic_bytes_per_launch": algo[dom], "avg_launch_ms": kern[dom]["avg_ms"]}
+        cpu = None
+        if not args.no_cpu_baseline:
+            r = run_cpu_reference(args, 2, 1, args.cpu_sample_pairs)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"],
+                   "kind": "reference" if r["impl"] == "ref_cpu" else "port", "sample": r["sample"]}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_hbm / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfgj,
+                "objects_per_sec": world * args.steps / (ms_hbm * 1e-3),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "objects_per_sec": world * args.steps / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""ctypes binding of ``libcppf_b200.so`` (C ABI in ``include/cppf_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or a call returns a
+CUDA error, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcppf_b200.so")
+_lib = None
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_f = C.c_float
+
+# name -> (restype, argtypes); mirrors include/cppf_b200.h line by line
+SIGNATURES = {
+    "cppf_abi_version": (_i, []),
+    "cppf_error_string": (C.c_char_p, [_i]),
+    "cppf_launch_count": (C.c_uint64, []),
+    "cppf_ppf_blob_floats": (_i, [_i]),
+    "cppf_ppf_feat_dim": (_i, []),
+    "cppf_ppf_preproject": (_i, [_p, _p, _p, _i, _p]),
+    "cppf_ppf_encode": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _i, _i64, _i, _i, _i, _p]),
+    "cppf_sample_bins": (_i, [_p, _i64, _i, _i, _i, _i, _p, C.c_uint64, C.c_uint32, _f, _f, _f, _f, _p, _i, _p, _p]),
+    "cppf_ppf_vote": (_i, [_p, _p, _p, _p, _i, _p, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),
+    "cppf_grid_argmax": (_i, [_p, _i64, _p, _p, _p]),
+    "cppf_backvote": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _i, _i64, _i, _i, _i, _i, _p, _f, _p]),
+    "cppf_compact_scratch_bytes": (_i64, [_i64]),
+    "cppf_compact_pairs": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _p, _p]),
+    "cppf_rot_vote": (_i, [_p, _p, _p, _p, _i, _i64, _i, _p]),
+    "cppf_sphere_count": (_i, [_p, _i64, _p, _i, _f, _p, _p]),
+    "cppf_findpeak": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+}
+
+
+def lib():
+    """The loaded library; raises loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m cppf_b200.build` "
+                "(cppf_b200 has no CPU or PyTorch fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str = "cppf_b200") -> None:
+    if code != 0:
+        msg = lib().cppf_error_string(code)
+        raise RuntimeError(f"{what} failed: CUDA error {code} ({msg.decode() if msg else '?'})")
+
+
+def launch_count() -> int:
+    return int(lib().cppf_launch_count())

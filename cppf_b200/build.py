@@ -1,0 +1,68 @@
+"""Build recipe for libcppf_b200.so: plain nvcc, sm_100a only, in-tree output.
+
+``python -m cppf_b200.build`` (or ``__graft_entry__.build()``) cross-compiles every
+``csrc/*.cu`` with ``-gencode arch=compute_100a,code=sm_100a -lineinfo`` and links
+them into ``cppf_b200/libcppf_b200.so`` (git-ignored; travels to the GPU box).
+"""
+from __future__ import annotations
+
+import glob
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
+LIB = os.path.join(HERE, "libcppf_b200.so")
+NVCC = os.environ.get("NVCC", "nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _digest(paths):
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for p in sorted(paths):
+        h.update(p.encode())
+        h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + \
+        [os.path.join(os.path.dirname(HERE), "include", "cppf_b200.h")]
+    stamp = os.path.join(OBJ, "stamp")
+    dig = _digest(deps)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    logs = {}
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        logs[src] = r.stdout + r.stderr
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{logs[src]}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
+        for s in srcs:
+            f.write(f"==== {os.path.basename(s)}\n{logs[s]}\n")
+    with open(stamp, "w") as f:
+        f.write(dig)
+    if verbose:
+        print(open(os.path.join(OBJ, "ptxas.log")).read(), file=sys.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

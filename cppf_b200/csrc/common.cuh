@@ -1,0 +1,113 @@
+// Shared device helpers for the cppf_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cppf {
+
+// process-wide launch counter behind cppf_launch_count() (defined in abi.cu)
+void count_launch(int n = 1);
+
+#define CPPF_RETURN_IF(err_expr)                         \
+    do {                                                 \
+        cudaError_t _e = (err_expr);                     \
+        if (_e != cudaSuccess) return (int)_e;           \
+    } while (0)
+
+#define CPPF_LAUNCH_CHECK()                              \
+    do {                                                 \
+        cppf::count_launch();                            \
+        cudaError_t _e = cudaGetLastError();             \
+        if (_e != cudaSuccess) return (int)_e;           \
+    } while (0)
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+struct f3 {
+    float x, y, z;
+};
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ f3 operator/(f3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float len3(f3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ f3 ld3(const float* __restrict__ p, int64_t i) {
+    return {__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)};
+}
+
+// (a, b) of pair p: from an int32/int64 index list, or row-major dense enumeration.
+template <bool IDX64>
+__device__ __forceinline__ void pair_ab(const void* __restrict__ idx, int64_t p, int n_points, int& a, int& b) {
+    if (idx == nullptr) {
+        a = (int)(p / n_points);
+        b = (int)(p - (int64_t)a * n_points);
+    } else if (IDX64) {
+        const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(idx) + p);
+        a = (int)v.x;
+        b = (int)v.y;
+    } else {
+        const int2 v = __ldg(reinterpret_cast<const int2*>(idx) + p);
+        a = v.x;
+        b = v.y;
+    }
+}
+
+// The frame every voting kernel of the reference builds first
+// (models/voting.py:18-29, 84-94, 127-137): unit ab and the unit in-plane axis ex.
+// The double-precision islands of the CUDA-C strings (`1e-7` literals) are kept:
+// the degenerate test is a double compare, the normaliser a double sum rounded to float.
+__device__ __forceinline__ bool pair_frame(f3 a, f3 b, f3& ab, f3& ex) {
+    ab = a - b;
+    const float len = len3(ab);
+    if ((double)len < 1e-7) return false;
+    ab = ab / (float)((double)len + 1e-7);
+    f3 co = {0.f, -ab.z, ab.y};
+    float lc = len3(co);
+    if ((double)lc < 1e-7) {
+        co = {-ab.y, ab.x, 0.f};
+        lc = len3(co);
+    }
+    ex = co / (float)((double)lc + 1e-7);
+    return true;
+}
+
+// angle_i = float(double(2 i) * pi / double(n)) -- models/voting.py:33,99,140
+__device__ __forceinline__ float rot_angle(int i, int n) {
+    return (float)((double)(i * 2) * 3.14159265358979323846264338327950288 / (double)n);
+}
+
+// adaptive rotation count -- models/voting.py:31,97: min(int(odist / res * (2*M_PI)), n_rots)
+__device__ __forceinline__ int adaptive_rots(float odist, float res, int n_rots) {
+    const int m = (int)((double)(odist / res) * (2 * 3.14159265358979323846264338327950288));
+    return m < n_rots ? m : n_rots;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: 4 uniform words per (key, counter).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// uniform in [0,1) with 24 random bits
+__device__ __forceinline__ float u01(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+
+}  // namespace cppf

@@ -1,0 +1,265 @@
+"""Host-side mirror of the reference's ``models/model.py`` (PointEncoder, PPFEncoder,
+ResLayer) backed by the sm_100a kernels in ``libcppf_b200.so``.
+
+Same class names, constructor kwargs, ``state_dict`` keys/shapes and call signatures as
+the reference (``models/model.py:8-137``, ``models/sprin.py:63-107``), so checkpoints
+load unchanged and ``nocs/inference.py:82-88,181-182,236`` can use these classes as is.
+Inference only: the modules never build autograd graphs and raise if asked to.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+# offsets of cppf_b200/csrc/mlp_layout.h
+_F = 40
+_OFF_PRE_WA = 0
+_OFF_PRE_WB = _OFF_PRE_WA + _F * 64
+_OFF_PRE_BIAS = _OFF_PRE_WB + _F * 64
+_OFF_PAIR = _OFF_PRE_BIAS + 64
+_FINAL_CHUNK = 48
+SUPPORTED_PPFFCS = (2 * _F + 4, 32, 32, 16)
+
+
+def _perm_cols(m: np.ndarray, no: int) -> np.ndarray:
+    """[K, 8*no] logical column j = og + 8c  ->  stored column og*no + c (mlp_layout.h)."""
+    k = m.shape[0]
+    return np.ascontiguousarray(m.reshape(k, no, 8).transpose(0, 2, 1).reshape(k, 8 * no))
+
+
+def pack_ppf_weights(sd, out_dim: int) -> np.ndarray:
+    """Pack a PPFEncoder ``state_dict`` into the blob the kernels read (mlp_layout.h)."""
+    g = lambda k: sd[k].detach().to("cpu", torch.float32).numpy()
+    w1_0, b1_0 = g("res_layers.0.fc1.weight"), g("res_layers.0.fc1.bias")
+    w0_0, b0_0 = g("res_layers.0.fc0.weight"), g("res_layers.0.fc0.bias")
+    w2_0, b2_0 = g("res_layers.0.fc2.weight"), g("res_layers.0.fc2.bias")
+    w1_1, b1_1 = g("res_layers.1.fc1.weight"), g("res_layers.1.fc1.bias")
+    w2_1, b2_1 = g("res_layers.1.fc2.weight"), g("res_layers.1.fc2.bias")
+    w1_2, b1_2 = g("res_layers.2.fc1.weight"), g("res_layers.2.fc1.bias")
+    w0_2, b0_2 = g("res_layers.2.fc0.weight"), g("res_layers.2.fc0.bias")
+    w2_2, b2_2 = g("res_layers.2.fc2.weight"), g("res_layers.2.fc2.bias")
+    wf, bf = g("final.weight"), g("final.bias")
+    if w1_0.shape != (32, 2 * _F + 4) or w1_1.shape != (32, 32) or w1_2.shape != (16, 32) or wf.shape != (out_dim, 16):
+        raise NotImplementedError("the sm_100a pair MLP is specialised to ppffcs=[84,32,32,16] "
+                                  f"(nocs/inference.py:83); got {w1_0.shape}, {w1_1.shape}, {w1_2.shape}, {wf.shape}")
+    outp = (out_dim + _FINAL_CHUNK - 1) // _FINAL_CHUNK * _FINAL_CHUNK
+    both0 = np.concatenate([w1_0, w0_0], 0)                       # [64, 84]
+    parts = [
+        both0[:, :_F].T,                                          # PRE_WA [40,64]
+        both0[:, _F:2 * _F].T,                                    # PRE_WB [40,64]
+        np.concatenate([b1_0, b0_0 + b2_0]),                      # PRE_BIAS
+        both0[:, 2 * _F:].T,                                      # W_PPF [4,64]
+        _perm_cols(w2_0.T, 4),
+        _perm_cols(w1_1.T, 4), _perm_cols(b1_1[None], 4),
+        _perm_cols(w2_1.T, 4), _perm_cols(b2_1[None], 4),
+        _perm_cols(np.concatenate([w1_2, w0_2], 0).T, 4),
+        _perm_cols(np.concatenate([b1_2, b0_2 + b2_2])[None], 4),
+        _perm_cols(w2_2.T, 2),
+    ]
+    wf_p = np.zeros((16, outp), np.float32)
+    wf_p[:, :out_dim] = wf.T
+    bf_p = np.zeros((1, outp), np.float32)
+    bf_p[0, :out_dim] = bf
+    nch = outp // _FINAL_CHUNK
+    perm_f = lambda m: m.reshape(m.shape[0], nch, 6, 8).transpose(0, 1, 3, 2).reshape(m.shape[0], outp)
+    parts += [perm_f(wf_p), perm_f(bf_p)]
+    blob = np.concatenate([np.ascontiguousarray(p, dtype=np.float32).reshape(-1) for p in parts])
+    assert blob.size == _lib.lib().cppf_ppf_blob_floats(out_dim), (blob.size, out_dim)
+    return blob
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _f32c(t, device):
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(t)
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _no_grad_only(*tensors):
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise RuntimeError("cppf_b200 is inference-only (training/backward is out of scope): "
+                           "call under torch.no_grad() with inputs that do not require grad")
+
+
+class ResLayer(nn.Module):
+    """Parameter container with the reference's names (models/model.py:8-25).  The
+    arithmetic (models/model.py:26-31) runs fused inside the pair-MLP kernel."""
+
+    def __init__(self, dim_in, dim_out, bn=False) -> None:
+        super().__init__()
+        assert bn is False
+        self.fc1 = nn.Linear(dim_in, dim_out)
+        self.fc2 = nn.Linear(dim_out, dim_out)
+        self.fc0 = nn.Linear(dim_in, dim_out) if dim_in != dim_out else None
+
+    def forward(self, x):
+        raise RuntimeError("ResLayer is evaluated inside PPFEncoder's fused sm_100a kernel; "
+                           "there is no stand-alone (PyTorch) path")
+
+
+class PPFEncoder(nn.Module):
+    """Drop-in for reference ``models/model.py:80-137``."""
+
+    def __init__(self, ppffcs, out_dim) -> None:
+        super().__init__()
+        self.ppffcs = tuple(int(v) for v in ppffcs)
+        self.out_dim = int(out_dim)
+        self.res_layers = nn.ModuleList(ResLayer(i, o, bn=False) for i, o in zip(ppffcs[:-1], ppffcs[1:]))
+        self.final = nn.Linear(ppffcs[-1], out_dim)
+        self._blob = None
+        self._blob_key = None
+
+    # ---- weight blob cache (re-packed whenever parameters move or change)
+    def weight_blob(self, device) -> torch.Tensor:
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._blob is None or self._blob_key != key:
+            if self.ppffcs != SUPPORTED_PPFFCS:
+                raise NotImplementedError(f"pair MLP kernels are specialised to ppffcs={list(SUPPORTED_PPFFCS)}, "
+                                          f"got {list(self.ppffcs)}")
+            blob = pack_ppf_weights(self.state_dict(), self.out_dim)
+            self._blob = torch.from_numpy(blob).to(device)
+            self._blob_key = key
+        return self._blob
+
+    def preproject(self, feat: torch.Tensor) -> torch.Tensor:
+        """Per-point table of ResLayer-0's feature columns (cppf_ppf_preproject)."""
+        n = feat.shape[0]
+        table = torch.empty((n, 128), dtype=torch.float32, device=feat.device)
+        L = _lib.lib()
+        _lib.check(L.cppf_ppf_preproject(feat.data_ptr(), self.weight_blob(feat.device).data_ptr(), table.data_ptr(),
+                                         n, _stream_ptr(feat.device)), "cppf_ppf_preproject")
+        return table
+
+    def _encode(self, pc, pc_normal, feat, idxs, dist, cols=None):
+        _no_grad_only(pc, pc_normal, feat, *self.parameters())
+        device = feat.device if isinstance(feat, torch.Tensor) else torch.device("cuda")
+        if device.type != "cuda":
+            raise RuntimeError("cppf_b200.PPFEncoder runs on CUDA tensors only (no CPU fallback)")
+        with torch.cuda.device(device):
+            pc, pc_normal, feat = _f32c(pc, device), _f32c(pc_normal, device), _f32c(feat, device)
+            n = pc.shape[0]
+            if feat.shape != (n, _F) or pc.shape != (n, 3) or pc_normal.shape != (n, 3):
+                raise ValueError(f"expected pc/normal [N,3] and feat [N,{_F}], got {tuple(pc.shape)}, "
+                                 f"{tuple(pc_normal.shape)}, {tuple(feat.shape)}")
+            table = self.preproject(feat)
+            col0, ncol = (0, self.out_dim) if cols is None else cols
+            if idxs is None:
+                n_pairs, idx_ptr, is64 = n * n, None, 0
+                if dist is not None:
+                    dist = _f32c(dist, device)
+                    if dist.shape != (n, n):
+                        raise ValueError("dist must be [N,N]")
+            else:
+                if isinstance(idxs, np.ndarray):
+                    idxs = torch.from_numpy(np.ascontiguousarray(idxs))
+                idxs = idxs.to(device)
+                if idxs.dtype not in (torch.int64, torch.int32):
+                    idxs = idxs.long()
+                idxs = idxs.contiguous()
+                if idxs.dim() != 2 or idxs.shape[1] != 2:
+                    raise ValueError("idxs must be [P,2]")
+                n_pairs, idx_ptr, is64 = idxs.shape[0], idxs.data_ptr(), int(idxs.dtype == torch.int64)
+            out = torch.empty((n_pairs, ncol), dtype=torch.float32, device=device)
+            L = _lib.lib()
+            _lib.check(L.cppf_ppf_encode(pc.data_ptr(), pc_normal.data_ptr(), table.data_ptr(),
+                                         self.weight_blob(device).data_ptr(), idx_ptr, is64,
+                                         dist.data_ptr() if dist is not None else None, out.data_ptr(),
+                                         n, n_pairs, self.out_dim, col0, ncol, _stream_ptr(device)), "cppf_ppf_encode")
+        return out
+
+    def forward(self, pc, pc_normal, feat, dist=None, idxs=None):
+        """models/model.py:89-115.  Batched [1,N,*] inputs; with ``idxs`` -> [1,P,out_dim],
+        dense -> [1,N,N,out_dim] (all ordered pairs, row = point a)."""
+        if idxs is not None:
+            return self.forward_with_idx(pc[0], pc_normal[0], feat[0], idxs)[None]
+        if pc.shape[0] != 1:
+            raise NotImplementedError("the reference drives batch size 1 (nocs/inference.py:174); got batch "
+                                      f"{pc.shape[0]}")
+        n = pc.shape[1]
+        out = self._encode(pc[0], pc_normal[0], feat[0], None, None if dist is None else dist[0])
+        return out.view(1, n, n, self.out_dim)
+
+    def forward_with_idx(self, pc, pc_normal, feat, idxs):
+        """models/model.py:117-137.  pc,pc_normal [N,3], feat [N,40], idxs [P,2] -> [P,out_dim]."""
+        return self._encode(pc, pc_normal, feat, idxs, None)
+
+
+# ---------------------------------------------------------------------------------------
+# Point encoder (reference models/model.py:34-77, models/sprin.py:63-107).
+def conv_kernel(iunit, ounit, *hunits):
+    """models/sprin.py:63-71 layout, so Sequential indices (state_dict keys) match."""
+    layers = []
+    for unit in hunits:
+        layers += [nn.Linear(iunit, unit), nn.LayerNorm(unit), nn.ReLU()]
+        iunit = unit
+    layers.append(nn.Linear(iunit, ounit))
+    return nn.Sequential(*layers)
+
+
+class GlobalInfoProp(nn.Module):
+    def __init__(self, n_in, n_global):
+        super().__init__()
+        self.linear = nn.Linear(n_in, n_global)
+
+
+class SparseSO3Conv(nn.Module):
+    def __init__(self, rank, n_in, n_out, *kernel_interns, layer_norm=True):
+        super().__init__()
+        self.kernel = conv_kernel(6, rank, *kernel_interns)
+        self.outnet = nn.Linear(rank * n_in, n_out)
+        self.rank = rank
+        self.layer_norm = nn.LayerNorm(n_out) if layer_norm else None
+
+
+class PointEncoder(nn.Module):
+    """Drop-in for reference ``models/model.py:34-77`` (num_layers=1 as at every call site,
+    nocs/inference.py:82).  O(N k) work; this round it is composed from torch CUDA ops on
+    the object's device (SURVEY.md section 8 row a5 / f1 schedules the fused kNN+SPRIN kernel next)."""
+
+    def __init__(self, k, spfcs, out_dim, num_layers=2, num_nbr_feats=2) -> None:
+        super().__init__()
+        if num_layers != 1:
+            raise NotImplementedError("every reference call site uses num_layers=1 (nocs/inference.py:82)")
+        self.k = k
+        self.spconvs = nn.ModuleList([SparseSO3Conv(32, num_nbr_feats, out_dim, *spfcs)])
+        self.aggrs = nn.ModuleList([GlobalInfoProp(out_dim, out_dim // 4)])
+
+    def forward(self, pc, pc_normal, dist):
+        """models/model.py:46-61: k nearest (self included) from the caller's distance matrix."""
+        _no_grad_only(pc, pc_normal, dist)
+        nbrs_idx = torch.topk(dist, self.k, largest=False, sorted=False)[1]
+        return self.forward_nbrs(pc, pc_normal, nbrs_idx)
+
+    def forward_nbrs(self, pc, pc_normal, nbrs_idx):
+        """models/model.py:63-77.  pc,pc_normal [B,N,3], nbrs_idx [B,N,K] -> [B,N,out+out//4]."""
+        _no_grad_only(pc, pc_normal)
+        with torch.no_grad():
+            conv, aggr = self.spconvs[0], self.aggrs[0]
+            b_idx = torch.arange(pc.shape[0], device=pc.device)[:, None, None]
+            nb = pc[b_idx, nbrs_idx]                                             # [B,N,K,3] absolute coords
+            centre = pc.unsqueeze(-2)
+            nbr_feat = torch.cat([(nb - centre).norm(dim=-1, keepdim=True),
+                                  (pc_normal[b_idx, nbrs_idx] * pc_normal.unsqueeze(-2)).sum(-1, keepdim=True)], -1)
+            # rotation-invariant edge features (models/sprin.py:40-60)
+            mean = nb.mean(-2, keepdim=True)
+            l1, l2, l3 = mean - nb, nb - centre, centre - mean
+            n1, n2 = l1.norm(dim=-1, keepdim=True), l2.norm(dim=-1, keepdim=True)
+            n3 = l3.norm(dim=-1, keepdim=True).expand_as(n2)
+            ri = torch.cat([n1, n2, n3,
+                            (l1 * l2).sum(-1, keepdim=True) / (n1 * n2 + 1e-7),
+                            (l2 * l3).sum(-1, keepdim=True) / (n2 * n3 + 1e-7),
+                            (l3 * l1).sum(-1, keepdim=True) / (n3 * n1 + 1e-7)], -1)
+            kern = conv.kernel(ri)                                               # [B,N,K,rank]
+            contracted = torch.einsum("bnkr,bnki->bnri", kern, nbr_feat).flatten(-2)
+            out = conv.outnet(contracted)
+            if conv.layer_norm is not None:
+                out = conv.layer_norm(out)
+            tran = aggr.linear(out)
+            glob = tran.max(-2, keepdim=True)[0].expand(*out.shape[:-1], tran.shape[-1])
+            return torch.cat([out, glob], -1)

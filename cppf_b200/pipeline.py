@@ -1,0 +1,213 @@
+"""Per-object pose pipeline: the script body of the reference's ``nocs/inference.py:174-339``
+(and ``sunrgbd/inference.py:142-287``) as a function over the cppf_b200 kernels.
+
+    point encoder -> pair MLP -> sample (mu, nu) -> centre vote -> argmax -> back-vote
+    -> compaction -> pair MLP on survivors -> sample axis angle -> orientation candidates
+    -> sphere histogram -> aux sign -> scale -> RT
+
+Everything between the host->device copy of the cloud and the device->host copy of the
+17-float pose record stays on the GPU; the only host round trip inside is the survivor
+count (one int64) that sizes the second pass.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import voting
+from .synth import vote_grid_geometry
+
+
+def fibonacci_sphere(samples: int) -> np.ndarray:
+    """Orientation bins, same construction as the reference's utils/util.py:102-118."""
+    i = np.arange(samples, dtype=np.float64)
+    y = 1 - (i / float(samples - 1)) * 2
+    r = np.sqrt(1 - y * y)
+    th = math.pi * (3.0 - math.sqrt(5.0)) * i
+    return np.stack([np.cos(th) * r, y, np.sin(th) * r], -1)
+
+
+@dataclass
+class PoseConfig:
+    """Per-category constants (config/config.yaml:1-28 + config/category/*.yaml of the reference)
+    and the inference flags of nocs/inference.py:32-43."""
+    res: float = 4e-3
+    vote_range: tuple = (0.25, 0.25)
+    scale_mean: tuple = (0.05, 0.15, 0.05)
+    up_sym: bool = True
+    regress_right: bool = False
+    z_right: bool = False
+    tr_num_bins: int = 32
+    rot_num_bins: int = 36
+    knn: int = 60
+    num_rots: int = 72
+    angle_prec: float = 1.5
+    adaptive_voting: bool = True
+    n_pairs: int = 100000               # nocs/inference.py:177; 0 = all N^2 ordered pairs
+    rot_subsample: int = 10000          # nocs/inference.py:279-281; 0 = use every survivor
+    scale_mul: float = 2.0              # nocs/inference.py:335 (SUN RGB-D: 1.0, sunrgbd/inference.py:281)
+    category: str = "bottle"
+    extra: dict = field(default_factory=dict)
+
+    @classmethod
+    def from_dict(cls, d):
+        keys = cls.__dataclass_fields__.keys()
+        return cls(**{k: (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in d.items() if k in keys})
+
+
+class PoseEstimator:
+    """One category's encoders + constants.  ``estimate`` handles one object."""
+
+    def __init__(self, point_encoder, ppf_encoder, cfg: PoseConfig, device="cuda"):
+        self.pe, self.ppf, self.cfg = point_encoder, ppf_encoder, cfg
+        self.device = torch.device(device)
+        n_bins = int(4 * np.pi / (cfg.angle_prec / 180 * np.pi))                  # nocs/inference.py:100-101
+        self.sphere_np = fibonacci_sphere(n_bins)
+        self.sphere = torch.from_numpy(self.sphere_np.astype(np.float32)).to(self.device)
+        self.cos_thr = float(np.float32(np.cos(cfg.angle_prec / 180 * np.pi)))     # :283
+        self.scale_mean = torch.tensor(cfg.scale_mean, dtype=torch.float32, device=self.device)
+        self.timers = None            # optional {name: [(start_event, end_event), ...]} filled by estimate()
+
+    def _timed(self, name):
+        est = self
+
+        class _Ctx:
+            def __enter__(self):
+                if est.timers is not None:
+                    self.a = torch.cuda.Event(enable_timing=True)
+                    self.b = torch.cuda.Event(enable_timing=True)
+                    self.a.record()
+
+            def __exit__(self, *exc):
+                if est.timers is not None:
+                    self.b.record()
+                    est.timers.setdefault(name, []).append((self.a, self.b))
+        return _Ctx()
+
+    # ------------------------------------------------------------------ stages
+    @torch.no_grad()
+    def point_features(self, pc, nrm):
+        dist = torch.cdist(pc[None], pc[None])                                      # nocs/inference.py:180
+        return self.pe(pc[None], nrm[None], dist)[0]                                # :181
+
+    @torch.no_grad()
+    def estimate(self, pc_host: np.ndarray, nrm_host: np.ndarray, seed: int = 0, idxs=None, noise=None,
+                 return_debug: bool = False):
+        """pc_host, nrm_host: float32 [N,3] host arrays (pinned or not).  Returns a dict with
+        RT [4,4], scales [3] (nocs/inference.py:336-339) and a 17-float `record`."""
+        cfg, dev = self.cfg, self.device
+        noise = noise or {}
+        n = pc_host.shape[0]
+        pc = torch.as_tensor(pc_host).to(dev, non_blocking=True)                    # :174-175
+        nrm = torch.as_tensor(nrm_host).to(dev, non_blocking=True)
+        if isinstance(pc_host, torch.Tensor) and pc_host.is_cuda:                   # cloud already resident in HBM
+            corner = pc.min(0)[0]
+            dims = tuple(int(v) for v in (((pc.max(0)[0] - corner) / cfg.res).int() + 1).cpu())
+        else:
+            corner_np, dims = vote_grid_geometry(np.asarray(pc_host), cfg.res)      # :194-195
+            corner = torch.from_numpy(corner_np).to(dev, non_blocking=True)
+        if idxs is None and cfg.n_pairs > 0:                                        # :177
+            g = torch.Generator(device=dev).manual_seed(seed)
+            idxs = torch.randint(0, n, (cfg.n_pairs, 2), generator=g, device=dev, dtype=torch.int32)
+        elif idxs is not None:
+            idxs = torch.as_tensor(idxs).to(dev)
+        feat = self.point_features(pc, nrm)
+
+        # ---- first pass: translation heads only (columns 0:64, :183-188)
+        B = cfg.tr_num_bins
+        with self._timed("ppf_encode_pass1"):
+            logits_tr = self.ppf._encode(pc, nrm, feat, idxs, None, cols=(0, 2 * B))
+        mu_nu = torch.empty((logits_tr.shape[0], 2), dtype=torch.float32, device=dev)
+        mu_nu[:, 0] = voting.sample_bins(logits_tr, 0, B, q=noise.get("q_mu"), u=noise.get("u_mu"), seed=seed, stream_id=0,
+                                         div=B - 1, mul_a=2.0, mul_b=cfg.vote_range[0], sub=cfg.vote_range[0])
+        mu_nu[:, 1] = voting.sample_bins(logits_tr, B, B, q=noise.get("q_nu"), u=noise.get("u_nu"), seed=seed, stream_id=1,
+                                         div=B - 1, mul_a=cfg.vote_range[1])
+        del logits_tr
+
+        # ---- centre voting + argmax (:191-211)
+        grid = torch.zeros(dims, dtype=torch.float32, device=dev)
+        with self._timed("ppf_vote"):
+            voting.ppf_vote(pc, mu_nu, idxs, grid, corner, cfg.res, cfg.num_rots, cfg.adaptive_voting)
+        flat = voting.grid_argmax(grid)
+        gyz = dims[1] * dims[2]
+        cell = torch.stack([flat // gyz, (flat % gyz) // dims[2], flat % dims[2]], -1)[0]
+        T_est = corner.double() + cell.double() * cfg.res                           # :209 float64 like numpy
+        centre = T_est.float()
+
+        # ---- back-vote filter + compaction (:216-231)
+        _, mask = voting.backvote(pc, mu_nu, idxs, dims, corner, cfg.res, centre, 3 * cfg.res, cfg.num_rots,
+                                  want_offsets=False)
+        kept, cnt, _ = voting.compact_pairs(mask, idxs, n)
+        n_kept = int(cnt.item())                                                    # the one host sync
+        kept = kept[:n_kept]
+        out = {"T": T_est, "n_survivors": n_kept, "grid_dims": dims, "argmax": flat}
+        if n_kept == 0:
+            raise RuntimeError("no pair voted for the winning centre (degenerate input)")
+
+        # ---- second pass on the survivors (:236-256): rotation / aux / scale heads
+        R0 = 2 * B
+        RB = cfg.rot_num_bins
+        heads = self.ppf._encode(pc, nrm, feat, kept, None, cols=(R0, self.ppf.out_dim - R0))
+        preds_up_aux, preds_right_aux = heads[:, -5], heads[:, -4]
+        log_scale = heads[:, -3:].mean(0)                                           # :335
+        dirs = []
+        for j, (col, aux, tag) in enumerate([(0, preds_up_aux, "up"), (RB, preds_right_aux, "right")]):
+            if j == 1 and not cfg.regress_right:                                    # :260-261
+                continue
+            rot = voting.sample_bins(heads, col, RB, q=noise.get(f"q_{tag}"), u=noise.get(f"u_{tag}"), seed=seed,
+                                     stream_id=2 + j, div=RB - 1, mul_a=float(np.float32(np.pi)))     # :250-256
+            sub = kept
+            if cfg.rot_subsample and n_kept > cfg.rot_subsample:                    # :277-281
+                g = torch.Generator(device=dev).manual_seed(seed + 17 + j)
+                sel = torch.randperm(n_kept, generator=g, device=dev)[:cfg.rot_subsample]
+                sub, rot_sub = kept[sel].contiguous(), rot[sel].contiguous()
+            else:
+                rot_sub = rot
+            cand = voting.rot_vote(pc, rot_sub, sub, cfg.num_rots)                  # :265-275
+            counts = voting.sphere_count(cand, self.sphere, self.cos_thr)           # :282-283
+            best = torch.argmax(counts)                                             # :284 (first max)
+            best_dir = self.sphere[best]
+            # aux sign (:286-302)
+            a_i, b_i = kept[:, 0].long(), kept[:, 1].long()
+            ab = pc[a_i] - pc[b_i]
+            abn = ab / (ab.pow(2).sum(-1).sqrt() + 1e-7)[:, None]
+            pn = nrm[a_i]
+            pn = torch.where(((pn * abn).sum(-1) < 0)[:, None], -pn, pn)
+            target = ((pn * best_dir).sum(-1) > 0).float()
+            up_loss = torch.nn.functional.binary_cross_entropy_with_logits(aux, target)
+            down_loss = torch.nn.functional.binary_cross_entropy_with_logits(aux, 1.0 - target)
+            sign = torch.where(down_loss < up_loss, -1.0, 1.0)
+            dirs.append((best, sign))
+            if return_debug:
+                out[f"counts_{tag}"] = counts
+        # ---- pose assembly (:305-339), on the host in float64 like the reference
+        rec = torch.cat([torch.stack([d[0].double() for d in dirs]), torch.stack([d[1].double() for d in dirs]),
+                         T_est, log_scale.double()]).cpu().numpy()                  # single D2H
+        k = len(dirs)
+        up = self.sphere_np[int(rec[0])] * rec[k]
+        if cfg.regress_right:
+            right = self.sphere_np[int(rec[1])] * rec[k + 1]
+            right = right - np.dot(up, right) * up
+            right /= (np.linalg.norm(right) + 1e-9)
+        else:
+            right = np.array([0, -up[2], up[1]])
+            right /= (np.linalg.norm(right) + 1e-9)
+        if np.linalg.norm(right) < 1e-7:
+            right = np.array([up[1], -up[0], 0.0])
+            right /= (np.linalg.norm(right) + 1e-9)
+        R = np.stack([np.cross(up, right), up, right], -1) if cfg.z_right else np.stack([right, up, np.cross(right, up)], -1)
+        T = rec[2 * k:2 * k + 3]
+        pred_scale = np.exp(rec[2 * k + 3:2 * k + 6].astype(np.float32)) * np.asarray(cfg.scale_mean) * cfg.scale_mul
+        sn = np.linalg.norm(pred_scale)
+        RT = np.eye(4, dtype=np.float32)
+        RT[:3, :3] = R * sn
+        RT[:3, 3] = T
+        out.update(RT=RT, scales=(pred_scale / sn).astype(np.float32), up=up, right=right, T_host=T,
+                   pred_scale=pred_scale,
+                   record=np.concatenate([[0.0, float(n_kept)], pred_scale, R.reshape(-1), T]).astype(np.float32))
+        if return_debug:
+            out.update(grid=grid, mu_nu=mu_nu, kept=kept, idxs=idxs, feat=feat)
+        return out

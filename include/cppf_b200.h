@@ -1,0 +1,129 @@
+/* cppf_b200 -- C ABI of the B200 (sm_100a) implementation of CPPF's per-object hot path.
+ *
+ * Drop-in boundary.  The reference reaches this path through two
+ * Python modules; each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree):
+ *
+ *   models/model.py:117-137  PPFEncoder.forward_with_idx  -> cppf_ppf_encode (idx != NULL)
+ *   models/model.py:89-115   PPFEncoder.forward (dense)    -> cppf_ppf_encode (idx == NULL)
+ *   models/voting.py:4-67    ppf_kernel      (RawKernel)   -> cppf_ppf_vote
+ *   models/voting.py:70-113  backvote_kernel (RawKernel)   -> cppf_backvote
+ *   models/voting.py:115-148 rot_voting_kernel             -> cppf_rot_vote
+ *   models/voting.py:150-172 findpeak_kernel               -> cppf_findpeak
+ *   nocs/inference.py:185-188 softmax+multinomial+decode   -> cppf_sample_bins
+ *   nocs/inference.py:207-208 grid.get()+np.argmax         -> cppf_grid_argmax
+ *   nocs/inference.py:229-231 mask + compaction            -> cppf_compact_pairs
+ *   nocs/inference.py:276-284 candidates.mm(sphere)>thr    -> cppf_sphere_count
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Every pointer is a DEVICE
+ * pointer unless its name starts with `h_`.  The caller owns all buffers.  Every
+ * call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ * and returns a cudaError_t-style int (0 = success); nothing throws.  Degenerate
+ * pairs and out-of-grid votes are silently dropped exactly as the reference
+ * kernels do (models/voting.py:21,36-39).
+ */
+#ifndef CPPF_B200_H
+#define CPPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library info -------------------------------------------------------- */
+int cppf_abi_version(void);                 /* bumped on any signature change */
+const char* cppf_error_string(int code);    /* cudaGetErrorString passthrough */
+/* Number of CUDA kernels this library has launched since load (for bench.py's
+ * `gpu_launches`).  Process-wide, monotonically increasing. */
+uint64_t cppf_launch_count(void);
+
+/* ---- pair MLP weights ------------------------------------------------------
+ * The pair MLP is specialised to the reference architecture
+ * ppffcs=[2*40+4, 32, 32, 16] (nocs/inference.py:83); out_dim is free (141 for
+ * NOCS/SUN RGB-D, 9 for the zero-shot regression head).
+ * cppf_ppf_blob_floats(out_dim) gives the size of the packed weight blob; the host
+ * side packs a PPFEncoder state_dict into it (cppf_b200/model.py:pack_ppf_weights)
+ * following the layout documented in cppf_b200/csrc/mlp_layout.h. */
+int cppf_ppf_blob_floats(int out_dim);
+int cppf_ppf_feat_dim(void);                /* 40 */
+
+/* Per-point pre-projection of ResLayer-0's feature columns (layer-0 algebra,
+ * SURVEY.md section 7): table[n, 0:128].  Must run before cppf_ppf_encode / fused calls
+ * whenever feat or the weights change.  feat [n_points, 40], table [n_points, 128]. */
+int cppf_ppf_preproject(const float* feat, const float* blob, float* table, int n_points, void* stream);
+
+/* replaces PPFEncoder.forward_with_idx (models/model.py:117-137) when idx != NULL:
+ *   out[p, :] = final(ResLayers([feat[a], feat[b], ppf(a,b)])),  (a,b) = idx[p]
+ * and PPFEncoder.forward's dense branch (models/model.py:92-115) when idx == NULL:
+ *   all n_points^2 ordered pairs, row-major (p = a*n_points + b), n_pairs must be
+ *   n_points^2; `dist` (optional, [n_points, n_points]) is the caller-supplied
+ *   distance matrix of the reference signature -- NULL means exact norms.
+ * pc, nrm [n_points,3]; table from cppf_ppf_preproject; idx [n_pairs,2] int64 or
+ * int32 (idx_is_64); out [n_pairs, out_dim] fp32.
+ * col_begin/col_count restrict the `final` layer to a column window (e.g. 0,64 for the
+ * translation heads); out then has col_count columns. */
+int cppf_ppf_encode(const float* pc, const float* nrm, const float* table, const float* blob,
+                    const void* idx, int idx_is_64, const float* dist,
+                    float* out, int n_points, int64_t n_pairs, int out_dim,
+                    int col_begin, int col_count, void* stream);
+
+/* replaces softmax + torch.multinomial + bin decode (nocs/inference.py:185-188,245-256).
+ * logits [n_rows, row_stride], one categorical draw per row over columns
+ * [col0, col0+n_bins).  mode 0: exponential race argmax(p/q) with injected noise
+ * q[n_rows, n_bins] (reproduces torch.multinomial under the same generator);
+ * mode 1: inverse CDF with injected uniforms u[n_rows]; mode 2: inverse CDF with
+ * Philox4x32-10 uniforms keyed by (seed, row, stream_id).
+ * value = ((bin / div) * mul_a) * mul_b - sub, each step rounded to fp32 like the torch
+ * expression it replaces, written to out_val[row*out_stride]; out_bin (optional)
+ * receives the int32 bin. */
+int cppf_sample_bins(const float* logits, int64_t n_rows, int row_stride, int col0, int n_bins,
+                     int mode, const float* noise, uint64_t seed, uint32_t stream_id,
+                     float div, float mul_a, float mul_b, float sub,
+                     float* out_val, int out_stride, int32_t* out_bin, void* stream);
+
+/* replaces ppf_kernel / ppf_voting (models/voting.py:8-66).  grid [gx,gy,gz] is
+ * accumulated in place (caller zeroes it).  idx int32 [n_pairs,2] like the reference
+ * (nocs/inference.py:202) or int64.  idx == NULL enumerates all n_points^2 pairs. */
+int cppf_ppf_vote(const float* points, const float* mu_nu, const float* probs, const void* idx, int idx_is_64,
+                  float* grid, const float* corner, float res, int n_points, int64_t n_pairs, int n_rots,
+                  int gx, int gy, int gz, int adaptive, void* stream);
+
+/* replaces grid.get() + np.argmax (nocs/inference.py:207-208): first maximal flat
+ * index in C order -> *out_index (int64, device), optional *out_value. */
+int cppf_grid_argmax(const float* grid, int64_t n_cells, int64_t* out_index, float* out_value, void* stream);
+
+/* replaces backvote_kernel (models/voting.py:74-112).  out_offsets [n_pairs,3] follows
+ * the reference (written only for non-degenerate pairs); out_mask (optional, uint8
+ * [n_pairs]) = any(out_offsets != 0), the only thing the caller consumes
+ * (nocs/inference.py:229-230).  Either output may be NULL. */
+int cppf_backvote(const float* points, const float* mu_nu, float* out_offsets, uint8_t* out_mask,
+                  const void* idx, int idx_is_64, const float* corner, float res, int n_points, int64_t n_pairs,
+                  int n_rots, int gx, int gy, int gz, const float* centre, float tol, void* stream);
+
+/* replaces point_idxs[mask] (nocs/inference.py:230-231): order-preserving stream
+ * compaction of the surviving pairs.  out_idx [<= n_pairs, 2] int32 (a,b); out_pos
+ * (optional) the source pair position; *out_count (int64, device) the survivor count.
+ * scratch must hold cppf_compact_scratch_bytes(n_pairs) bytes. */
+int64_t cppf_compact_scratch_bytes(int64_t n_pairs);
+int cppf_compact_pairs(const uint8_t* mask, const void* idx, int idx_is_64, int n_points, int64_t n_pairs,
+                       int32_t* out_idx, int64_t* out_pos, int64_t* out_count, void* scratch, void* stream);
+
+/* replaces rot_voting_kernel (models/voting.py:119-147): outputs_up [n_pairs, n_rots, 3]. */
+int cppf_rot_vote(const float* points, const float* preds_rot, float* outputs_up, const void* idx, int idx_is_64,
+                  int64_t n_pairs, int n_rots, void* stream);
+
+/* replaces candidates.mm(sphere) > thr, sum(0) (nocs/inference.py:282-283).
+ * cand [n_cand,3], sphere [n_bins,3] fp32, counts int32 [n_bins] accumulated in place. */
+int cppf_sphere_count(const float* cand, int64_t n_cand, const float* sphere, int n_bins, float thr,
+                      int32_t* counts, void* stream);
+
+/* replaces findpeak_kernel (models/voting.py:154-171).  literal != 0 reproduces the
+ * string as shipped (comma operator at :165-166 drops the x term of the y reads);
+ * literal == 0 is the intended 6-neighbour second difference. */
+int cppf_findpeak(const float* grid, float* out, int width, int gx, int gy, int gz, int literal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPPF_B200_H */

@@ -1,0 +1,32 @@
+"""CPU: libcppf_b200.so loads (cross-compiled for sm_100a) and exports every symbol
+include/cppf_b200.h declares; the ctypes table mirrors the header."""
+import os
+import re
+
+from conftest import ROOT
+from cppf_b200 import _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cppf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cppf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    L = _lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in cppf_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in cppf_b200/_lib.py"
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_host_only_entry_points():
+    L = _lib.lib()
+    assert L.cppf_abi_version() >= 1
+    assert L.cppf_ppf_feat_dim() == 40
+    assert L.cppf_ppf_blob_floats(141) == 12336
+    assert L.cppf_compact_scratch_bytes(100000) > 0
+    assert L.cppf_launch_count() == 0 or L.cppf_launch_count() > 0

@@ -1,0 +1,85 @@
+"""CPU: the packed weight blob (cppf_b200/csrc/mlp_layout.h, model.pack_ppf_weights) is
+interpreted here in numpy exactly the way the kernels walk it -- pre-projection, PPF
+columns, permuted k-major matrices, 48-wide final chunks -- and must reproduce the
+reference logits of the golden fixture."""
+import numpy as np
+import torch
+
+from conftest import load_golden, split_state
+from cppf_b200 import model
+
+
+def _unperm(m, no):
+    k = m.shape[0]
+    return m.reshape(k, 8, no).transpose(0, 2, 1).reshape(k, 8 * no)     # stored og*no+c -> logical og+8c
+
+
+def test_blob_interpreter_reproduces_reference_logits():
+    d = load_golden("encoder_bottle.npz")
+    sd = split_state(d, "ppf/")
+    out_dim = 141
+    blob = model.pack_ppf_weights(sd, out_dim)
+    F = 40
+    o = 0
+    take = lambda n, shape: (blob[o:o + n].reshape(shape))
+    pre_wa = blob[0:F * 64].reshape(F, 64)
+    pre_wb = blob[F * 64:2 * F * 64].reshape(F, 64)
+    pre_b = blob[2 * F * 64:2 * F * 64 + 64]
+    p = blob[2 * F * 64 + 64:]
+    sec = {}
+    off = 0
+    for name, n in [("wppf", 256), ("w2_0", 1024), ("w1_1", 1024), ("b1_1", 32), ("w2_1", 1024), ("b2_1", 32),
+                    ("w10_2", 1024), ("b10_2", 32), ("w2_2", 256)]:
+        sec[name] = p[off:off + n]
+        off += n
+    outp = (out_dim + 47) // 48 * 48
+    wf = p[off:off + 16 * outp].reshape(16, outp)
+    bf = p[off + 16 * outp:off + 17 * outp]
+    assert off + 17 * outp == p.size
+
+    pc, nrm, feat, idxs = d["pc"], d["nrm"], d["feat"], d["idxs"]
+    table = np.concatenate([feat @ pre_wa + pre_b, feat @ pre_wb], 1)        # [N,128]
+    a, b = idxs[:, 0], idxs[:, 1]
+    dv = pc[a] - pc[b]
+    dn = np.sqrt((dv * dv).sum(-1)).astype(np.float32)
+    dh = dv / (dn[:, None] + np.float32(1e-7))
+    ppf = np.stack([(nrm[a] * dh).sum(-1), (nrm[b] * dh).sum(-1), (nrm[a] * nrm[b]).sum(-1), dn], -1)
+    l0 = table[a, :64] + table[b, 64:] + ppf @ sec["wppf"].reshape(4, 64)
+    h, r = np.maximum(l0[:, :32], 0), l0[:, 32:]
+    x1 = h @ _unperm(sec["w2_0"].reshape(32, 32), 4) + r
+    u = np.maximum(x1 @ _unperm(sec["w1_1"].reshape(32, 32), 4) + _unperm(sec["b1_1"][None], 4), 0)
+    x2 = u @ _unperm(sec["w2_1"].reshape(32, 32), 4) + _unperm(sec["b2_1"][None], 4) + x1
+    ur = x2 @ _unperm(sec["w10_2"].reshape(32, 32), 4) + _unperm(sec["b10_2"][None], 4)
+    x3 = np.maximum(ur[:, :16], 0) @ _unperm(sec["w2_2"].reshape(16, 16), 2) + ur[:, 16:]
+    unperm_f = lambda m: m.reshape(m.shape[0], outp // 48, 8, 6).transpose(0, 1, 3, 2).reshape(m.shape[0], outp)
+    logits = (x3 @ unperm_f(wf) + unperm_f(bf[None]))[:, :out_dim]
+    np.testing.assert_allclose(logits, d["logits"], rtol=2e-4, atol=2e-5)
+
+
+def test_state_dict_keys_match_reference_checkpoints():
+    d = load_golden("encoder_bottle.npz")
+    ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141)
+    pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32)
+    assert set(ppf.state_dict()) == set(split_state(d, "ppf/"))
+    assert set(pe.state_dict()) == set(split_state(d, "pe/"))
+    ppf.load_state_dict(split_state(d, "ppf/"))
+    pe.load_state_dict(split_state(d, "pe/"))
+    for k, v in pe.state_dict().items():
+        assert tuple(v.shape) == d["pe/" + k].shape
+
+
+def test_point_encoder_host_composition_matches_reference():
+    d = load_golden("encoder_bottle.npz")
+    pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).eval()
+    pe.load_state_dict(split_state(d, "pe/"))
+    with torch.no_grad():
+        f = pe.forward_nbrs(torch.from_numpy(d["pc"])[None], torch.from_numpy(d["nrm"])[None],
+                            torch.from_numpy(d["nbrs"])[None])
+    np.testing.assert_allclose(f[0].numpy(), d["feat_nbrs"], rtol=1e-4, atol=1e-5)
+
+
+def test_unsupported_architecture_fails_loudly():
+    import pytest
+    m = model.PPFEncoder(ppffcs=[84, 64, 32, 16], out_dim=141)
+    with pytest.raises(NotImplementedError):
+        m.weight_blob(torch.device("cpu"))
