@@ -35,6 +35,14 @@ SIGNATURES = {
     "cppf_rot_vote": (_i, [_p, _p, _p, _p, _i, _i64, _i, _p]),
     "cppf_sphere_count": (_i, [_p, _i64, _p, _i, _f, _p, _p]),
     "cppf_findpeak": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "cppf_head_blob_floats": (_i, []),
+    "cppf_encode_sample": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _p, C.c_uint64, _i, _p, _p, _p]),
+    "cppf_vote_scratch_bytes": (_i64, [_i, _i, _i]),
+    "cppf_vote_private_max_cells": (_i, []),
+    "cppf_vote_fast": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),
+    "cppf_backvote_bins": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _f, _f, _i, _i64, _i, _i, _i, _i, _p]),
+    "cppf_rot_hist": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i64, C.c_uint64, _f, _p]),
+    "cppf_survivor_stats": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i64, _p]),
 }
 
 

@@ -41,6 +41,20 @@ static int ensure_rot_table(cudaStream_t stream) {
     return 0;
 }
 
+// For kernels in other translation units (no relocatable device code): device address of the
+// initialised table, or nullptr with *err set.
+const float2* rot_table_device(cudaStream_t stream, int* err) {
+    *err = ensure_rot_table(stream);
+    if (*err) return nullptr;
+    void* ptr = nullptr;
+    const cudaError_t e = cudaGetSymbolAddress(&ptr, g_rot_table);
+    if (e != cudaSuccess) {
+        *err = (int)e;
+        return nullptr;
+    }
+    return reinterpret_cast<const float2*>(ptr);
+}
+
 // Smallest float f with (double)f >= d: turns the reference's double-precision bound
 // tests `(double)g < d` / `(double)g >= d` into exact float compares `g < f` / `g >= f`.
 static float float_ceil(double d) {
@@ -335,9 +349,9 @@ __global__ void __launch_bounds__(kCompactBlock) compact_scatter_kernel(const ui
 #pragma unroll
     for (int k = 0; k < kCompactItems; ++k) {
         if (flags & (1u << k)) {
-            int a, b;
-            pair_ab<IDX64>(idx, base + k, n_points, a, b);
-            reinterpret_cast<int2*>(out_idx)[o] = make_int2(a, b);
+            int a = 0, b = 0;
+            if (out_idx) pair_ab<IDX64>(idx, base + k, n_points, a, b);
+            if (out_idx) reinterpret_cast<int2*>(out_idx)[o] = make_int2(a, b);
             if (out_pos) out_pos[o] = base + k;
             ++o;
         }

@@ -1,0 +1,483 @@
+// Fast-path voting kernels (the "mode F" pipeline after encode_sample):
+//   * centre voting into a shared-memory-privatised fixed-point grid,
+//   * back-vote filter driven by the sampled bins,
+//   * fused orientation candidates + sphere histogram (no [P,72,3] dump),
+//   * survivor statistics (scale mean, aux-sign sums).
+// Semantics follow models/voting.py:8-66, 74-112, 119-147 and nocs/inference.py:276-302,335;
+// the measurements behind the design are in profiles/r1_atomics_microbench.json:
+// shared-memory u32 atomics sustain ~2000 G/s (500+ G/s on hot cells) against 90-180 G/s
+// (16 G/s hot) for global fp32 reductions.
+#include "common.cuh"
+
+#include "../../include/cppf_b200.h"
+
+#include <math.h>
+
+namespace cppf {
+
+constexpr int kMaxRotsP = 72;
+constexpr int kRotTabP = kMaxRotsP * (kMaxRotsP + 1) / 2;
+const float2* rot_table_device(cudaStream_t stream, int* err);   // vote.cu: (cos, sin) of angle(i, n), row n at n(n-1)/2
+
+constexpr int kFixShift = 14;                      // fixed-point fraction bits of a vote weight
+constexpr float kFixScale = 16384.f;
+constexpr unsigned kFixBudget = 0xFFFFFFFFu >> kFixShift;   // whole votes a u32 cell can absorb between flushes
+
+static float float_ceil_p(double d) {
+    float f = (float)d;
+    if ((double)f < d) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+// a / b with b fixed: q0 = a*y, r = a - b*q0 (exact in an FMA), q = q0 + r*y.  With y the correctly
+// rounded reciprocal of b this returns the correctly rounded quotient (Markstein), i.e. the same
+// bits as the reference's `/ res`, in 3 instructions instead of the ~8 of an IEEE divide.
+__device__ __forceinline__ float div_by(float a, float b, float y) {
+    const float q0 = a * y;
+    const float r = fmaf(-b, q0, a);
+    return fmaf(r, y, q0);
+}
+
+struct VotePParams {
+    const float2* rot_tab;
+    const float* points;
+    const float* mu_nu;        // [P][2] floats, or
+    const uint8_t* bins;       // [P][4] bins decoded through lut (mu: lut[0:32], nu: lut[32:64])
+    const float* lut;
+    const void* idx;
+    unsigned long long* acc;   // [cells] fixed-point accumulator (global)
+    const float* corner;
+    float res, inv_res;
+    float lo, hx, hy, hz;
+    int n_points;
+    long long n_pairs;
+    int n_rots, gx, gy, gz, adaptive;
+};
+
+template <bool IDX64, bool BINS>
+__global__ void __launch_bounds__(1024, 1) vote_private_kernel(const VotePParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tab = reinterpret_cast<float2*>(smem_raw);
+    float* s_lut = reinterpret_cast<float*>(s_tab + kRotTabP);
+    unsigned* s_grid = reinterpret_cast<unsigned*>(s_lut + 64);
+    __shared__ unsigned s_tally;
+    const int cells = prm.gx * prm.gy * prm.gz;
+    for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
+    if (BINS && threadIdx.x < 64) s_lut[threadIdx.x] = __ldg(prm.lut + threadIdx.x);
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) s_grid[i] = 0u;
+    if (threadIdx.x == 0) s_tally = 0u;
+    __syncthreads();
+
+    const int gyz = prm.gy * prm.gz, gz = prm.gz;
+    const float cx = __ldg(prm.corner), cy = __ldg(prm.corner + 1), cz = __ldg(prm.corner + 2);
+    const unsigned worst_batch = (unsigned)blockDim.x * (unsigned)prm.n_rots;
+    const long long n_batches = (prm.n_pairs + blockDim.x - 1) / blockDim.x;
+
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        const long long p = batch * blockDim.x + threadIdx.x;
+        unsigned voted = 0;
+        if (p < prm.n_pairs) {
+            int ia, ib;
+            pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
+            float mu, nu;
+            if (BINS) {
+                const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
+                mu = s_lut[bn.x];
+                nu = s_lut[32 + bn.y];
+            } else {
+                const float2 mn = __ldg(reinterpret_cast<const float2*>(prm.mu_nu) + p);
+                mu = mn.x;
+                nu = mn.y;
+            }
+            const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
+            f3 ab, ex;
+            if (pair_frame(a, b, ab, ex)) {                                    // voting.py:21
+                const f3 c = a - ab * mu;                                      // :23
+                const f3 x = ex * nu;                                          // :28
+                const f3 y = cross3(x, ab);                                    // :29
+                int n = prm.n_rots;
+                if (prm.adaptive) n = adaptive_rots(nu, prm.res, prm.n_rots);  // :31
+                const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
+                for (int i = 0; i < n; ++i) {
+                    const float2 cs = tab[i];
+                    const f3 off = x * cs.x + y * cs.y;                        // :34
+                    const float gxf = div_by(c.x + off.x - cx, prm.res, prm.inv_res);   // :35
+                    const float gyf = div_by(c.y + off.y - cy, prm.res, prm.inv_res);
+                    const float gzf = div_by(c.z + off.z - cz, prm.res, prm.inv_res);
+                    if (gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= prm.hx || gyf >= prm.hy || gzf >= prm.hz)
+                        continue;                                              // :36-39
+                    const int fx = (int)gxf, fy = (int)gyf, fz = (int)gzf;     // :40
+                    const float rx = gxf - floorf(gxf), ry = gyf - floorf(gyf), rz = gzf - floorf(gzf);
+                    const float wx0 = 1.f - rx, wy0 = 1.f - ry, wz0 = 1.f - rz;
+                    unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
+                    // :47-63, weights rounded to 2^-14 (prob == 1: nocs/inference.py:201)
+                    atomicAdd(cell, __float2uint_rn(wx0 * wy0 * wz0 * kFixScale));
+                    atomicAdd(cell + 1, __float2uint_rn(wx0 * wy0 * rz * kFixScale));
+                    atomicAdd(cell + gz, __float2uint_rn(wx0 * ry * wz0 * kFixScale));
+                    atomicAdd(cell + gz + 1, __float2uint_rn(wx0 * ry * rz * kFixScale));
+                    atomicAdd(cell + gyz, __float2uint_rn(rx * wy0 * wz0 * kFixScale));
+                    atomicAdd(cell + gyz + 1, __float2uint_rn(rx * wy0 * rz * kFixScale));
+                    atomicAdd(cell + gyz + gz, __float2uint_rn(rx * ry * wz0 * kFixScale));
+                    atomicAdd(cell + gyz + gz + 1, __float2uint_rn(rx * ry * rz * kFixScale));
+                    ++voted;
+                }
+            }
+        }
+        // overflow guard: a cell can have received at most `tally` whole votes since the last flush
+        voted = __reduce_add_sync(0xffffffffu, voted);
+        if ((threadIdx.x & 31) == 0 && voted) atomicAdd(&s_tally, voted);
+        __syncthreads();
+        const bool flush = s_tally + worst_batch + worst_batch / 8 > kFixBudget;   // (+1/8: rounding slack)
+        __syncthreads();
+        if (flush) {
+            for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+                const unsigned v = s_grid[i];
+                if (v) {
+                    atomicAdd(prm.acc + i, (unsigned long long)v);
+                    s_grid[i] = 0u;
+                }
+            }
+            if (threadIdx.x == 0) s_tally = 0u;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        const unsigned v = s_grid[i];
+        if (v) atomicAdd(prm.acc + i, (unsigned long long)v);
+    }
+}
+
+// grid[i] += acc[i] * 2^-14   (exact integer sum -> one rounding; deterministic run to run)
+__global__ void __launch_bounds__(256) vote_finalize_kernel(const unsigned long long* __restrict__ acc,
+                                                            float* __restrict__ grid, int cells) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cells) grid[i] += (float)((double)acc[i] * (1.0 / 16384.0));
+}
+
+// ---------------------------------------------------------------------------
+// Back-vote from bins -- models/voting.py:74-112 with (mu, nu) decoded from the sampled bins.
+struct BackvotePParams {
+    const float2* rot_tab;
+    const float* points;
+    const uint8_t* bins;
+    const float* lut;
+    const void* idx;
+    uint8_t* out_mask;
+    const float* corner;
+    const long long* argmax_flat;    // winning cell (device) -> centre = corner + cell * res
+    float res, inv_res, tol;
+    float hx, hy, hz;
+    int n_points;
+    long long n_pairs;
+    int n_rots, gx, gy, gz;
+};
+
+template <bool IDX64>
+__global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParams prm) {
+    __shared__ float2 s_tab[kRotTabP];
+    __shared__ float s_lut[64];
+    for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
+    if (threadIdx.x < 64) s_lut[threadIdx.x] = __ldg(prm.lut + threadIdx.x);
+    __syncthreads();
+    const float cx = __ldg(prm.corner), cy = __ldg(prm.corner + 1), cz = __ldg(prm.corner + 2);
+    // nocs/inference.py:208-209: T = corner + cell * res in float64, cast to float32 for the kernel (:226)
+    const long long flat = *prm.argmax_flat;
+    const int gyz = prm.gy * prm.gz;
+    const int ix = (int)(flat / gyz), iy = (int)((flat % gyz) / prm.gz), iz = (int)(flat % prm.gz);
+    const float tx = (float)((double)cx + (double)ix * (double)prm.res);
+    const float ty = (float)((double)cy + (double)iy * (double)prm.res);
+    const float tz = (float)((double)cz + (double)iz * (double)prm.res);
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < prm.n_pairs;
+         p += (long long)gridDim.x * blockDim.x) {
+        int ia, ib;
+        pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
+        const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
+        const float mu = s_lut[bn.x], nu = s_lut[32 + bn.y];
+        const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
+        f3 ab, ex;
+        bool hit = false;
+        if (pair_frame(a, b, ab, ex)) {
+            const f3 c = a - ab * mu;
+            const f3 x = ex * nu;
+            const f3 y = cross3(x, ab);
+            const int n = adaptive_rots(nu, prm.res, prm.n_rots);              // :97
+            const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
+            for (int i = 0; i < n; ++i) {
+                const float2 cs = tab[i];
+                const f3 off = x * cs.x + y * cs.y;
+                const f3 pc = c + off;
+                const f3 dlt = {pc.x - tx, pc.y - ty, pc.z - tz};
+                if (len3(dlt) > prm.tol) continue;                             // :102
+                const float gxf = div_by(pc.x - cx, prm.res, prm.inv_res);
+                const float gyf = div_by(pc.y - cy, prm.res, prm.inv_res);
+                const float gzf = div_by(pc.z - cz, prm.res, prm.inv_res);
+                if (gxf < 0.f || gyf < 0.f || gzf < 0.f || gxf >= prm.hx || gyf >= prm.hy || gzf >= prm.hz) continue;
+                hit = off.x != 0.f || off.y != 0.f || off.z != 0.f;            // inference.py:230 any(oc != 0)
+                break;
+            }
+        }
+        prm.out_mask[p] = hit ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Orientation voting on a sub-sample of the survivors, fused with the sphere histogram:
+// models/voting.py:119-147 + nocs/inference.py:276-284.  Survivor j of the sub-sample is
+// pos[(offset + j*stride) mod count] (stride coprime with count: a sample without
+// replacement, like the reference's shuffle).  A 512-thread block takes 16 pairs: frames ->
+// 16 x n_rots candidates in shared memory -> thread s accumulates bin s.
+struct RotHistParams {
+    const float2* rot_tab;
+    const float* points;
+    const uint8_t* bins;
+    const float* lut;            // up angles lut[64:100], right angles lut[100:136]
+    const void* idx;
+    const long long* pos;        // compacted survivor pair positions
+    const long long* count;      // number of survivors (device)
+    const float* sphere;         // [n_bins][3]
+    float* counts;               // [n_bins] float (exact integers)
+    int n_points, n_rots, n_bins, which;   // which: 0 up, 1 right
+    long long max_samples;
+    unsigned long long offset_seed;
+    float thr;
+};
+
+constexpr int kRotHistPairs = 16;
+
+template <bool IDX64>
+__global__ void __launch_bounds__(512) rot_hist_kernel(const RotHistParams prm) {
+    __shared__ float s_frame[kRotHistPairs][12];
+    __shared__ float4 s_cand[kRotHistPairs * kMaxRotsP];
+    const long long count = *prm.count;
+    const long long m = count < prm.max_samples ? count : prm.max_samples;
+    const long long j0 = (long long)blockIdx.x * kRotHistPairs;
+    if (j0 >= m) return;
+    // stride: a prime that does not divide count (so j -> (off + j*stride) mod count is a bijection)
+    unsigned long long stride = 1000003ull;
+    if (count % 1000003ll == 0) stride = 999983ull;
+    if (m == count) stride = 1ull;
+    const unsigned long long off = m == count ? 0ull : prm.offset_seed % (unsigned long long)count;
+    if (threadIdx.x < kRotHistPairs) {
+        float* fr = s_frame[threadIdx.x];
+        fr[10] = 0.f;
+        const long long j = j0 + threadIdx.x;
+        if (j < m) {
+            const long long p = prm.pos[(off + (unsigned long long)j * stride) % (unsigned long long)count];
+            int ia, ib;
+            pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
+            const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
+            const float rot = __ldg(prm.lut + (prm.which == 0 ? 64 + bn.z : 100 + bn.w));
+            const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
+            f3 ab, ex;
+            if (pair_frame(a, b, ab, ex)) {
+                const f3 y = cross3(ex, ab);
+                fr[0] = ab.x; fr[1] = ab.y; fr[2] = ab.z;
+                fr[3] = ex.x; fr[4] = ex.y; fr[5] = ex.z;
+                fr[6] = y.x; fr[7] = y.y; fr[8] = y.z;
+                fr[9] = tanf(rot);
+                fr[10] = 1.f;
+            }
+        }
+    }
+    __syncthreads();
+    const float2* tab = prm.rot_tab + prm.n_rots * (prm.n_rots - 1) / 2;
+    const int total = kRotHistPairs * prm.n_rots;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int lp = t / prm.n_rots, i = t - lp * prm.n_rots;
+        const float* fr = s_frame[lp];
+        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);       // zero vector never exceeds thr (> 0)
+        if (fr[10] != 0.f) {
+            const float2 cs = __ldg(tab + i);
+            const f3 ab = {fr[0], fr[1], fr[2]}, x = {fr[3], fr[4], fr[5]}, y = {fr[6], fr[7], fr[8]};
+            const float tn = fr[9];
+            const f3 o = x * cs.x + y * cs.y;
+            const f3 axis = tn > 0.f ? ab : f3{-ab.x, -ab.y, -ab.z};
+            f3 up = o * tn + axis;
+            up = up / (float)((double)len3(up) + 1e-7);
+            cv = make_float4(up.x, up.y, up.z, 0.f);
+        }
+        s_cand[t] = cv;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < prm.n_bins; s += blockDim.x) {
+        const float sx = __ldg(prm.sphere + 3 * s), sy = __ldg(prm.sphere + 3 * s + 1), sz = __ldg(prm.sphere + 3 * s + 2);
+        int cnt = 0;
+#pragma unroll 4
+        for (int i = 0; i < total; ++i) {
+            const float4 c = s_cand[i];
+            cnt += fmaf(c.z, sz, fmaf(c.y, sy, c.x * sx)) > prm.thr ? 1 : 0;
+        }
+        if (cnt) atomicAdd(prm.counts + s, (float)cnt);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Survivor statistics: out[0:3] = sum of log-scales, out[3] = count, out[4] = S_up, out[5] = S_right with
+// S = sum_i aux_i * (2 t_i - 1), t_i = [flip(n_a) . best_dir > 0]  (nocs/inference.py:286-302,335).
+// up_loss - down_loss of the reference's two BCE-with-logits means equals -2 S / count, so
+// `down_loss < up_loss`  <=>  S < 0.
+struct StatsParams {
+    const float* points;
+    const float* nrm;
+    const float* tail;           // [5][n_pairs]
+    const void* idx;
+    const long long* pos;
+    const long long* count;
+    const float* sphere;
+    const long long* best_up;    // argmax of the up histogram (device)
+    const long long* best_right; // or nullptr
+    double* out;                 // [6]
+    int n_points;
+    long long n_pairs;
+};
+
+template <bool IDX64>
+__global__ void __launch_bounds__(256) survivor_stats_kernel(const StatsParams prm) {
+    const long long count = *prm.count;
+    const long long bu = *prm.best_up;
+    const f3 du = {__ldg(prm.sphere + 3 * bu), __ldg(prm.sphere + 3 * bu + 1), __ldg(prm.sphere + 3 * bu + 2)};
+    f3 dr = {0.f, 0.f, 0.f};
+    if (prm.best_right) {
+        const long long br = *prm.best_right;
+        dr = {__ldg(prm.sphere + 3 * br), __ldg(prm.sphere + 3 * br + 1), __ldg(prm.sphere + 3 * br + 2)};
+    }
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (long long)gridDim.x * blockDim.x) {
+        const long long p = prm.pos[j];
+        int ia, ib;
+        pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
+        const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
+        const f3 ab = a - b;
+        const float inv = sqrtf(dot3(ab, ab)) + 1e-7f;                         // :288-289 (float32 numpy)
+        const f3 abn = {ab.x / inv, ab.y / inv, ab.z / inv};
+        f3 n = ld3(prm.nrm, ia);
+        if (dot3(n, abn) < 0.f) n = {-n.x, -n.y, -n.z};                        // :291-292
+        const float tu = dot3(n, du) > 0.f ? 1.f : -1.f;                       // :295
+        acc[0] += prm.tail[2 * prm.n_pairs + p];
+        acc[1] += prm.tail[3 * prm.n_pairs + p];
+        acc[2] += prm.tail[4 * prm.n_pairs + p];
+        acc[3] += 1.0;
+        acc[4] += (double)(prm.tail[p] * tu);
+        if (prm.best_right) acc[5] += (double)(prm.tail[prm.n_pairs + p] * (dot3(n, dr) > 0.f ? 1.f : -1.f));
+    }
+    __shared__ double s[8][6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0;
+        for (int w = 0; w < 8; ++w) v += s[w][threadIdx.x];
+        atomicAdd(prm.out + threadIdx.x, v);
+    }
+}
+
+}  // namespace cppf
+
+using namespace cppf;
+
+extern "C" int64_t cppf_vote_scratch_bytes(int gx, int gy, int gz) { return (int64_t)gx * gy * gz * 8; }
+
+extern "C" int cppf_vote_private_max_cells(void) {
+    return (int)((220 * 1024 - kRotTabP * 8 - 64 * 4 - 64) / 4);
+}
+
+extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut,
+                              const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
+                              int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
+                              void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long cells = (long long)gx * gy * gz;
+    if (cells <= 0 || cells > cppf_vote_private_max_cells() || n_rots > kMaxRotsP || n_rots <= 0)
+        return (int)cudaErrorInvalidValue;
+    if ((mu_nu == nullptr) == (bins == nullptr)) return (int)cudaErrorInvalidValue;
+    if (bins != nullptr && lut == nullptr) return (int)cudaErrorInvalidValue;
+    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
+    if (n_pairs <= 0) return 0;
+    int terr = 0;
+    const float2* rot_tab = rot_table_device(stream, &terr);
+    if (terr) return terr;
+    CPPF_RETURN_IF(cudaMemsetAsync(scratch, 0, (size_t)cells * 8, stream));
+    VotePParams prm{rot_tab, points, mu_nu, bins, lut, idx, reinterpret_cast<unsigned long long*>(scratch), corner, res,
+                    (float)(1.0 / (double)res), float_ceil_p(0.01), float_ceil_p((double)gx - 1.01),
+                    float_ceil_p((double)gy - 1.01), float_ceil_p((double)gz - 1.01), n_points, (long long)n_pairs,
+                    n_rots, gx, gy, gz, adaptive};
+    const size_t smem = (size_t)kRotTabP * 8 + 64 * 4 + (size_t)cells * 4;
+    const int threads = 1024;
+    long long blocks = (n_pairs + threads - 1) / threads;
+    if (blocks > sm_count()) blocks = sm_count();
+    void (*kern)(const VotePParams);
+    if (bins) kern = idx_is_64 ? vote_private_kernel<true, true> : vote_private_kernel<false, true>;
+    else kern = idx_is_64 ? vote_private_kernel<true, false> : vote_private_kernel<false, false>;
+    CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(int)blocks, threads, smem, stream>>>(prm);
+    CPPF_LAUNCH_CHECK();
+    vote_finalize_kernel<<<(int)((cells + 255) / 256), 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(scratch),
+                                                                        grid, (int)cells);
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, const float* lut, const void* idx,
+                                  int idx_is_64, uint8_t* out_mask, const float* corner, const int64_t* argmax_flat,
+                                  float res, float tol, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz,
+                                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pairs <= 0) return 0;
+    if (n_rots > kMaxRotsP || n_rots <= 0) return (int)cudaErrorInvalidValue;
+    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
+    int terr = 0;
+    const float2* rot_tab = rot_table_device(stream, &terr);
+    if (terr) return terr;
+    BackvotePParams prm{rot_tab, points, bins, lut, idx, out_mask, corner, reinterpret_cast<const long long*>(argmax_flat), res,
+                        (float)(1.0 / (double)res), tol, (float)(gx - 1), (float)(gy - 1), (float)(gz - 1), n_points,
+                        (long long)n_pairs, n_rots, gx, gy, gz};
+    long long blocks = (n_pairs + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (idx_is_64) backvote_bins_kernel<true><<<(int)blocks, 256, 0, stream>>>(prm);
+    else backvote_bins_kernel<false><<<(int)blocks, 256, 0, stream>>>(prm);
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cppf_rot_hist(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                             const int64_t* pos, const int64_t* count, const float* sphere, float* counts, int n_points,
+                             int n_rots, int n_bins, int which, int64_t max_samples, uint64_t offset_seed, float thr,
+                             void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_rots > kMaxRotsP || n_rots <= 0 || max_samples <= 0 || n_bins <= 0) return (int)cudaErrorInvalidValue;
+    int terr = 0;
+    const float2* rot_tab = rot_table_device(stream, &terr);
+    if (terr) return terr;
+    RotHistParams prm{rot_tab, points, bins, lut, idx, reinterpret_cast<const long long*>(pos),
+                      reinterpret_cast<const long long*>(count), sphere, counts, n_points, n_rots, n_bins, which,
+                      (long long)max_samples, offset_seed, thr};
+    const long long blocks = (max_samples + kRotHistPairs - 1) / kRotHistPairs;
+    if (blocks > 0x7FFFFFFF) return (int)cudaErrorInvalidValue;
+    if (idx_is_64) rot_hist_kernel<true><<<(int)blocks, 512, 0, stream>>>(prm);
+    else rot_hist_kernel<false><<<(int)blocks, 512, 0, stream>>>(prm);
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cppf_survivor_stats(const float* points, const float* nrm, const float* tail, const void* idx,
+                                   int idx_is_64, const int64_t* pos, const int64_t* count, const float* sphere,
+                                   const int64_t* best_up, const int64_t* best_right, double* out, int n_points,
+                                   int64_t n_pairs, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CPPF_RETURN_IF(cudaMemsetAsync(out, 0, 6 * sizeof(double), stream));
+    StatsParams prm{points, nrm, tail, idx, reinterpret_cast<const long long*>(pos),
+                    reinterpret_cast<const long long*>(count), sphere, reinterpret_cast<const long long*>(best_up),
+                    reinterpret_cast<const long long*>(best_right), out, n_points, (long long)n_pairs};
+    const int blocks = sm_count() * 4;
+    if (idx_is_64) survivor_stats_kernel<true><<<blocks, 256, 0, stream>>>(prm);
+    else survivor_stats_kernel<false><<<blocks, 256, 0, stream>>>(prm);
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}

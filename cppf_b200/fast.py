@@ -1,0 +1,119 @@
+"""Fused per-object path: thin torch-tensor wrappers over the `cppf_*` fast entry points
+(include/cppf_b200.h, section "fused per-object path").  Bins, tail logits, the vote grid
+and the survivor list stay on the device; nothing here synchronises."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import ROT_BINS, TR_BINS
+
+HEAD_TR, HEAD_UP, HEAD_RIGHT, HEAD_TAIL = 1, 2, 4, 8
+
+
+def _sp(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _idx_args(idxs):
+    if idxs is None:
+        return None, 0
+    assert idxs.dtype in (torch.int32, torch.int64) and idxs.is_contiguous()
+    return idxs.data_ptr(), int(idxs.dtype == torch.int64)
+
+
+def decode_lut(vote_range, tr_bins=TR_BINS, rot_bins=ROT_BINS) -> torch.Tensor:
+    """[136] fp32: value of every bin, built with the reference's own fp32 expression order
+    (nocs/inference.py:187-188: b/(B-1)*2*vr0 - vr0, b/(B-1)*vr1; :252,256: b/(R-1)*pi)."""
+    assert tr_bins == TR_BINS and rot_bins == ROT_BINS
+    t = torch.arange(tr_bins).float()
+    mu = t / (tr_bins - 1) * 2 * vote_range[0] - vote_range[0]
+    nu = t / (tr_bins - 1) * vote_range[1]
+    r = torch.arange(rot_bins).float() / (rot_bins - 1) * np.pi
+    return torch.cat([mu, nu, r, r]).float().contiguous()
+
+
+def encode_sample(ppf_encoder, pc, nrm, table, idxs, *, heads, uniforms=None, seed=0, bins=None, tail=None):
+    """-> (bins uint8 [P,4], tail f32 [5,P] | None)."""
+    dev = pc.device
+    n = pc.shape[0]
+    ip, is64 = _idx_args(idxs)
+    n_pairs = n * n if idxs is None else idxs.shape[0]
+    if bins is None:
+        bins = torch.empty((n_pairs, 4), dtype=torch.uint8, device=dev)
+    if (heads & HEAD_TAIL) and tail is None:
+        tail = torch.empty((5, n_pairs), dtype=torch.float32, device=dev)
+    if uniforms is not None:
+        assert uniforms.shape == (n_pairs, 4) and uniforms.is_contiguous() and uniforms.dtype == torch.float32
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cppf_encode_sample(
+            pc.data_ptr(), nrm.data_ptr(), table.data_ptr(), ppf_encoder.weight_blob(dev).data_ptr(),
+            ppf_encoder.head_blob(dev).data_ptr(), ip, is64, n, n_pairs,
+            uniforms.data_ptr() if uniforms is not None else None, int(seed), int(heads), bins.data_ptr(),
+            tail.data_ptr() if tail is not None else None, _sp(dev)), "cppf_encode_sample")
+    return bins, tail
+
+
+def vote_fits_private(dims) -> bool:
+    return int(dims[0]) * int(dims[1]) * int(dims[2]) <= _lib.lib().cppf_vote_private_max_cells()
+
+
+def vote_fast(points, idxs, grid, corner, res, *, mu_nu=None, bins=None, lut=None, n_rots=72, adaptive=True, scratch=None):
+    dev = points.device
+    n = points.shape[0]
+    ip, is64 = _idx_args(idxs)
+    n_pairs = n * n if idxs is None else idxs.shape[0]
+    gx, gy, gz = grid.shape
+    if scratch is None:
+        scratch = torch.empty(gx * gy * gz, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cppf_vote_fast(
+            points.data_ptr(), mu_nu.data_ptr() if mu_nu is not None else None,
+            bins.data_ptr() if bins is not None else None, lut.data_ptr() if lut is not None else None, ip, is64,
+            grid.data_ptr(), scratch.data_ptr(), corner.data_ptr(), float(res), n, n_pairs, int(n_rots), gx, gy, gz,
+            int(bool(adaptive)), _sp(dev)), "cppf_vote_fast")
+    return grid
+
+
+def backvote_bins(points, bins, lut, idxs, dims, corner, argmax_flat, res, tol, n_rots=72, mask=None):
+    dev = points.device
+    n = points.shape[0]
+    ip, is64 = _idx_args(idxs)
+    n_pairs = n * n if idxs is None else idxs.shape[0]
+    if mask is None:
+        mask = torch.empty(n_pairs, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cppf_backvote_bins(
+            points.data_ptr(), bins.data_ptr(), lut.data_ptr(), ip, is64, mask.data_ptr(), corner.data_ptr(),
+            argmax_flat.data_ptr(), float(res), float(tol), n, n_pairs, int(n_rots), int(dims[0]), int(dims[1]),
+            int(dims[2]), _sp(dev)), "cppf_backvote_bins")
+    return mask
+
+
+def rot_hist(points, bins, lut, idxs, pos, count, sphere, *, which, n_rots=72, max_samples=10000, offset_seed=0, thr,
+             counts=None):
+    dev = points.device
+    ip, is64 = _idx_args(idxs)
+    if counts is None:
+        counts = torch.zeros(sphere.shape[0], dtype=torch.float32, device=dev)
+    max_samples = max(1, min(int(max_samples), pos.shape[0]))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cppf_rot_hist(
+            points.data_ptr(), bins.data_ptr(), lut.data_ptr(), ip, is64, pos.data_ptr(), count.data_ptr(),
+            sphere.data_ptr(), counts.data_ptr(), points.shape[0], int(n_rots), sphere.shape[0], int(which),
+            int(max_samples), int(offset_seed), float(thr), _sp(dev)), "cppf_rot_hist")
+    return counts
+
+
+def survivor_stats(points, nrm, tail, idxs, pos, count, sphere, best_up, best_right=None):
+    """-> float64 [6]: sum log-scale x3, survivor count, S_up, S_right."""
+    dev = points.device
+    ip, is64 = _idx_args(idxs)
+    out = torch.empty(6, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cppf_survivor_stats(
+            points.data_ptr(), nrm.data_ptr(), tail.data_ptr(), ip, is64, pos.data_ptr(), count.data_ptr(),
+            sphere.data_ptr(), best_up.data_ptr(), best_right.data_ptr() if best_right is not None else None,
+            out.data_ptr(), points.shape[0], tail.shape[1], _sp(dev)), "cppf_survivor_stats")
+    return out

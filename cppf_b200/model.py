@@ -71,6 +71,38 @@ def pack_ppf_weights(sd, out_dim: int) -> np.ndarray:
     return blob
 
 
+TR_BINS, ROT_BINS = 32, 36          # config/config.yaml:7-8 of the reference
+HEAD_OUT_DIM = 2 * TR_BINS + 2 * ROT_BINS + 2 + 3
+
+
+def pack_head_weights(sd) -> np.ndarray:
+    """`final` layer re-cut head by head for the fused encode+sample kernel (csrc/fused.cu):
+    mu | nu : W[16][32] (permuted, NO=4) + b[32];  up | right : Wa[16][32] + ba[32] + Wb[16][8] + bb[8]
+    (bins 32..35 in columns 0..3 of Wb);  tail : W[16][8] + b[8] (aux_up, aux_right, log-scale x3)."""
+    wf = sd["final.weight"].detach().to("cpu", torch.float32).numpy()
+    bf = sd["final.bias"].detach().to("cpu", torch.float32).numpy()
+    if wf.shape != (HEAD_OUT_DIM, 16):
+        raise NotImplementedError(f"fused heads need out_dim == 2*{TR_BINS}+2*{ROT_BINS}+5 = {HEAD_OUT_DIM} "
+                                  f"(nocs/inference.py:83), got {wf.shape[0]}")
+    parts = []
+    for r0 in (0, TR_BINS):
+        parts += [_perm_cols(wf[r0:r0 + 32].T, 4), _perm_cols(bf[None, r0:r0 + 32], 4)]
+    for r0 in (2 * TR_BINS, 2 * TR_BINS + ROT_BINS):
+        wb = np.zeros((16, 8), np.float32)
+        bb = np.zeros(8, np.float32)
+        wb[:, :ROT_BINS - 32] = wf[r0 + 32:r0 + ROT_BINS].T
+        bb[:ROT_BINS - 32] = bf[r0 + 32:r0 + ROT_BINS]
+        parts += [_perm_cols(wf[r0:r0 + 32].T, 4), _perm_cols(bf[None, r0:r0 + 32], 4), wb, bb]
+    wt = np.zeros((16, 8), np.float32)
+    bt = np.zeros(8, np.float32)
+    wt[:, :5] = wf[HEAD_OUT_DIM - 5:].T
+    bt[:5] = bf[HEAD_OUT_DIM - 5:]
+    parts += [wt, bt]
+    blob = np.concatenate([np.ascontiguousarray(q, dtype=np.float32).reshape(-1) for q in parts])
+    assert blob.size == _lib.lib().cppf_head_blob_floats(), blob.size
+    return blob
+
+
 def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -114,6 +146,8 @@ class PPFEncoder(nn.Module):
         self.final = nn.Linear(ppffcs[-1], out_dim)
         self._blob = None
         self._blob_key = None
+        self._hblob = None
+        self._hblob_key = None
 
     # ---- weight blob cache (re-packed whenever parameters move or change)
     def weight_blob(self, device) -> torch.Tensor:
@@ -126,6 +160,14 @@ class PPFEncoder(nn.Module):
             self._blob = torch.from_numpy(blob).to(device)
             self._blob_key = key
         return self._blob
+
+    def head_blob(self, device) -> torch.Tensor:
+        """Head-wise `final` weights for the fused encode+sample kernel (pack_head_weights)."""
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.final.parameters())
+        if self._hblob is None or self._hblob_key != key:
+            self._hblob = torch.from_numpy(pack_head_weights(self.state_dict())).to(device)
+            self._hblob_key = key
+        return self._hblob
 
     def preproject(self, feat: torch.Tensor) -> torch.Tensor:
         """Per-point table of ResLayer-0's feature columns (cppf_ppf_preproject)."""

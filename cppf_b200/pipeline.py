@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from . import voting
+from . import fast, voting
 from .synth import vote_grid_geometry
 
 
@@ -70,6 +70,7 @@ class PoseEstimator:
         self.cos_thr = float(np.float32(np.cos(cfg.angle_prec / 180 * np.pi)))     # :283
         self.scale_mean = torch.tensor(cfg.scale_mean, dtype=torch.float32, device=self.device)
         self.timers = None            # optional {name: [(start_event, end_event), ...]} filled by estimate()
+        self.lut = fast.decode_lut(cfg.vote_range, cfg.tr_num_bins, cfg.rot_num_bins).to(self.device)
 
     def _timed(self, name):
         est = self
@@ -210,4 +211,98 @@ class PoseEstimator:
                    record=np.concatenate([[0.0, float(n_kept)], pred_scale, R.reshape(-1), T]).astype(np.float32))
         if return_debug:
             out.update(grid=grid, mu_nu=mu_nu, kept=kept, idxs=idxs, feat=feat)
+        return out
+
+
+    # ------------------------------------------------------------------ fused path
+    def _pose_from_record(self, rec, n_dirs):
+        """Host tail of nocs/inference.py:305-339 from one small device->host record:
+        rec = [flat, best_up, (best_right), scale_sum x3, count, S_up, S_right, corner x3] (float64)."""
+        cfg = self.cfg
+        flat = int(rec[0])
+        bests = [int(rec[1 + j]) for j in range(n_dirs)]
+        st = rec[1 + n_dirs:7 + n_dirs]
+        corner = rec[7 + n_dirs:10 + n_dirs]
+        dims = self._last_dims
+        cell = np.array(np.unravel_index(flat, dims))
+        T = corner + cell * cfg.res                                                 # :209
+        cnt = max(st[3], 1.0)
+        up = self.sphere_np[bests[0]] * (-1.0 if st[4] < 0 else 1.0)                # :299-302
+        if cfg.regress_right:
+            right = self.sphere_np[bests[1]] * (-1.0 if st[5] < 0 else 1.0)
+            right = right - np.dot(up, right) * up
+            right /= (np.linalg.norm(right) + 1e-9)
+        else:
+            right = np.array([0, -up[2], up[1]])
+            right /= (np.linalg.norm(right) + 1e-9)
+        if np.linalg.norm(right) < 1e-7:
+            right = np.array([up[1], -up[0], 0.0])
+            right /= (np.linalg.norm(right) + 1e-9)
+        R = np.stack([np.cross(up, right), up, right], -1) if cfg.z_right else np.stack([right, up, np.cross(right, up)], -1)
+        pred_scale = np.exp((st[:3] / cnt).astype(np.float32)) * np.asarray(cfg.scale_mean) * cfg.scale_mul    # :335
+        sn = np.linalg.norm(pred_scale)
+        RT = np.eye(4, dtype=np.float32)
+        RT[:3, :3] = R * sn
+        RT[:3, 3] = T
+        return dict(RT=RT, scales=(pred_scale / sn).astype(np.float32), up=up, right=right, T_host=T, pred_scale=pred_scale,
+                    n_survivors=int(st[3]), argmax_flat=flat, best_bins=bests,
+                    record=np.concatenate([[0.0, st[3]], pred_scale, R.reshape(-1), T]).astype(np.float32))
+
+    @torch.no_grad()
+    def estimate_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, return_debug: bool = False,
+                       sync: bool = True):
+        """Same pose as `estimate`, through the fused kernels: logits, (mu,nu) floats and rotation
+        candidates never reach HBM; a single ~100-byte record comes back to the host.
+        With sync=False returns the device record (torch tensor) and a finisher callable."""
+        cfg, dev = self.cfg, self.device
+        n = pc_in.shape[0]
+        pc = torch.as_tensor(pc_in).to(dev, non_blocking=True)
+        nrm = torch.as_tensor(nrm_in).to(dev, non_blocking=True)
+        if isinstance(pc_in, torch.Tensor) and pc_in.is_cuda:
+            corner = pc.min(0)[0]
+            dims = tuple(int(v) for v in (((pc.max(0)[0] - corner) / cfg.res).int() + 1).cpu())
+        else:
+            corner_np, dims = vote_grid_geometry(np.asarray(pc_in), cfg.res)
+            corner = torch.from_numpy(corner_np).to(dev, non_blocking=True)
+        self._last_dims = dims
+        if idxs is None and cfg.n_pairs > 0:
+            g = torch.Generator(device=dev).manual_seed(seed)
+            idxs = torch.randint(0, n, (cfg.n_pairs, 2), generator=g, device=dev, dtype=torch.int32)
+        elif idxs is not None:
+            idxs = torch.as_tensor(idxs).to(dev).contiguous()
+        with self._timed("point_encoder"):
+            feat = self.point_features(pc, nrm)
+        table = self.ppf.preproject(feat)
+        heads = fast.HEAD_TR | fast.HEAD_UP | fast.HEAD_TAIL | (fast.HEAD_RIGHT if cfg.regress_right else 0)
+        with self._timed("encode_sample"):
+            bins, tail = fast.encode_sample(self.ppf, pc, nrm, table, idxs, heads=heads, uniforms=uniforms, seed=seed)
+        grid = torch.zeros(dims, dtype=torch.float32, device=dev)
+        with self._timed("vote"):
+            if fast.vote_fits_private(dims) and cfg.num_rots <= 72:
+                fast.vote_fast(pc, idxs, grid, corner, cfg.res, bins=bins, lut=self.lut, n_rots=cfg.num_rots,
+                               adaptive=cfg.adaptive_voting)
+            else:                                   # grid too large for one SM's shared memory: global fp32 reductions
+                b = bins.long()
+                mu_nu = torch.stack([self.lut[b[:, 0]], self.lut[32 + b[:, 1]]], -1).contiguous()
+                voting.ppf_vote(pc, mu_nu, idxs, grid, corner, cfg.res, cfg.num_rots, cfg.adaptive_voting)
+        flat = voting.grid_argmax(grid)
+        with self._timed("backvote"):
+            mask = fast.backvote_bins(pc, bins, self.lut, idxs, dims, corner, flat, cfg.res, 3 * cfg.res, cfg.num_rots)
+            _, cnt, pos = voting.compact_pairs(mask, idxs, n, want_pos=True, want_idx=False)
+        bests = []
+        with self._timed("rot_hist"):
+            for j in range(2 if cfg.regress_right else 1):
+                counts = fast.rot_hist(pc, bins, self.lut, idxs, pos, cnt, self.sphere, which=j, n_rots=cfg.num_rots,
+                                       max_samples=cfg.rot_subsample or (1 << 40), offset_seed=seed * 7919 + j,
+                                       thr=self.cos_thr)
+                bests.append(voting.grid_argmax(counts))
+            stats = fast.survivor_stats(pc, nrm, tail, idxs, pos, cnt, self.sphere, bests[0],
+                                        bests[1] if cfg.regress_right else None)
+        rec_dev = torch.cat([flat.double()] + [b.double() for b in bests] + [stats, corner.double()])
+        nd = len(bests)
+        if not sync:
+            return rec_dev, (lambda host: self._pose_from_record(host, nd))
+        out = self._pose_from_record(rec_dev.cpu().numpy(), nd)
+        if return_debug:
+            out.update(grid=grid, bins=bins, tail=tail, mask=mask, pos=pos, count=cnt, feat=feat, idxs=idxs, table=table)
         return out

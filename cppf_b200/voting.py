@@ -115,7 +115,7 @@ def backvote(points, mu_nu, idxs, grid_shape, corner, res, centre, tol, n_rots=7
     return off, mask
 
 
-def compact_pairs(mask, idxs, n_points, want_pos=False):
+def compact_pairs(mask, idxs, n_points, want_pos=False, want_idx=True):
     """point_idxs[mask] (nocs/inference.py:230-231), order preserving, on device.
     -> (idx int32 [P,2] (first `count` rows valid), count int64[1] device, pos | None)."""
     dev = mask.device
@@ -126,12 +126,13 @@ def compact_pairs(mask, idxs, n_points, want_pos=False):
         idxs, is64 = _idx(idxs, dev)
         ip = idxs.data_ptr()
     L = _lib.lib()
-    out = torch.empty((n_pairs, 2), dtype=torch.int32, device=dev)
+    out = torch.empty((n_pairs, 2), dtype=torch.int32, device=dev) if want_idx else None
     pos = torch.empty(n_pairs, dtype=torch.int64, device=dev) if want_pos else None
     cnt = torch.empty(1, dtype=torch.int64, device=dev)
     scratch = torch.empty(int(L.cppf_compact_scratch_bytes(n_pairs)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.cppf_compact_pairs(mask.data_ptr(), ip, is64, int(n_points), n_pairs, out.data_ptr(),
+        _lib.check(L.cppf_compact_pairs(mask.data_ptr(), ip, is64, int(n_points), n_pairs,
+                                        out.data_ptr() if want_idx else None,
                                         pos.data_ptr() if want_pos else None, cnt.data_ptr(), scratch.data_ptr(),
                                         _stream_ptr(dev)), "cppf_compact_pairs")
     return out, cnt, pos

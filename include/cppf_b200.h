@@ -102,7 +102,7 @@ int cppf_backvote(const float* points, const float* mu_nu, float* out_offsets, u
                   int n_rots, int gx, int gy, int gz, const float* centre, float tol, void* stream);
 
 /* replaces point_idxs[mask] (nocs/inference.py:230-231): order-preserving stream
- * compaction of the surviving pairs.  out_idx [<= n_pairs, 2] int32 (a,b); out_pos
+ * compaction of the surviving pairs.  out_idx (optional) [<= n_pairs, 2] int32 (a,b); out_pos
  * (optional) the source pair position; *out_count (int64, device) the survivor count.
  * scratch must hold cppf_compact_scratch_bytes(n_pairs) bytes. */
 int64_t cppf_compact_scratch_bytes(int64_t n_pairs);
@@ -122,6 +122,60 @@ int cppf_sphere_count(const float* cand, int64_t n_cand, const float* sphere, in
  * string as shipped (comma operator at :165-166 drops the x term of the y reads);
  * literal == 0 is the intended 6-neighbour second difference. */
 int cppf_findpeak(const float* grid, float* out, int width, int gx, int gy, int gz, int literal, void* stream);
+
+/* ==== fused per-object path ==================================================
+ * The same reference lines, re-cut so that logits, (mu,nu) floats and the [P,72,3]
+ * candidate dump never reach HBM.  Per pair the path keeps 4 bin bytes and 5 tail floats.
+ *
+ * Decode table `lut` (device, 136 floats): [0:32] mu of each translation bin, [32:64] nu,
+ * [64:100] up angle, [100:136] right angle -- the fp32 values of nocs/inference.py:187-188,
+ * 252,256 computed once on the host.  These entry points are specialised to the reference
+ * head layout out_dim = 2*32 + 2*36 + 2 + 3 (config/config.yaml:7-8). */
+
+int cppf_head_blob_floats(void);
+
+/* models/model.py:117-137 + nocs/inference.py:183-188 + :236-256 in one pass: pair MLP with
+ * the `final` layer evaluated head by head in shared memory, one inverse-CDF categorical
+ * draw per head (uniforms: optional [n_pairs,4] = (mu,nu,up,right); NULL -> Philox4x32-10
+ * keyed by (seed, pair index)).  heads: bit0 mu+nu, bit1 up, bit2 right, bit3 tail.
+ * bins [n_pairs,4] uint8; tail [5, n_pairs] fp32 = (aux_up, aux_right, log-scale x3). */
+int cppf_encode_sample(const float* pc, const float* nrm, const float* table, const float* blob,
+                       const float* head_blob, const void* idx, int idx_is_64, int n_points, int64_t n_pairs,
+                       const float* uniforms, uint64_t seed, int heads, uint8_t* bins, float* tail, void* stream);
+
+/* models/voting.py:8-66 with prob == 1 (nocs/inference.py:201): votes accumulate in a
+ * shared-memory-privatised fixed-point grid (weights rounded to 2^-14, exact integer sums,
+ * deterministic) flushed into `scratch` (cppf_vote_scratch_bytes) and added to `grid`.
+ * Exactly one of mu_nu ([n_pairs,2] fp32) / bins (+lut) is given.  Needs
+ * gx*gy*gz <= cppf_vote_private_max_cells() and n_rots <= 72; cudaErrorInvalidValue otherwise
+ * (use cppf_ppf_vote). */
+int64_t cppf_vote_scratch_bytes(int gx, int gy, int gz);
+int cppf_vote_private_max_cells(void);
+int cppf_vote_fast(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut,
+                   const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
+                   int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, void* stream);
+
+/* models/voting.py:74-112 + nocs/inference.py:207-211,229-230 from bins: the winning cell is
+ * read from device memory (*argmax_flat), centre = corner + cell*res as at :209; out_mask[p] =
+ * any(out_offsets[p] != 0). */
+int cppf_backvote_bins(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                       uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
+                       int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, void* stream);
+
+/* models/voting.py:119-147 + nocs/inference.py:276-284 fused: orientation candidates of a
+ * sub-sample (without replacement, <= max_samples) of the survivors pos[0:*count] are counted
+ * against the sphere bins in shared memory; counts [n_bins] fp32 (exact integers) accumulate
+ * in place.  which: 0 = up head, 1 = right head. */
+int cppf_rot_hist(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                  const int64_t* pos, const int64_t* count, const float* sphere, float* counts, int n_points,
+                  int n_rots, int n_bins, int which, int64_t max_samples, uint64_t offset_seed, float thr,
+                  void* stream);
+
+/* nocs/inference.py:286-302,335 over the survivors: out[0:3] = sum of log-scales, out[3] =
+ * count, out[4] = S_up, out[5] = S_right, S = sum aux*(2t-1); down_loss < up_loss <=> S < 0. */
+int cppf_survivor_stats(const float* points, const float* nrm, const float* tail, const void* idx, int idx_is_64,
+                        const int64_t* pos, const int64_t* count, const float* sphere, const int64_t* best_up,
+                        const int64_t* best_right, double* out, int n_points, int64_t n_pairs, void* stream);
 
 #ifdef __cplusplus
 }

@@ -130,13 +130,17 @@ def sample_bins_race(logits, q):
     return torch.argmax(torch.softmax(logits, -1) / q, -1)
 
 
-def sample_bins_cdf(logits, u):
+def sample_bins_cdf(logits, u, exp2=False):
     """Inverse-CDF categorical draw: same distribution as torch.multinomial, one uniform
     per row.  This is the product kernels' native sampler (cppf_b200/csrc), restated:
     e_k = exp(l_k - max l); pick the first k with cumsum(e)[k] > u * sum(e), computed in
-    fp32 sequentially in bin order; clamp to the last bin."""
+    fp32 sequentially in bin order; clamp to the last bin.  exp2=True restates the fused
+    kernel's form e_k = 2^((l_k - max) * log2 e)."""
     l = logits.float()
-    e = torch.exp(l - l.max(-1, keepdim=True)[0])
+    if exp2:
+        e = torch.exp2((l - l.max(-1, keepdim=True)[0]) * 1.4426950408889634)
+    else:
+        e = torch.exp(l - l.max(-1, keepdim=True)[0])
     tot = torch.zeros(l.shape[0], dtype=torch.float32)
     for k in range(l.shape[1]):
         tot = tot + e[:, k]

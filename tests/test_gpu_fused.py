@@ -1,0 +1,212 @@
+"""GPU parity of the fused per-object path (encode+sample, privatised vote, back-vote from
+bins, fused orientation histogram, survivor statistics) against the oracle and against the
+unfused kernels, which test_gpu_parity.py pins to the reference."""
+import numpy as np
+import pytest
+import torch
+
+from cppf_b200 import fast, model, synth, voting
+from cppf_b200.pipeline import PoseConfig, PoseEstimator
+from oracle import clib, philox, ref_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(a, dt=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV, dt)
+
+
+def _setup(n, seed, out_dim=141):
+    torch.manual_seed(seed)
+    m = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=out_dim).to(DEV).eval()
+    with torch.no_grad():
+        m.final.weight.mul_(6.0)                     # sharper heads than default init: exercises the CDF search
+    pc, nrm = synth.synth_bottle(n, seed)
+    feat = torch.randn(n, 40, generator=torch.Generator().manual_seed(seed))
+    return m, pc, nrm, feat
+
+
+@pytest.mark.parametrize("n,p,seed", [(512, 50000, 0), (777, 4099, 1)])
+def test_encode_sample_matches_oracle(n, p, seed):
+    m, pc, nrm, feat = _setup(n, seed)
+    idxs = synth.sample_pairs(n, p, seed).astype(np.int32)
+    u = torch.rand(p, 4, generator=torch.Generator().manual_seed(seed + 9))
+    with torch.no_grad():
+        table = m.preproject(feat.to(DEV))
+        bins, tail = fast.encode_sample(m, _t(pc), _t(nrm), table, _t(idxs, torch.int32), heads=15, uniforms=u.to(DEV))
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    logits = ref_model.ppf_encode_idx(torch.from_numpy(pc), torch.from_numpy(nrm), feat, idxs, sd)
+    bins = bins.cpu().long()
+    for h, (c0, nb) in enumerate([(0, 32), (32, 32), (64, 36), (100, 36)]):
+        ref = ref_model.sample_bins_cdf(logits[:, c0:c0 + nb], u[:, h], exp2=True)
+        mism = int((bins[:, h] != ref).sum())
+        assert mism <= max(2, p // 5000), f"head {h}: {mism} of {p} draws differ"     # fp32 ulp at a CDF edge
+        assert int((bins[:, h] - ref).abs().max()) <= 1
+    np.testing.assert_allclose(tail.cpu().numpy().T, logits[:, 136:].numpy(), rtol=1e-4, atol=2e-5)
+
+
+def test_encode_sample_dense_philox_and_head_mask():
+    n = 96
+    m, pc, nrm, feat = _setup(n, 4)
+    with torch.no_grad():
+        table = m.preproject(feat.to(DEV))
+        b_seed, t_seed = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, seed=1234567890123)
+        u = philox.pair_uniforms(1234567890123, n * n)
+        b_inj, t_inj = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, uniforms=_t(u))
+        b_idx, _ = fast.encode_sample(m, _t(pc), _t(nrm), table, _t(synth.dense_pairs(n), torch.int64), heads=15,
+                                      uniforms=_t(u))
+        b_tr, none_tail = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=fast.HEAD_TR, uniforms=_t(u))
+    assert torch.equal(b_seed, b_inj) and torch.equal(t_seed, t_inj)       # kernel Philox == oracle Philox
+    assert torch.equal(b_idx, b_inj)                                        # dense enumeration == explicit list
+    assert none_tail is None and torch.equal(b_tr[:, :2], b_inj[:, :2]) and not b_tr[:, 2:].any()
+
+
+def _vote_case(n, p, seed, dense=False):
+    cfg = synth.BOTTLE
+    pc, _ = synth.synth_bottle(n, seed)
+    idxs = synth.dense_pairs(n) if dense else synth.sample_pairs(n, p, seed)
+    tr = synth.trained_like_tr(pc, idxs)
+    corner, dims = synth.vote_grid_geometry(pc, cfg["res"])
+    return cfg, pc, idxs, tr, corner, dims
+
+
+@pytest.mark.parametrize("adaptive", [True, False])
+def test_vote_fast_matches_oracle_and_is_deterministic(adaptive):
+    cfg, pc, idxs, tr, corner, dims = _vote_case(1024, 200000, 3)
+    ref = clib.ppf_voting(pc, tr, np.ones(len(pc), np.float32), idxs.astype(np.int32), dims, corner, cfg["res"], 72,
+                          adaptive, f64=True)
+    grids = []
+    for _ in range(2):
+        g = torch.zeros(dims, device=DEV)
+        fast.vote_fast(_t(pc), _t(idxs, torch.int32), g, _t(corner), cfg["res"], mu_nu=_t(tr), adaptive=adaptive)
+        grids.append(g)
+    assert torch.equal(grids[0], grids[1])                                  # integer accumulation: run-to-run identical
+    got = grids[0].cpu().numpy()
+    # weights are rounded to 2^-14 per corner: |err| <= 2^-15 * contributions
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=5e-3)
+    assert int(voting.grid_argmax(grids[0]).item()) == int(np.argmax(ref))
+    slow = torch.zeros(dims, device=DEV)
+    voting.ppf_vote(_t(pc), _t(tr), _t(idxs, torch.int32), slow, _t(corner), cfg["res"], 72, adaptive)
+    assert int(voting.grid_argmax(slow).item()) == int(np.argmax(ref))
+    assert abs(float(got.sum()) - float(ref.sum())) / float(ref.sum()) < 1e-5
+
+
+def test_vote_fast_from_bins_dense_and_overflow_flush():
+    cfg, pc, idxs, tr, corner, dims = _vote_case(600, 0, 5, dense=True)      # 360k pairs
+    lut = fast.decode_lut(cfg["vote_range"])
+    b_mu = torch.argmin((torch.from_numpy(tr[:, 0:1]) - lut[None, :32]).abs(), -1)
+    b_nu = torch.argmin((torch.from_numpy(tr[:, 1:2]) - lut[None, 32:64]).abs(), -1)
+    bins = torch.stack([b_mu, b_nu, torch.zeros_like(b_mu), torch.zeros_like(b_mu)], -1).to(torch.uint8)
+    mu_nu = torch.stack([lut[b_mu], lut[32 + b_nu]], -1)
+    np.testing.assert_array_equal(mu_nu.numpy(), tr)                         # lut reproduces nocs/inference.py:187-188
+    g_bins = torch.zeros(dims, device=DEV)
+    fast.vote_fast(_t(pc), None, g_bins, _t(corner), cfg["res"], bins=bins.to(DEV), lut=lut.to(DEV))
+    g_mn = torch.zeros(dims, device=DEV)
+    fast.vote_fast(_t(pc), _t(idxs, torch.int64), g_mn, _t(corner), cfg["res"], mu_nu=mu_nu.to(DEV))
+    assert torch.equal(g_bins, g_mn)
+    ref = clib.ppf_voting(pc, tr, np.ones(len(pc), np.float32), idxs.astype(np.int32), dims, corner, cfg["res"], 72, True,
+                          f64=True)
+    np.testing.assert_allclose(g_bins.cpu().numpy(), ref, rtol=1e-4, atol=5e-3)
+    assert int(voting.grid_argmax(g_bins).item()) == int(np.argmax(ref))
+    # adversarial overflow case: every pair's 72 non-adaptive candidates fall into one cell
+    n = 64
+    pts = np.zeros((n, 3), np.float32)
+    pts[:, 0] = np.linspace(0.02, 0.021, n)
+    pts[0] = (0, 0, 0); pts[1] = (0.04, 0.04, 0.04)
+    p = 3_000_000
+    idx = np.stack([np.full(p, 10), np.full(p, 20)], -1).astype(np.int32)
+    mn = np.tile(np.array([[0.0, 1e-6]], np.float32), (p, 1))
+    cor, dm = synth.vote_grid_geometry(pts, 4e-3)
+    g = torch.zeros(dm, device=DEV)
+    fast.vote_fast(_t(pts), _t(idx, torch.int32), g, _t(cor), 4e-3, mu_nu=_t(mn), adaptive=False)
+    assert abs(float(g.sum().item()) - 72.0 * p) / (72.0 * p) < 1e-4          # 2.2e8 votes, far beyond one u32 cell
+
+
+def test_backvote_bins_matches_oracle():
+    cfg, pc, idxs, tr, corner, dims = _vote_case(512, 30000, 6)
+    lut = fast.decode_lut(cfg["vote_range"])
+    b_mu = torch.argmin((torch.from_numpy(tr[:, 0:1]) - lut[None, :32]).abs(), -1)
+    b_nu = torch.argmin((torch.from_numpy(tr[:, 1:2]) - lut[None, 32:64]).abs(), -1)
+    bins = torch.stack([b_mu, b_nu, b_mu * 0, b_mu * 0], -1).to(torch.uint8).to(DEV)
+    grid = torch.zeros(dims, device=DEV)
+    fast.vote_fast(_t(pc), _t(idxs, torch.int32), grid, _t(corner), cfg["res"], bins=bins, lut=lut.to(DEV))
+    flat = voting.grid_argmax(grid)
+    mask = fast.backvote_bins(_t(pc), bins, lut.to(DEV), _t(idxs, torch.int32), dims, _t(corner), flat, cfg["res"],
+                              3 * cfg["res"])
+    _, centre = ref_model.centre_from_grid(grid.cpu().numpy(), corner, cfg["res"])
+    ref = clib.backvote(pc, tr, idxs.astype(np.int32), dims, corner, cfg["res"], centre.astype(np.float32), 3 * cfg["res"])
+    agree = (mask.cpu().numpy().astype(bool) == np.any(ref != 0, -1)).mean()
+    assert agree > 0.999
+
+
+def test_rot_hist_equals_unfused_and_stats_match_numpy():
+    n, p = 400, 6000
+    cfg = synth.BOTTLE
+    pc, nrm = synth.synth_bottle(n, 7)
+    idxs = synth.sample_pairs(n, p, 7).astype(np.int32)
+    rng = np.random.default_rng(7)
+    bins = torch.from_numpy(rng.integers(0, 32, (p, 4)).astype(np.uint8)).to(DEV)
+    lut = fast.decode_lut(cfg["vote_range"]).to(DEV)
+    mask = torch.from_numpy((rng.random(p) < 0.6).astype(np.uint8)).to(DEV)
+    mask[:5] = 1
+    idxs[:5, 1] = idxs[:5, 0]                                                 # degenerate survivors
+    kept, cnt, pos = voting.compact_pairs(mask, _t(idxs, torch.int32), n, want_pos=True)
+    c = int(cnt.item())
+    sphere = torch.from_numpy(ref_model.fibonacci_sphere(480).astype(np.float32)).to(DEV)
+    thr = float(np.float32(np.cos(1.5 / 180 * np.pi)))
+    for which in (0, 1):
+        counts = fast.rot_hist(_t(pc), bins, lut, _t(idxs, torch.int32), pos, cnt, sphere, which=which, max_samples=p, thr=thr)
+        rot = lut[(64 if which == 0 else 100) + bins[pos[:c], 2 + which].long()]
+        cand = voting.rot_vote(_t(pc), rot.contiguous(), kept[:c].contiguous(), 72)
+        ref = voting.sphere_count(cand, sphere, thr)
+        assert torch.equal(counts.int(), ref)
+        # sub-sample: without replacement, exactly max_samples pairs
+        sub = fast.rot_hist(_t(pc), bins, lut, _t(idxs, torch.int32), pos, cnt, sphere, which=which, max_samples=1000,
+                            offset_seed=5, thr=thr)
+        assert 0 < float(sub.sum()) < float(counts.sum())
+    tail = torch.randn(5, p, generator=torch.Generator().manual_seed(1)).to(DEV)
+    best_up = torch.tensor([17], device=DEV)
+    best_right = torch.tensor([333], device=DEV)
+    st = fast.survivor_stats(_t(pc), _t(nrm), tail, _t(idxs, torch.int32), pos, cnt, sphere, best_up, best_right).cpu().numpy()
+    sel = pos[:c].cpu().numpy()
+    tl = tail.cpu().numpy()
+    assert st[3] == c
+    np.testing.assert_allclose(st[:3], tl[2:5, sel].sum(1), rtol=1e-6, atol=1e-4)
+    sph = sphere.cpu().numpy()
+    ab = pc[idxs[sel, 0]] - pc[idxs[sel, 1]]
+    abn = ab / (np.sqrt((ab ** 2).sum(-1)) + np.float32(1e-7))[:, None]
+    pn = nrm[idxs[sel, 0]].copy()
+    pn[(pn * abn).sum(-1) < 0] *= -1
+    for k, b in ((4, 17), (5, 333)):
+        t = np.where((pn * sph[b]).sum(-1) > 0, 1.0, -1.0)
+        np.testing.assert_allclose(st[k], (tl[k - 4, sel] * t).sum(), rtol=1e-5, atol=1e-3)
+        # the sign rule equals the reference's BCE comparison (nocs/inference.py:295-302)
+        _, up_l, down_l = ref_model.aux_sign(pc, nrm, idxs[sel], sph[b].astype(np.float64), tl[k - 4, sel])
+        assert (st[k] < 0) == (down_l < up_l)
+
+
+@pytest.mark.parametrize("regress_right", [False, True])
+def test_fused_pipeline_equals_two_pass_pipeline(regress_right):
+    torch.manual_seed(0)
+    pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(DEV).eval()
+    ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).to(DEV).eval()
+    cfg = PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=30000, rot_subsample=0, regress_right=regress_right))
+    est = PoseEstimator(pe, ppf, cfg, DEV)
+    n = 700
+    pc, nrm = synth.synth_bottle(n, 11)
+    idxs = synth.sample_pairs(n, cfg.n_pairs, 11).astype(np.int32)
+    u = torch.rand(cfg.n_pairs, 4, generator=torch.Generator().manual_seed(2)).to(DEV)
+    fused = est.estimate_fused(pc, nrm, seed=0, idxs=idxs, uniforms=u, return_debug=True)
+    # two-pass path with the same draws: survivors' rotation uniforms are the rows of u they came from
+    two = est.estimate(pc, nrm, seed=0, idxs=idxs, noise={"u_mu": u[:, 0].contiguous(), "u_nu": u[:, 1].contiguous()},
+                       return_debug=True)
+    assert fused["argmax_flat"] == int(two["argmax"].item())
+    np.testing.assert_allclose(fused["T_host"], two["T_host"], rtol=0, atol=1e-9)
+    assert abs(fused["n_survivors"] - two["n_survivors"]) <= 3
+    np.testing.assert_allclose(fused["pred_scale"], two["pred_scale"], rtol=1e-3)
+    # fused vote grid vs the float-reduction grid of the two-pass path: identical up to the 2^-14 weight rounding,
+    # except where one of the 60k draws fell on a CDF edge (exp2f vs expf) and moved a whole circle of votes
+    diff = np.abs(fused["grid"].cpu().numpy() - two["grid"].cpu().numpy())
+    assert (diff > 5e-3).mean() < 0.05
+    assert np.isfinite(fused["RT"]).all() and abs(np.linalg.norm(fused["up"]) - 1) < 1e-6
