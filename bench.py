@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--n-points", type=int, default=4096)
     ap.add_argument("--cpu-sample-pairs", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--votes", default="trained_like", choices=["trained_like", "network"],
+                    help="trained_like: after sampling, the (mu,nu,up) bins are replaced by the geometric targets a trained "
+                         "network would emit (SURVEY.md 8d i) so that voting runs under a realistic load; network: votes "
+                         "come from the random-init network's own samples (cheap: most candidates fall outside the grid)")
     ap.add_argument("--path", default="fused", choices=["fused", "twopass"],
                     help="fused: encode+sample / privatised vote kernels; twopass: materialised logits like the reference")
     return ap.parse_args()
@@ -56,7 +60,8 @@ def workload_config(args):
                         "bottle constants (res 4e-3, 32 tr bins, 36 rot bins, 72 rots, adaptive), 1 object/rank/step",
             "n_points": args.n_points, "pairs_per_object": args.n_points ** 2, "objects_per_step_per_rank": 1,
             "out_dim": 141, "parallelism": f"objects sharded over {args.gpus} rank(s), one NCCL all_gather of pose records",
-            "path": args.path,
+            "path": args.path, "votes": args.votes,
+            "weights": "torch.manual_seed(0) default init of the reference architecture (no checkpoints exist offline)",
             "l2_policy": "per-step working set (bins + tail logits of 16.7M pairs = 403 MB, + 134 MB survivor list) exceeds the "
                          "126 MB L2; each step is a different cloud"}
 
@@ -219,13 +224,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(leg):
+    inject = [None] * n_obj
+    if args.votes == "trained_like" and args.path == "fused":
+        inject = [synth.trained_like_bins_dense_torch(torch.from_numpy(p).to(dev), synth.BOTTLE) for p, _ in clouds]
+
+    def run(leg, votes_injected=True):
         """leg 'hbm': clouds already on the device; leg 'e2e': pinned host buffers in, pose record out."""
         records = []
         resident = [(p.to(dev), q.to(dev)) for p, q in pinned] if leg == "hbm" else None
         timers = {}
         est.timers = timers
-        step = est.estimate_fused if args.path == "fused" else est.estimate
+        if args.path == "fused":
+            step = lambda a, b, seed: est.estimate_fused(a, b, seed=seed, inject_bins=inject[seed] if votes_injected else None)
+        else:
+            step = lambda a, b, seed: est.estimate(a, b, seed=seed)
         for s in range(args.warmup):
             src = resident[s] if leg == "hbm" else pinned[s]
             step(src[0], src[1], seed=s)
@@ -255,6 +267,9 @@ def main():
 
     ms_hbm, launches, clocks, timers = run("hbm")
     ms_e2e, _, _, _ = run("e2e")
+    ms_net = None
+    if args.votes == "trained_like" and args.path == "fused":
+        ms_net, _, _, _ = run("hbm", votes_injected=False)
     total_pairs = world * args.steps * pairs_per_obj
     value = total_pairs / (ms_hbm * 1e-3)
     e2e = total_pairs / (ms_e2e * 1e-3)
@@ -300,6 +315,10 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "objects_per_sec": world * args.steps / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu}
+        if ms_net is not None:
+            line["variant_network_votes"] = {"value": total_pairs / (ms_net * 1e-3), "unit": UNIT,
+                                             "ms_per_step": ms_net / args.steps,
+                                             "note": "no bin injection: votes from the random-init network's own samples"}
         print(json.dumps(line))
     if dist_on:
         dist.destroy_process_group()

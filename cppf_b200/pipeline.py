@@ -250,7 +250,7 @@ class PoseEstimator:
 
     @torch.no_grad()
     def estimate_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, return_debug: bool = False,
-                       sync: bool = True):
+                       sync: bool = True, inject_bins=None):
         """Same pose as `estimate`, through the fused kernels: logits, (mu,nu) floats and rotation
         candidates never reach HBM; a single ~100-byte record comes back to the host.
         With sync=False returns the device record (torch tensor) and a finisher callable."""
@@ -276,6 +276,8 @@ class PoseEstimator:
         heads = fast.HEAD_TR | fast.HEAD_UP | fast.HEAD_TAIL | (fast.HEAD_RIGHT if cfg.regress_right else 0)
         with self._timed("encode_sample"):
             bins, tail = fast.encode_sample(self.ppf, pc, nrm, table, idxs, heads=heads, uniforms=uniforms, seed=seed)
+        if inject_bins is not None:           # benchmark aid: vote load of a trained network (SURVEY.md 8d i)
+            bins[:, :inject_bins.shape[1]] = inject_bins
         grid = torch.zeros(dims, dtype=torch.float32, device=dev)
         with self._timed("vote"):
             if fast.vote_fits_private(dims) and cfg.num_rots <= 72:

@@ -87,3 +87,29 @@ def trained_like_rot(pc: np.ndarray, idxs: np.ndarray, rot_num_bins: int = 36, u
         ang = np.minimum(ang, np.pi - ang)
     b = np.clip(np.rint(ang / np.pi * (rot_num_bins - 1)), 0, rot_num_bins - 1)
     return (b.astype(np.float32) / np.float32(rot_num_bins - 1) * np.float32(np.pi)).astype(np.float32)
+
+
+def trained_like_bins_dense_torch(pc, cfg, chunk_rows: int = 256):
+    """Device-side version of trained_like_tr / trained_like_rot for ALL ordered pairs of a cloud
+    (row-major): uint8 [N*N, 3] = (mu bin, nu bin, up bin).  Used to give the vote stage the load
+    a trained network would produce (SURVEY.md section 8d i) when only random-init weights exist."""
+    import torch
+    n = pc.shape[0]
+    tb, rb = cfg["tr_num_bins"], cfg["rot_num_bins"]
+    vr0, vr1 = cfg["vote_range"]
+    out = torch.empty((n * n, 3), dtype=torch.uint8, device=pc.device)
+    pcd = pc.double()
+    for r0 in range(0, n, chunk_rows):
+        a = pcd[r0:r0 + chunk_rows, None, :]
+        d = a - pcd[None, :, :]
+        du = d / (d.norm(dim=-1, keepdim=True) + 1e-7)
+        mu = (a * du).sum(-1)
+        nu = (a - mu[..., None] * du).norm(dim=-1)
+        ang = torch.arccos(du[..., 1].clamp(-1, 1))
+        if cfg["up_sym"]:
+            ang = torch.minimum(ang, np.pi - ang)
+        b = torch.stack([((mu + vr0) / (2 * vr0) * (tb - 1)).round().clamp(0, tb - 1),
+                         (nu / vr1 * (tb - 1)).round().clamp(0, tb - 1),
+                         (ang / np.pi * (rb - 1)).round().clamp(0, rb - 1)], -1)
+        out[r0 * n:(r0 + a.shape[0]) * n] = b.reshape(-1, 3).to(torch.uint8)
+    return out

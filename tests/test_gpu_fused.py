@@ -112,7 +112,8 @@ def test_vote_fast_from_bins_dense_and_overflow_flush():
     # adversarial overflow case: every pair's 72 non-adaptive candidates fall into one cell
     n = 64
     pts = np.zeros((n, 3), np.float32)
-    pts[:, 0] = np.linspace(0.02, 0.021, n)
+    pts[:] = (0.02, 0.02, 0.02)
+    pts[:, 0] += np.linspace(0.0, 0.008, n)
     pts[0] = (0, 0, 0); pts[1] = (0.04, 0.04, 0.04)
     p = 3_000_000
     idx = np.stack([np.full(p, 10), np.full(p, 20)], -1).astype(np.int32)
