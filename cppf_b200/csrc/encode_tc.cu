@@ -1,0 +1,451 @@
+// Pair encoder + categorical sampling on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Same contract as encode_sample_kernel (fused.cu): for every pair the PPF tuple, the ResLayer
+// stack of models/model.py:117-137 and the `final` layer are evaluated on chip, one categorical
+// draw per head is taken (nocs/inference.py:183-188, 245-256) and only 4 bin bytes + 5 tail
+// logits per pair reach HBM.  Here the dense layers are true GEMMs on the tensor pipe:
+//
+//   * a tile is 128 pairs = the M dimension of one tcgen05.mma (cta_group::1, M = 128);
+//     thread t of a 128-thread group owns pair (row) t = TMEM lane t for the whole chain, so
+//     residuals and biases stay in that thread's registers and no activation ever crosses threads;
+//   * every layer is  D[128 x N] (TMEM, fp32) = A[128 x K] (smem) . W[N x K]^T (smem)  in 3xTF32:
+//     operands are split into a tf32 `hi` part and the fp32 remainder `lo`, and
+//     lo.hi + hi.lo + hi.hi is accumulated in TMEM -- fp32-grade logits (|err| ~ 2^-21 per product)
+//     from a 10-bit-mantissa pipe, which is what the 1e-4 parity tolerance needs;
+//   * operands use the no-swizzle K-major canonical layout: element (row r, k) of a [rows x K]
+//     operand sits at byte  (k/4) * rows*16 + r*16 + (k%4)*4 , i.e. one 16-byte chunk per row per
+//     "K plane"; a thread writes its own row with conflict-free 128-bit stores;
+//   * ResLayer 0 (84 -> 32) never sees the 80 feature columns: their products are pre-projected
+//     per point (cppf_ppf_preproject) and gathered; only the 4 PPF columns go through a K = 8 MMA;
+//   * a CTA holds 4 independent 128-thread groups (4 tiles in flight per SM) sharing one copy of
+//     the weights; each group has its own A buffers, mbarrier and 128 TMEM columns, and its own
+//     elected MMA-issuing thread, so one group's SIMT epilogue overlaps the others' MMAs.
+#include "common.cuh"
+
+#include "../../include/cppf_b200.h"
+
+namespace cppf {
+namespace tc {
+
+constexpr int kGroups = 4;
+constexpr int kTile = 128;
+constexpr int kThreads = kGroups * kTile;
+
+// ---- packed weight blob (floats); every matrix is [K/4][N][4] (canonical K-major), hi block then lo block
+constexpr int kOffWppf = 0;                       // N = 64, K = 8 (k 4..7 zero): [fc1_0 | fc0_0] PPF columns
+constexpr int kOffW2_0 = kOffWppf + 2 * 512;      // N = 32, K = 32
+constexpr int kOffW1_1 = kOffW2_0 + 2 * 1024;
+constexpr int kOffW2_1 = kOffW1_1 + 2 * 1024;
+constexpr int kOffW10_2 = kOffW2_1 + 2 * 1024;    // rows 0:16 fc1_2, 16:32 fc0_2
+constexpr int kOffW2_2 = kOffW10_2 + 2 * 1024;    // N = 16, K = 16
+constexpr int kOffHB1 = kOffW2_2 + 2 * 256;       // N = 64, K = 16: [mu 32 | nu 32]
+constexpr int kOffHB2 = kOffHB1 + 2 * 1024;       // N = 48, K = 16: [up 36 | tail 5 | 0 x 7]
+constexpr int kOffHB3 = kOffHB2 + 2 * 768;        // N = 48, K = 16: [right 36 | 0 x 12]
+constexpr int kOffBias = kOffHB3 + 2 * 768;       // b1_1 32 | b2_1 32 | b10_2 32 | bh1 64 | bh2 48 | bh3 48
+constexpr int kBlobFloats = kOffBias + 256;
+constexpr int kBiasB1_1 = 0, kBiasB2_1 = 32, kBiasB10_2 = 64, kBiasH1 = 96, kBiasH2 = 160, kBiasH3 = 208;
+
+constexpr int kAPlane = kTile * 16;               // bytes of one K plane of an A operand
+constexpr int kABytes = 8 * kAPlane;              // K = 32
+constexpr int kGroupBytes = 2 * kABytes;          // hi + lo
+constexpr int kSmemBytes = kBlobFloats * 4 + kGroups * kGroupBytes;
+constexpr int kTmemColsPerGroup = 128;
+
+struct Params {
+    const float* pc;
+    const float* nrm;
+    const float* table;
+    const float* blob;
+    const void* idx;
+    const float* uniforms;
+    unsigned long long seed;
+    uint8_t* bins;
+    float* tail;
+    float* dbg_x3;              // optional [n_pairs][16]: output of the third ResLayer
+    int n_points;
+    long long n_pairs;
+    int heads;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle, K-major: LBO = byte stride between K planes,
+// SBO = byte stride between 8-row groups (= 128: rows are contiguous 16-byte chunks)
+__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, uint32_t lbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// D[128 x N] = A . B^T in 3xTF32: lo.hi + hi.lo + hi.hi (small terms first)
+template <int N, int K>
+__device__ __forceinline__ void issue3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi) {
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+    constexpr uint32_t bplane = N * 16;
+    constexpr uint32_t b_lo_off = N * K * 4;
+#pragma unroll
+    for (int ps = 0; ps < 3; ++ps) {
+        const uint32_t a = ps == 0 ? a_lo : a_hi;
+        const uint32_t b = ps == 1 ? b_hi + b_lo_off : b_hi;
+#pragma unroll
+        for (int j = 0; j < K / 8; ++j)
+            mma_tf32(tmem_d, kdesc(a + j * 2 * kAPlane, kAPlane), kdesc(b + j * 2 * bplane, bplane), idesc,
+                     (ps | j) != 0 ? 1u : 0u);
+    }
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+// TMEM -> registers: this thread's lane, consecutive columns (load + wait in one statement so no
+// use of the destination registers can be scheduled before the wait)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// this thread's row, K chunk c (4 consecutive k) -> hi / lo planes
+__device__ __forceinline__ void st_chunk(unsigned char* a_hi, int c, int row, float x0, float x1, float x2, float x3) {
+    const float h0 = tf32_hi(x0), h1 = tf32_hi(x1), h2 = tf32_hi(x2), h3 = tf32_hi(x3);
+    *reinterpret_cast<float4*>(a_hi + c * kAPlane + row * 16) = make_float4(h0, h1, h2, h3);
+    *reinterpret_cast<float4*>(a_hi + kABytes + c * kAPlane + row * 16) = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
+}
+
+// One categorical draw from NB logits in registers: e_k = 2^((l_k - max) log2 e);
+// bin = #{k : cumsum(e)_k <= u * sum(e)}, clamped (same operation order as fused.cu / the oracle).
+template <int NB>
+__device__ __forceinline__ int sample_regs(float (&l)[NB], float u) {
+    float m = l[0];
+#pragma unroll
+    for (int k = 1; k < NB; ++k) m = fmaxf(m, l[k]);
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        l[k] = exp2f((l[k] - m) * 1.4426950408889634f);
+        tot += l[k];
+    }
+    const float t = u * tot;
+    float acc = 0.f;
+    int bin = 0;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        acc += l[k];
+        bin += acc <= t ? 1 : 0;
+    }
+    return bin < NB - 1 ? bin : NB - 1;
+}
+
+__device__ __forceinline__ void ppf_of(f3 pa, f3 pb, f3 na, f3 nb, float (&ppf)[4]) {   // models/model.py:120-129
+    const f3 d = pa - pb;
+    const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    const float inv = dn + 1e-7f;
+    const f3 dh = {d.x / inv, d.y / inv, d.z / inv};
+    ppf[0] = na.x * dh.x + na.y * dh.y + na.z * dh.z;
+    ppf[1] = nb.x * dh.x + nb.y * dh.y + nb.z * dh.z;
+    ppf[2] = na.x * nb.x + na.y * nb.y + na.z * nb.z;
+    ppf[3] = dn;
+}
+
+template <bool IDX64>
+__global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Params prm) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar[kGroups];
+    __shared__ uint32_t s_tmem;
+    float* sblob = reinterpret_cast<float*>(smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int g = tid >> 7, tg = tid & 127;             // group, row within the tile
+    unsigned char* a_hi = smem + kBlobFloats * 4 + g * kGroupBytes;
+
+    {   // weights -> shared memory (one copy per CTA), TMEM allocation, barriers
+        const float4* src = reinterpret_cast<const float4*>(prm.blob);
+        float4* dst = reinterpret_cast<float4*>(sblob);
+        for (int i = tid; i < kBlobFloats / 4; i += kThreads) dst[i] = __ldg(src + i);
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                         "r"(kGroups * kTmemColsPerGroup)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        if (tid < kGroups) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[tid])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const uint32_t tm = s_tmem + g * kTmemColsPerGroup;                    // MMA destination (lane 0, column base)
+    const uint32_t tml = tm + ((uint32_t)((warp & 3) * 32) << 16);         // this warp's lane quarter for tcgen05.ld
+    const uint32_t bar = smem_u32(&s_bar[g]);
+    const uint32_t sA = smem_u32(a_hi), sAl = sA + kABytes;
+    const uint32_t sW = smem_u32(sblob);
+    const float4* sbias = reinterpret_cast<const float4*>(sblob + kOffBias);
+    const bool leader = tg == 0;
+    uint32_t phase = 0;
+
+// publish this group's A operand, let the leader issue `ISSUE`, wait until the accumulators are complete
+#define CPPF_TC_STEP(ISSUE)                                                                                 \
+    do {                                                                                                    \
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                        \
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                    \
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");                                          \
+        if (leader) {                                                                                       \
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                 \
+            ISSUE;                                                                                          \
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) \
+                         : "memory");                                                                       \
+        }                                                                                                   \
+        __syncwarp();                                                                                       \
+        mbar_wait(bar, phase);                                                                              \
+        phase ^= 1u;                                                                                        \
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                     \
+    } while (0)
+
+    const long long n_tiles = (prm.n_pairs + kTile - 1) / kTile;
+    for (long long tile = (long long)blockIdx.x * kGroups + g; tile < n_tiles; tile += (long long)gridDim.x * kGroups) {
+        const long long p = tile * kTile + tg;
+        const bool valid = p < prm.n_pairs;
+        int a = 0, b = 0;
+        if (valid) pair_ab<IDX64>(prm.idx, p, prm.n_points, a, b);
+        float ppf[4];
+        ppf_of(ld3(prm.pc, a), ld3(prm.pc, b), ld3(prm.nrm, a), ld3(prm.nrm, b), ppf);
+        float4 u4;
+        if (prm.uniforms != nullptr) {
+            u4 = valid ? __ldg(reinterpret_cast<const float4*>(prm.uniforms) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const uint4 w = philox4x32_10(make_uint4((uint32_t)p, (uint32_t)((unsigned long long)p >> 32), 0u, 0u),
+                                          make_uint2((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32)));
+            u4 = make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
+        }
+        const float4* TA = reinterpret_cast<const float4*>(prm.table + (long long)a * 128);
+        const float4* TB = reinterpret_cast<const float4*>(prm.table + (long long)b * 128 + 64);
+
+        // ---- ResLayer 0 front end: [fc1_0 | fc0_0](x) = TA[a] + TB[b] + ppf . Wppf  (K = 8 MMA, N = 64)
+        st_chunk(a_hi, 0, tg, ppf[0], ppf[1], ppf[2], ppf[3]);
+        st_chunk(a_hi, 1, tg, 0.f, 0.f, 0.f, 0.f);
+        float R[32];
+        {
+            float4 ta[8], tb[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                ta[q] = __ldg(TA + q);
+                tb[q] = __ldg(TB + q);
+            }
+            CPPF_TC_STEP((issue3<64, 8>(tm, sA, sAl, sW + kOffWppf * 4)));
+            float acc[32];
+            tmem_ld32(tml, acc);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)       // h = relu(fc1_0(x))                       models/model.py:27,29
+                st_chunk(a_hi, q, tg, fmaxf(ta[q].x + tb[q].x + acc[4 * q], 0.f), fmaxf(ta[q].y + tb[q].y + acc[4 * q + 1], 0.f),
+                         fmaxf(ta[q].z + tb[q].z + acc[4 * q + 2], 0.f), fmaxf(ta[q].w + tb[q].w + acc[4 * q + 3], 0.f));
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {     // r = fc0_0(x) + fc2_0.b  (second half of the table row)
+                ta[q] = __ldg(TA + 8 + q);
+                tb[q] = __ldg(TB + 8 + q);
+            }
+            CPPF_TC_STEP((issue3<32, 32>(tm + 64, sA, sAl, sW + kOffW2_0 * 4)));
+            tmem_ld32(tml + 32, R);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                R[4 * q] += ta[q].x + tb[q].x;
+                R[4 * q + 1] += ta[q].y + tb[q].y;
+                R[4 * q + 2] += ta[q].z + tb[q].z;
+                R[4 * q + 3] += ta[q].w + tb[q].w;
+            }
+        }
+        float x[32];
+        // ---- x1 = fc2_0(h) + r                                                          models/model.py:30-31
+        tmem_ld32(tml + 64, x);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) R[i] += x[i];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st_chunk(a_hi, q, tg, R[4 * q], R[4 * q + 1], R[4 * q + 2], R[4 * q + 3]);
+        // ---- u = relu(fc1_1(x1))
+        CPPF_TC_STEP((issue3<32, 32>(tm, sA, sAl, sW + kOffW1_1 * 4)));
+        tmem_ld32(tml, x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 bq = sbias[kBiasB1_1 / 4 + q];
+            st_chunk(a_hi, q, tg, fmaxf(x[4 * q] + bq.x, 0.f), fmaxf(x[4 * q + 1] + bq.y, 0.f), fmaxf(x[4 * q + 2] + bq.z, 0.f),
+                     fmaxf(x[4 * q + 3] + bq.w, 0.f));
+        }
+        // ---- x2 = fc2_1(u) + x1   (identity skip)
+        CPPF_TC_STEP((issue3<32, 32>(tm, sA, sAl, sW + kOffW2_1 * 4)));
+        tmem_ld32(tml, x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 bq = sbias[kBiasB2_1 / 4 + q];
+            R[4 * q] += x[4 * q] + bq.x;
+            R[4 * q + 1] += x[4 * q + 1] + bq.y;
+            R[4 * q + 2] += x[4 * q + 2] + bq.z;
+            R[4 * q + 3] += x[4 * q + 3] + bq.w;
+            st_chunk(a_hi, q, tg, R[4 * q], R[4 * q + 1], R[4 * q + 2], R[4 * q + 3]);
+        }
+        // ---- [u ; r] = [relu(fc1_2(x2)) ; fc0_2(x2) + fc2_2.b]
+        CPPF_TC_STEP((issue3<32, 32>(tm, sA, sAl, sW + kOffW10_2 * 4)));
+        tmem_ld32(tml, x);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 bq = sbias[kBiasB10_2 / 4 + q];
+            st_chunk(a_hi, q, tg, fmaxf(x[4 * q] + bq.x, 0.f), fmaxf(x[4 * q + 1] + bq.y, 0.f), fmaxf(x[4 * q + 2] + bq.z, 0.f),
+                     fmaxf(x[4 * q + 3] + bq.w, 0.f));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 bq = sbias[kBiasB10_2 / 4 + 4 + q];
+            R[4 * q] = x[16 + 4 * q] + bq.x;
+            R[4 * q + 1] = x[16 + 4 * q + 1] + bq.y;
+            R[4 * q + 2] = x[16 + 4 * q + 2] + bq.z;
+            R[4 * q + 3] = x[16 + 4 * q + 3] + bq.w;
+        }
+        // ---- x3 = fc2_2(u) + r
+        CPPF_TC_STEP((issue3<16, 16>(tm, sA, sAl, sW + kOffW2_2 * 4)));
+        {
+            float y[16];
+            tmem_ld16(tml, y);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] += R[i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st_chunk(a_hi, q, tg, y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+            if (prm.dbg_x3 != nullptr && valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    reinterpret_cast<float4*>(prm.dbg_x3 + p * 16)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+            }
+        }
+        // ---- `final`, head by head (models/model.py:137): [mu | nu] -> columns 0:64, [up | tail] -> 64:112
+        CPPF_TC_STEP((issue3<64, 16>(tm, sA, sAl, sW + kOffHB1 * 4), issue3<48, 16>(tm + 64, sA, sAl, sW + kOffHB2 * 4)));
+        uchar4 bins = make_uchar4(0, 0, 0, 0);
+        if (prm.heads & 1) {
+            tmem_ld32(tml, x);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 bq = sbias[kBiasH1 / 4 + q];
+                x[4 * q] += bq.x; x[4 * q + 1] += bq.y; x[4 * q + 2] += bq.z; x[4 * q + 3] += bq.w;
+            }
+            bins.x = (unsigned char)sample_regs<32>(x, u4.x);
+            tmem_ld32(tml + 32, x);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 bq = sbias[kBiasH1 / 4 + 8 + q];
+                x[4 * q] += bq.x; x[4 * q + 1] += bq.y; x[4 * q + 2] += bq.z; x[4 * q + 3] += bq.w;
+            }
+            bins.y = (unsigned char)sample_regs<32>(x, u4.y);
+        }
+        if (prm.heads & (2 | 8)) {
+            float y[16];                       // columns 96..111: up bins 32..35, tail 0..4, padding
+            tmem_ld16(tml + 96, y);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 bq = sbias[kBiasH2 / 4 + 8 + q];
+                y[4 * q] += bq.x; y[4 * q + 1] += bq.y; y[4 * q + 2] += bq.z; y[4 * q + 3] += bq.w;
+            }
+            if ((prm.heads & 8) && valid) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) prm.tail[(long long)k * prm.n_pairs + p] = y[4 + k];
+            }
+            if (prm.heads & 2) {
+                float l[36];
+                {
+                    float z[32];
+                    tmem_ld32(tml + 64, z);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bq = sbias[kBiasH2 / 4 + q];
+                        l[4 * q] = z[4 * q] + bq.x; l[4 * q + 1] = z[4 * q + 1] + bq.y;
+                        l[4 * q + 2] = z[4 * q + 2] + bq.z; l[4 * q + 3] = z[4 * q + 3] + bq.w;
+                    }
+                }
+                l[32] = y[0]; l[33] = y[1]; l[34] = y[2]; l[35] = y[3];
+                bins.z = (unsigned char)sample_regs<36>(l, u4.z);
+            }
+        }
+        if (prm.heads & 4) {                   // right head: one more MMA into columns 0:48 (mu/nu already consumed)
+            CPPF_TC_STEP((issue3<48, 16>(tm, sA, sAl, sW + kOffHB3 * 4)));
+            float l[36];
+            {
+                float z[32];
+                tmem_ld32(tml, z);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 bq = sbias[kBiasH3 / 4 + q];
+                    l[4 * q] = z[4 * q] + bq.x; l[4 * q + 1] = z[4 * q + 1] + bq.y;
+                    l[4 * q + 2] = z[4 * q + 2] + bq.z; l[4 * q + 3] = z[4 * q + 3] + bq.w;
+                }
+                float y[16];
+                tmem_ld16(tml + 32, y);
+                const float4 bq = sbias[kBiasH3 / 4 + 8];
+                l[32] = y[0] + bq.x; l[33] = y[1] + bq.y; l[34] = y[2] + bq.z; l[35] = y[3] + bq.w;
+            }
+            bins.w = (unsigned char)sample_regs<36>(l, u4.w);
+        }
+        if (valid) reinterpret_cast<uchar4*>(prm.bins)[p] = bins;
+    }
+#undef CPPF_TC_STEP
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(kGroups * kTmemColsPerGroup)
+                     : "memory");
+}
+
+}  // namespace tc
+}  // namespace cppf
+
+using namespace cppf;
+
+extern "C" int cppf_tc_blob_floats(void) { return tc::kBlobFloats; }
+
+extern "C" int cppf_encode_sample_tc(const float* pc, const float* nrm, const float* table, const float* tc_blob,
+                                     const void* idx, int idx_is_64, int n_points, int64_t n_pairs, const float* uniforms,
+                                     uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_x3, void* stream) {
+    if (n_pairs <= 0) return 0;
+    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
+    if ((heads & 8) && tail == nullptr) return (int)cudaErrorInvalidValue;
+    tc::Params prm{pc, nrm, table, tc_blob, idx, uniforms, seed, bins, tail, dbg_x3, n_points, (long long)n_pairs, heads};
+    const long long n_tiles = (n_pairs + tc::kTile - 1) / tc::kTile;
+    long long ctas = (n_tiles + tc::kGroups - 1) / tc::kGroups;
+    if (ctas > sm_count()) ctas = sm_count();
+    auto kern = idx_is_64 ? tc::encode_sample_tc_kernel<true> : tc::encode_sample_tc_kernel<false>;
+    CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    kern<<<(int)ctas, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>(prm);
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}

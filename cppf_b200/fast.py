@@ -34,8 +34,10 @@ def decode_lut(vote_range, tr_bins=TR_BINS, rot_bins=ROT_BINS) -> torch.Tensor:
     return torch.cat([mu, nu, r, r]).float().contiguous()
 
 
-def encode_sample(ppf_encoder, pc, nrm, table, idxs, *, heads, uniforms=None, seed=0, bins=None, tail=None):
-    """-> (bins uint8 [P,4], tail f32 [5,P] | None)."""
+def encode_sample(ppf_encoder, pc, nrm, table, idxs, *, heads, uniforms=None, seed=0, bins=None, tail=None, impl="tc",
+                  dbg_x3=None):
+    """-> (bins uint8 [P,4], tail f32 [5,P] | None).  impl "tc": tcgen05 tensor-core encoder (3xTF32);
+    "simt": fp32 FFMA warp-tile encoder."""
     dev = pc.device
     n = pc.shape[0]
     ip, is64 = _idx_args(idxs)
@@ -46,6 +48,15 @@ def encode_sample(ppf_encoder, pc, nrm, table, idxs, *, heads, uniforms=None, se
         tail = torch.empty((5, n_pairs), dtype=torch.float32, device=dev)
     if uniforms is not None:
         assert uniforms.shape == (n_pairs, 4) and uniforms.is_contiguous() and uniforms.dtype == torch.float32
+    if impl == "tc":
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cppf_encode_sample_tc(
+                pc.data_ptr(), nrm.data_ptr(), table.data_ptr(), ppf_encoder.tc_blob(dev).data_ptr(), ip, is64, n, n_pairs,
+                uniforms.data_ptr() if uniforms is not None else None, int(seed), int(heads), bins.data_ptr(),
+                tail.data_ptr() if tail is not None else None, dbg_x3.data_ptr() if dbg_x3 is not None else None,
+                _sp(dev)), "cppf_encode_sample_tc")
+        return bins, tail
+    assert impl == "simt", impl
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().cppf_encode_sample(
             pc.data_ptr(), nrm.data_ptr(), table.data_ptr(), ppf_encoder.weight_blob(dev).data_ptr(),

@@ -103,6 +103,51 @@ def pack_head_weights(sd) -> np.ndarray:
     return blob
 
 
+def _canon_hi_lo(w: np.ndarray, n_pad: int, k_pad: int) -> list:
+    """nn.Linear weight [n, k] -> tcgen05 no-swizzle K-major operand [k_pad/4][n_pad][4], split into the
+    tf32 `hi` part (low 13 mantissa bits cleared) and the fp32 remainder `lo` (csrc/encode_tc.cu)."""
+    m = np.zeros((n_pad, k_pad), np.float32)
+    m[:w.shape[0], :w.shape[1]] = w
+    hi = (m.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = (m - hi).astype(np.float32)
+    canon = lambda a: np.ascontiguousarray(a.reshape(n_pad, k_pad // 4, 4).transpose(1, 0, 2)).reshape(-1)
+    return [canon(hi), canon(lo)]
+
+
+def pack_tc_weights(sd) -> np.ndarray:
+    """Pack a PPFEncoder ``state_dict`` for the tcgen05 encoder (layout: csrc/encode_tc.cu, kOff*)."""
+    g = lambda k: sd[k].detach().to("cpu", torch.float32).numpy()
+    w1_0, w0_0 = g("res_layers.0.fc1.weight"), g("res_layers.0.fc0.weight")
+    wf, bf = g("final.weight"), g("final.bias")
+    if w1_0.shape != (32, 2 * _F + 4) or wf.shape != (HEAD_OUT_DIM, 16):
+        raise NotImplementedError("the tcgen05 pair encoder is specialised to ppffcs=[84,32,32,16], "
+                                  f"out_dim={HEAD_OUT_DIM} (nocs/inference.py:83)")
+    r_up, r_rt, r_tail = 2 * TR_BINS, 2 * TR_BINS + ROT_BINS, 2 * TR_BINS + 2 * ROT_BINS
+    parts = []
+    parts += _canon_hi_lo(np.concatenate([w1_0[:, 2 * _F:], w0_0[:, 2 * _F:]], 0), 64, 8)            # WPPF
+    parts += _canon_hi_lo(g("res_layers.0.fc2.weight"), 32, 32)
+    parts += _canon_hi_lo(g("res_layers.1.fc1.weight"), 32, 32)
+    parts += _canon_hi_lo(g("res_layers.1.fc2.weight"), 32, 32)
+    parts += _canon_hi_lo(np.concatenate([g("res_layers.2.fc1.weight"), g("res_layers.2.fc0.weight")], 0), 32, 32)
+    parts += _canon_hi_lo(g("res_layers.2.fc2.weight"), 16, 16)
+    parts += _canon_hi_lo(wf[:r_up], 64, 16)                                                         # HB1 mu | nu
+    parts += _canon_hi_lo(np.concatenate([wf[r_up:r_rt], wf[r_tail:]], 0), 48, 16)                   # HB2 up | tail
+    parts += _canon_hi_lo(wf[r_rt:r_tail], 48, 16)                                                   # HB3 right
+    bias = np.zeros(256, np.float32)
+    bias[0:32] = g("res_layers.1.fc1.bias")
+    bias[32:64] = g("res_layers.1.fc2.bias")
+    bias[64:80] = g("res_layers.2.fc1.bias")
+    bias[80:96] = g("res_layers.2.fc0.bias") + g("res_layers.2.fc2.bias")
+    bias[96:160] = bf[:r_up]
+    bias[160:196] = bf[r_up:r_rt]
+    bias[196:201] = bf[r_tail:]
+    bias[208:244] = bf[r_rt:r_tail]
+    parts.append(bias)
+    blob = np.concatenate([np.ascontiguousarray(q, dtype=np.float32).reshape(-1) for q in parts])
+    assert blob.size == _lib.lib().cppf_tc_blob_floats(), blob.size
+    return blob
+
+
 def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -148,6 +193,8 @@ class PPFEncoder(nn.Module):
         self._blob_key = None
         self._hblob = None
         self._hblob_key = None
+        self._tcblob = None
+        self._tcblob_key = None
 
     # ---- weight blob cache (re-packed whenever parameters move or change)
     def weight_blob(self, device) -> torch.Tensor:
@@ -168,6 +215,16 @@ class PPFEncoder(nn.Module):
             self._hblob = torch.from_numpy(pack_head_weights(self.state_dict())).to(device)
             self._hblob_key = key
         return self._hblob
+
+    def tc_blob(self, device) -> torch.Tensor:
+        """Weights in tcgen05 operand layout for the tensor-core encoder (pack_tc_weights)."""
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._tcblob is None or self._tcblob_key != key:
+            if self.ppffcs != SUPPORTED_PPFFCS:
+                raise NotImplementedError(f"pair MLP kernels are specialised to ppffcs={list(SUPPORTED_PPFFCS)}")
+            self._tcblob = torch.from_numpy(pack_tc_weights(self.state_dict())).to(device)
+            self._tcblob_key = key
+        return self._tcblob
 
     def preproject(self, feat: torch.Tensor) -> torch.Tensor:
         """Per-point table of ResLayer-0's feature columns (cppf_ppf_preproject)."""

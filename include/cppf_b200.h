@@ -143,6 +143,15 @@ int cppf_encode_sample(const float* pc, const float* nrm, const float* table, co
                        const float* head_blob, const void* idx, int idx_is_64, int n_points, int64_t n_pairs,
                        const float* uniforms, uint64_t seed, int heads, uint8_t* bins, float* tail, void* stream);
 
+/* The same contract as cppf_encode_sample with the dense layers on the 5th-generation tensor cores
+ * (tcgen05.mma kind::tf32, accumulators in TMEM, 3xTF32 operand splitting for fp32-grade logits;
+ * csrc/encode_tc.cu).  tc_blob: cppf_tc_blob_floats() floats packed by cppf_b200/model.py:pack_tc_weights.
+ * dbg_x3 (optional, [n_pairs,16]) receives the output of the third ResLayer (models/model.py:136). */
+int cppf_tc_blob_floats(void);
+int cppf_encode_sample_tc(const float* pc, const float* nrm, const float* table, const float* tc_blob,
+                          const void* idx, int idx_is_64, int n_points, int64_t n_pairs, const float* uniforms,
+                          uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_x3, void* stream);
+
 /* models/voting.py:8-66 with prob == 1 (nocs/inference.py:201): votes accumulate in a
  * shared-memory-privatised fixed-point grid (weights rounded to 2^-14, exact integer sums,
  * deterministic) flushed into `scratch` (cppf_vote_scratch_bytes) and added to `grid`.

@@ -27,14 +27,16 @@ def _setup(n, seed, out_dim=141):
     return m, pc, nrm, feat
 
 
+@pytest.mark.parametrize("impl", ["tc", "simt"])
 @pytest.mark.parametrize("n,p,seed", [(512, 50000, 0), (777, 4099, 1)])
-def test_encode_sample_matches_oracle(n, p, seed):
+def test_encode_sample_matches_oracle(n, p, seed, impl):
     m, pc, nrm, feat = _setup(n, seed)
     idxs = synth.sample_pairs(n, p, seed).astype(np.int32)
     u = torch.rand(p, 4, generator=torch.Generator().manual_seed(seed + 9))
     with torch.no_grad():
         table = m.preproject(feat.to(DEV))
-        bins, tail = fast.encode_sample(m, _t(pc), _t(nrm), table, _t(idxs, torch.int32), heads=15, uniforms=u.to(DEV))
+        bins, tail = fast.encode_sample(m, _t(pc), _t(nrm), table, _t(idxs, torch.int32), heads=15, uniforms=u.to(DEV),
+                                        impl=impl)
     sd = {k: v.cpu() for k, v in m.state_dict().items()}
     logits = ref_model.ppf_encode_idx(torch.from_numpy(pc), torch.from_numpy(nrm), feat, idxs, sd)
     bins = bins.cpu().long()
@@ -46,17 +48,41 @@ def test_encode_sample_matches_oracle(n, p, seed):
     np.testing.assert_allclose(tail.cpu().numpy().T, logits[:, 136:].numpy(), rtol=1e-4, atol=2e-5)
 
 
-def test_encode_sample_dense_philox_and_head_mask():
+def test_encode_tc_third_reslayer_matches_oracle():
+    """x3 (input of `final`, models/model.py:134-136) from the tcgen05 chain vs the oracle's fp32 stack:
+    checks the 3xTF32 layers before any sampling is involved, incl. a ragged last tile (p % 128 != 0)."""
+    n, p = 300, 128 * 37 + 5
+    m, pc, nrm, feat = _setup(n, 3)
+    idxs = synth.sample_pairs(n, p, 3).astype(np.int64)
+    x3 = torch.full((p, 16), float("nan"), device=DEV)
+    with torch.no_grad():
+        table = m.preproject(feat.to(DEV))
+        fast.encode_sample(m, _t(pc), _t(nrm), table, _t(idxs, torch.int64), heads=15, seed=5, impl="tc", dbg_x3=x3)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    tpc, tn = torch.from_numpy(pc), torch.from_numpy(nrm)
+    ia, ib = torch.from_numpy(idxs[:, 0]), torch.from_numpy(idxs[:, 1])
+    d = tpc[ia] - tpc[ib]
+    dn = torch.norm(d, dim=-1)
+    dh = d / (dn[:, None] + 1e-7)
+    x = torch.cat([feat[ia], feat[ib], (tn[ia] * dh).sum(-1, keepdim=True), (tn[ib] * dh).sum(-1, keepdim=True),
+                   (tn[ia] * tn[ib]).sum(-1, keepdim=True), dn[:, None]], -1)
+    for i in range(3):
+        x = ref_model.res_layer(x, sd, f"res_layers.{i}")
+    np.testing.assert_allclose(x3.cpu().numpy(), x.numpy(), rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_encode_sample_dense_philox_and_head_mask(impl):
     n = 96
     m, pc, nrm, feat = _setup(n, 4)
     with torch.no_grad():
         table = m.preproject(feat.to(DEV))
-        b_seed, t_seed = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, seed=1234567890123)
+        b_seed, t_seed = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, seed=1234567890123, impl=impl)
         u = philox.pair_uniforms(1234567890123, n * n)
-        b_inj, t_inj = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, uniforms=_t(u))
+        b_inj, t_inj = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, uniforms=_t(u), impl=impl)
         b_idx, _ = fast.encode_sample(m, _t(pc), _t(nrm), table, _t(synth.dense_pairs(n), torch.int64), heads=15,
-                                      uniforms=_t(u))
-        b_tr, none_tail = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=fast.HEAD_TR, uniforms=_t(u))
+                                      uniforms=_t(u), impl=impl)
+        b_tr, none_tail = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=fast.HEAD_TR, uniforms=_t(u), impl=impl)
     assert torch.equal(b_seed, b_inj) and torch.equal(t_seed, t_inj)       # kernel Philox == oracle Philox
     assert torch.equal(b_idx, b_inj)                                        # dense enumeration == explicit list
     assert none_tail is None and torch.equal(b_tr[:, :2], b_inj[:, :2]) and not b_tr[:, 2:].any()
