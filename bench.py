@@ -35,6 +35,9 @@ if ROOT not in sys.path:
 
 METRIC = "point_pairs_per_sec"
 UNIT = "pairs/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r1_tc_encoder_ncu.md, profiles/r1_fused_kernels_ncu.md), N=4096 dense
+TRAFFIC_NCU = {"encode_sample": 2.608128e6 + 347.031296e6, "vote": 67.345152e6 + 0.514816e6}
 
 
 def parse():
@@ -50,6 +53,8 @@ def parse():
                     help="trained_like: after sampling, the (mu,nu,up) bins are replaced by the geometric targets a trained "
                          "network would emit (SURVEY.md 8d i) so that voting runs under a realistic load; network: votes "
                          "come from the random-init network's own samples (cheap: most candidates fall outside the grid)")
+    ap.add_argument("--encoder", default="tc", choices=["tc", "simt"],
+                    help="fused path's pair encoder: tc = tcgen05 tensor cores (3xTF32), simt = fp32 FFMA warp tiles")
     ap.add_argument("--path", default="fused", choices=["fused", "twopass"],
                     help="fused: encode+sample / privatised vote kernels; twopass: materialised logits like the reference")
     return ap.parse_args()
@@ -60,7 +65,7 @@ def workload_config(args):
                         "bottle constants (res 4e-3, 32 tr bins, 36 rot bins, 72 rots, adaptive), 1 object/rank/step",
             "n_points": args.n_points, "pairs_per_object": args.n_points ** 2, "objects_per_step_per_rank": 1,
             "out_dim": 141, "parallelism": f"objects sharded over {args.gpus} rank(s), one NCCL all_gather of pose records",
-            "path": args.path, "votes": args.votes,
+            "path": args.path, "votes": args.votes, "encoder": args.encoder,
             "weights": "torch.manual_seed(0) default init of the reference architecture (no checkpoints exist offline)",
             "l2_policy": "per-step working set (bins + tail logits of 16.7M pairs = 403 MB, + 134 MB survivor list) exceeds the "
                          "126 MB L2; each step is a different cloud"}
@@ -195,7 +200,7 @@ def main():
         print(json.dumps(line))
         return
 
-    from cppf_b200 import _lib, model, synth
+    from cppf_b200 import _lib, model, shard, synth
     from cppf_b200.pipeline import PoseConfig, PoseEstimator
 
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
@@ -211,6 +216,7 @@ def main():
     ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).to(dev).eval()
     pcfg = PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=0))        # 0 = all N^2 ordered pairs
     est = PoseEstimator(pe, ppf, pcfg, dev)
+    est.encoder_impl = args.encoder
     n = args.n_points
     pairs_per_obj = n * n
     n_obj = args.warmup + args.steps
@@ -250,10 +256,9 @@ def main():
         for s in range(args.warmup, n_obj):
             src = resident[s] if leg == "hbm" else pinned[s]
             records.append(step(src[0], src[1], seed=s)["record"])
-        rec = torch.from_numpy(np.stack(records)).to(dev)
-        if dist_on:
-            allrec = [torch.empty_like(rec) for _ in range(world)]
-            dist.all_gather(allrec, rec)                                  # the one collective: pose hypotheses
+        rec = np.stack(records)
+        ids = [rank * args.steps + i for i in range(args.steps)]
+        shard.gather_records(ids, rec, world * args.steps, device=dev)    # the one collective: pose hypotheses
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -281,28 +286,53 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))      # kernels are timed inside a long step
+        peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
         kern = {}
         for name, evs in timers.items():
             durs = [a.elapsed_time(b) for a, b in evs]
             if durs:
                 kern[name] = {"avg_ms": sum(durs) / len(durs), "launches": len(durs)}
-        # algorithmic HBM bytes per launch.  Dense pairs are enumerated in-kernel (no
-        # index read).  fused: encode_sample writes 4 bin bytes + 5 tail floats per pair, vote reads the 4 bin
-        # bytes; twopass: first-pass encode writes 64 fp32 logits per pair, vote reads 8 B (mu,nu) per pair.
-        algo = {"encode_sample": pairs_per_obj * 24, "vote": pairs_per_obj * 4,
-                "ppf_encode_pass1": pairs_per_obj * 64 * 4, "ppf_vote": pairs_per_obj * 8}
+        # Algorithmic work per launch.  Dense pairs are enumerated in-kernel (no index read).
+        #   encode_sample : 24 B/pair written (4 bin bytes + 5 tail floats); 23 968 FLOP/pair canonical pair MLP
+        #                   (models/model.py:12-23,87; 13.9 k executed after the per-point pre-projection of layer 0)
+        #   vote          : 4 B/pair read (bins); ~180 shared-memory atomics/pair under the trained-like load
+        #   twopass       : first-pass encode writes 64 fp32 logits/pair, vote reads 8 B (mu,nu)/pair
+        algo_bytes = {"encode_sample": pairs_per_obj * 24, "vote": pairs_per_obj * 4, "backvote": pairs_per_obj * 5,
+                      "ppf_encode_pass1": pairs_per_obj * 64 * 4, "ppf_vote": pairs_per_obj * 8}
+        algo_flops = {"encode_sample": pairs_per_obj * 23968.0, "ppf_encode_pass1": pairs_per_obj * (23968.0 - 2 * 16 * 77)}
+        binding = {"encode_sample": "tensor pipe issue + MMA round-trip latency (tcgen05 3xTF32 chain)" if args.encoder == "tc"
+                                    else "fp32 FMA pipe",
+                   "vote": "shared-memory atomic throughput", "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput",
+                   "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "torch ops (cdist/topk/LayerNorm), launch-bound"}
+        detail = {}
+        for k, v in kern.items():
+            t = v["avg_ms"] * 1e-3
+            d = {"avg_ms": v["avg_ms"], "binding_resource": binding.get(k)}
+            if k in algo_bytes:
+                d["hbm"] = {"achieved": algo_bytes[k] / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": algo_bytes[k] / t / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": algo_bytes[k]}
+                v["achieved_gbs"] = d["hbm"]["achieved"]
+                v["pairs_per_s"] = pairs_per_obj / t
+            if k in algo_flops:
+                d["tensor"] = {"achieved": algo_flops[k] / t / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                               "frac": algo_flops[k] / t / 1e12 / tensor_peak,
+                               "algorithmic_flops_per_launch": algo_flops[k],
+                               "note": "canonical fp32 pair-MLP FLOPs against the measured dense bf16 peak; the kernel runs "
+                                       "tf32 (half the bf16 rate) in 3 passes for fp32-grade logits"}
+            detail[k] = d
         roof = None
-        if kern:
-            dom = max((k for k in kern if k in algo), key=lambda k: kern[k]["avg_ms"])
-            for k in kern:
-                if k in algo:
-                    kern[k]["achieved_gbs"] = algo[k] / (kern[k]["avg_ms"] * 1e-3) / 1e9
-                    kern[k]["pairs_per_s"] = pairs_per_obj / (kern[k]["avg_ms"] * 1e-3)
-            if dom in algo:
-                a = kern[dom]["achieved_gbs"]
-                roof = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
-                        "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                        "algorithmic_bytes_per_launch": algo[dom], "avg_launch_ms": kern[dom]["avg_ms"]}
+        timed = [k for k in kern if k in algo_bytes]
+        if timed:
+            dom = max(timed, key=lambda k: kern[k]["avg_ms"])
+            use_tensor = dom in algo_flops and args.encoder == "tc"
+            src = detail[dom]["tensor" if use_tensor else "hbm"]
+            roof = {"kernel": dom, "bound": "tensor" if use_tensor else "hbm", "achieved": src["achieved"], "peak": src["peak"],
+                    "unit": src["unit"], "frac": src["frac"], "traffic": TRAFFIC_NCU.get(dom), "peak_source": peak_src,
+                    "avg_launch_ms": kern[dom]["avg_ms"], "binding_resource": binding.get(dom),
+                    "note": "dominant kernel by live CUDA-event time; none of this path's kernels is HBM-bound "
+                            "(logits never reach HBM) -- see roofline_detail for every kernel against the resource "
+                            "that binds it"}
         cpu = None
         if not args.no_cpu_baseline:
             r = run_cpu_reference(args, 2, 1, args.cpu_sample_pairs)
@@ -314,7 +344,8 @@ def main():
                 "objects_per_sec": world * args.steps / (ms_hbm * 1e-3),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "objects_per_sec": world * args.steps / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_detail": detail, "kernels": kern,
+                "cpu_baseline": cpu}
         if ms_net is not None:
             line["variant_network_votes"] = {"value": total_pairs / (ms_net * 1e-3), "unit": UNIT,
                                              "ms_per_step": ms_net / args.steps,

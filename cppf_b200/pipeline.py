@@ -71,6 +71,7 @@ class PoseEstimator:
         self.scale_mean = torch.tensor(cfg.scale_mean, dtype=torch.float32, device=self.device)
         self.timers = None            # optional {name: [(start_event, end_event), ...]} filled by estimate()
         self.lut = fast.decode_lut(cfg.vote_range, cfg.tr_num_bins, cfg.rot_num_bins).to(self.device)
+        self.encoder_impl = "tc"      # "tc": tcgen05 3xTF32 encoder (csrc/encode_tc.cu); "simt": fp32 FFMA (csrc/fused.cu)
 
     def _timed(self, name):
         est = self
@@ -275,7 +276,8 @@ class PoseEstimator:
         table = self.ppf.preproject(feat)
         heads = fast.HEAD_TR | fast.HEAD_UP | fast.HEAD_TAIL | (fast.HEAD_RIGHT if cfg.regress_right else 0)
         with self._timed("encode_sample"):
-            bins, tail = fast.encode_sample(self.ppf, pc, nrm, table, idxs, heads=heads, uniforms=uniforms, seed=seed)
+            bins, tail = fast.encode_sample(self.ppf, pc, nrm, table, idxs, heads=heads, uniforms=uniforms, seed=seed,
+                                            impl=self.encoder_impl)
         if inject_bins is not None:           # benchmark aid: vote load of a trained network (SURVEY.md 8d i)
             bins[:, :inject_bins.shape[1]] = inject_bins
         grid = torch.zeros(dims, dtype=torch.float32, device=dev)

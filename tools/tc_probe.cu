@@ -128,6 +128,63 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS));
 }
 
+// pipe throughput: one thread issues n_mma m128nNk8 MMAs round-robin over n_acc independent accumulators, one commit
+template <int N>
+__global__ void __launch_bounds__(128) pace_kernel(int n_mma, int n_acc, long long* cycles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < (2 * 2048 + 2 * N * 16) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t da = make_desc(smem_u32(smem), 2048, 128);
+    const uint64_t db = make_desc(smem_u32(smem + 4096), N * 16, 128);
+    long long t0 = clock64();
+    if (t == 0) {
+        for (int i = 0; i < n_mma; ++i) mma_tf32(tmem + (uint32_t)((i % n_acc) * N), da, db, idesc, i >= n_acc ? 1u : 0u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    long long t1 = clock64();
+    if (t == 0) *cycles = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int N>
+void pace(const char* name) {
+    long long* dC;
+    cudaMalloc(&dC, 8);
+    const size_t smem = 2 * 2048 + 2 * N * 16;
+    for (int n_acc : {1, 2, 4}) {
+        if (n_acc * N > 512) continue;
+        long long c1 = 0, c2 = 0;
+        pace_kernel<N><<<1, 128, smem>>>(64, n_acc, dC);
+        cudaDeviceSynchronize();
+        cudaMemcpy(&c1, dC, 8, cudaMemcpyDeviceToHost);
+        pace_kernel<N><<<1, 128, smem>>>(576, n_acc, dC);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpy(&c2, dC, 8, cudaMemcpyDeviceToHost);
+        printf("pace %s n_acc=%d: %.1f cycles per m128k8 tf32 MMA (%s)\n", name, n_acc, (c2 - c1) / 512.0, cudaGetErrorString(e));
+    }
+    cudaFree(dC);
+}
+
 template <int N, int K>
 int run(const char* name) {
     std::vector<float> A(128 * K), B(N * K), D(128 * N);
@@ -185,6 +242,10 @@ int main() {
     bad += run<112, 16>("N=112 K=16");
     bad += run<144, 16>("N=144 K=16");
     bad += run<64, 8>("N=64  K=8 ");
+    pace<16>("N=16 ");
+    pace<32>("N=32 ");
+    pace<64>("N=64 ");
+    pace<128>("N=128");
     printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
     return bad;
 }
