@@ -16,7 +16,10 @@
 //     operand sits at byte  (k/4) * rows*16 + r*16 + (k%4)*4 , i.e. one 16-byte chunk per row per
 //     "K plane"; a thread writes its own row with conflict-free 128-bit stores;
 //   * ResLayer 0 (84 -> 32) never sees the 80 feature columns: their products are pre-projected
-//     per point (cppf_ppf_preproject) and gathered; only the 4 PPF columns go through a K = 8 MMA;
+//     per point (cppf_tc_preproject) and gathered; only the 4 PPF columns go through a K = 8 MMA;
+//   * adjacent linear maps are composed on the host (no nonlinearity sits between fc2 of one
+//     ResLayer and fc1/fc0 of the next, nor between fc2_2 and `final`), so a tile needs 4 dependent
+//     MMA steps instead of 8 and 39 MMAs instead of 69 -- see "chain algebra" below;
 //   * a CTA holds 4 independent 128-thread groups (4 tiles in flight per SM) sharing one copy of
 //     the weights; each group has its own A buffers, mbarrier and 128 TMEM columns, and its own
 //     elected MMA-issuing thread, so one group's SIMT epilogue overlaps the others' MMAs.
@@ -31,24 +34,41 @@ constexpr int kGroups = 4;
 constexpr int kTile = 128;
 constexpr int kThreads = kGroups * kTile;
 
-// ---- packed weight blob (floats); every matrix is [K/4][N][4] (canonical K-major), hi block then lo block
-constexpr int kOffWppf = 0;                       // N = 64, K = 8 (k 4..7 zero): [fc1_0 | fc0_0] PPF columns
-constexpr int kOffW2_0 = kOffWppf + 2 * 512;      // N = 32, K = 32
-constexpr int kOffW1_1 = kOffW2_0 + 2 * 1024;
-constexpr int kOffW2_1 = kOffW1_1 + 2 * 1024;
-constexpr int kOffW10_2 = kOffW2_1 + 2 * 1024;    // rows 0:16 fc1_2, 16:32 fc0_2
-constexpr int kOffW2_2 = kOffW10_2 + 2 * 1024;    // N = 16, K = 16
-constexpr int kOffHB1 = kOffW2_2 + 2 * 256;       // N = 64, K = 16: [mu 32 | nu 32]
-constexpr int kOffHB2 = kOffHB1 + 2 * 1024;       // N = 48, K = 16: [up 36 | tail 5 | 0 x 7]
-constexpr int kOffHB3 = kOffHB2 + 2 * 768;        // N = 48, K = 16: [right 36 | 0 x 12]
-constexpr int kOffBias = kOffHB3 + 2 * 768;       // b1_1 32 | b2_1 32 | b10_2 32 | bh1 64 | bh2 48 | bh3 48
-constexpr int kBlobFloats = kOffBias + 256;
-constexpr int kBiasB1_1 = 0, kBiasB2_1 = 32, kBiasB10_2 = 64, kBiasH1 = 96, kBiasH2 = 160, kBiasH3 = 208;
+// ---- chain algebra (models/model.py:26-31,134-137; W10_2 = [fc1_2 ; fc0_2], b10_2 = [b1_2 ; b0_2 + b2_2])
+//   v1 = fc1_0(x)                     r  = fc0_0(x) + b2_0            h = relu(v1)        x1 = W2_0 h + r
+//   u  = relu(W1_1 x1 + b1_1)         = relu((W1_1 W2_0) h + q1),     q1 = W1_1 r + b1_1
+//   x2 = W2_1 u + b2_1 + x1
+//   t  = W10_2 x2 + b10_2             = (W10_2 W2_1) u + (W10_2 W2_0) h + q2,   q2 = W10_2 (r + b2_1) + b10_2
+//   u2 = relu(t[0:16]), r2 = t[16:32]  x3 = W2_2 u2 + r2
+//   logits = Wf x3 + bf               = [Wf W2_2 | Wf] [u2 ; r2] + bf
+// v1, q1, q2 are linear in (feat[a], feat[b], ppf): the feature parts are pre-projected per point into a
+// [N, 192] table (A side 96 = v1|q1|q2 with the biases, B side 96), the ppf part is the K = 8 front MMA.
+//   step 0: D[0:96]   = ppf . [P_v1 | P_q1 | P_q2]                         -> h  = relu(D[0:32] + TA + TB)
+//   step 1: D[32:96] += h . [W1_1 W2_0 ; W10_2 W2_0]^T                      -> u  = relu(D[32:64] + TA + TB)
+//   step 2: D[64:96] += u . (W10_2 W2_1)^T                                  -> [u2 ; r2] from D[64:96] + TA + TB
+//   step 3: D[0:112]  = [u2 ; r2] . [Wf W2_2 | Wf]^T (mu | nu | up | tail)  -> softmax + inverse-CDF draws
+//
+// ---- packed blob (floats).  First the per-point projection (read by cppf_tc_preproject only), then the
+// part staged in shared memory: every MMA operand is [K/4][N][4] (canonical K-major), hi block then lo block.
+constexpr int kTabCols = 192;
+constexpr int kOffPreW = 0;                       // [40][192] k-major
+constexpr int kOffPreB = kOffPreW + 40 * kTabCols;   // [192] (A side carries the biases)
+constexpr int kOffSmem = kOffPreB + kTabCols;
+// offsets relative to kOffSmem
+constexpr int kOffWp = 0;                         // N = 96,  K = 8 (k 4..7 zero)
+constexpr int kOffWs1 = kOffWp + 2 * 96 * 8;      // N = 64,  K = 32
+constexpr int kOffWs2 = kOffWs1 + 2 * 64 * 32;    // N = 32,  K = 32
+constexpr int kOffWh = kOffWs2 + 2 * 32 * 32;     // N = 112, K = 32: mu 32 | nu 32 | up 36 | tail 5 | 0 x 7
+constexpr int kOffWr = kOffWh + 2 * 112 * 32;     // N = 48,  K = 32: right 36 | 0 x 12
+constexpr int kOffBias = kOffWr + 2 * 48 * 32;    // bh 112 | br 48 | pad -> 256
+constexpr int kSmemFloats = kOffBias + 256;
+constexpr int kBlobFloats = kOffSmem + kSmemFloats;
+constexpr int kBiasH = 0, kBiasR = 112;
 
 constexpr int kAPlane = kTile * 16;               // bytes of one K plane of an A operand
 constexpr int kABytes = 8 * kAPlane;              // K = 32
 constexpr int kGroupBytes = 2 * kABytes;          // hi + lo
-constexpr int kSmemBytes = kBlobFloats * 4 + kGroups * kGroupBytes;
+constexpr int kSmemBytes = kSmemFloats * 4 + kGroups * kGroupBytes;
 constexpr int kTmemColsPerGroup = 128;
 
 struct Params {
@@ -61,7 +81,7 @@ struct Params {
     unsigned long long seed;
     uint8_t* bins;
     float* tail;
-    float* dbg_x3;              // optional [n_pairs][16]: output of the third ResLayer
+    float* dbg_t;               // optional [n_pairs][32]: t = [fc1_2(x2) ; fc0_2(x2) + fc2_2.b] (before the ReLU)
     int n_points;
     long long n_pairs;
     int heads;
@@ -85,7 +105,7 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
 }
 
 // D[128 x N] = A . B^T in 3xTF32: lo.hi + hi.lo + hi.hi (small terms first)
-template <int N, int K>
+template <int N, int K, bool ACC_INIT = false>
 __device__ __forceinline__ void issue3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi) {
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
     constexpr uint32_t bplane = N * 16;
@@ -97,7 +117,7 @@ __device__ __forceinline__ void issue3(uint32_t tmem_d, uint32_t a_hi, uint32_t 
 #pragma unroll
         for (int j = 0; j < K / 8; ++j)
             mma_tf32(tmem_d, kdesc(a + j * 2 * kAPlane, kAPlane), kdesc(b + j * 2 * bplane, bplane), idesc,
-                     (ps | j) != 0 ? 1u : 0u);
+                     (ACC_INIT || (ps | j) != 0) ? 1u : 0u);
     }
 }
 
@@ -192,12 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     float* sblob = reinterpret_cast<float*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int g = tid >> 7, tg = tid & 127;             // group, row within the tile
-    unsigned char* a_hi = smem + kBlobFloats * 4 + g * kGroupBytes;
+    unsigned char* a_hi = smem + kSmemFloats * 4 + g * kGroupBytes;
 
     {   // weights -> shared memory (one copy per CTA), TMEM allocation, barriers
-        const float4* src = reinterpret_cast<const float4*>(prm.blob);
+        const float4* src = reinterpret_cast<const float4*>(prm.blob + kOffSmem);
         float4* dst = reinterpret_cast<float4*>(sblob);
-        for (int i = tid; i < kBlobFloats / 4; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < kSmemFloats / 4; i += kThreads) dst[i] = __ldg(src + i);
         if (warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                          "r"(kGroups * kTmemColsPerGroup)
@@ -254,117 +274,81 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
                                           make_uint2((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32)));
             u4 = make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
         }
-        const float4* TA = reinterpret_cast<const float4*>(prm.table + (long long)a * 128);
-        const float4* TB = reinterpret_cast<const float4*>(prm.table + (long long)b * 128 + 64);
+        // planar table: float4 chunk j of point n sits at [(side*24 + j) * N + n], so the 32 lanes of a warp
+        // (consecutive b in dense mode) read 512 contiguous bytes per load and the a side is a broadcast
+        const float4* TA = reinterpret_cast<const float4*>(prm.table) + a;
+        const float4* TB = reinterpret_cast<const float4*>(prm.table) + (long long)(kTabCols / 8) * prm.n_points + b;
+        const long long ts = prm.n_points;
+        float4 ta[8], tb[8];
+        float x[32];
 
-        // ---- ResLayer 0 front end: [fc1_0 | fc0_0](x) = TA[a] + TB[b] + ppf . Wppf  (K = 8 MMA, N = 64)
+        // ---- step 0: ppf columns of v1 | q1 | q2 (K = 8, N = 96) -> h = relu(fc1_0(x))            models/model.py:27,29
         st_chunk(a_hi, 0, tg, ppf[0], ppf[1], ppf[2], ppf[3]);
         st_chunk(a_hi, 1, tg, 0.f, 0.f, 0.f, 0.f);
-        float R[32];
-        {
-            float4 ta[8], tb[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                ta[q] = __ldg(TA + q);
-                tb[q] = __ldg(TB + q);
-            }
-            CPPF_TC_STEP((issue3<64, 8>(tm, sA, sAl, sW + kOffWppf * 4)));
-            float acc[32];
-            tmem_ld32(tml, acc);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)       // h = relu(fc1_0(x))                       models/model.py:27,29
-                st_chunk(a_hi, q, tg, fmaxf(ta[q].x + tb[q].x + acc[4 * q], 0.f), fmaxf(ta[q].y + tb[q].y + acc[4 * q + 1], 0.f),
-                         fmaxf(ta[q].z + tb[q].z + acc[4 * q + 2], 0.f), fmaxf(ta[q].w + tb[q].w + acc[4 * q + 3], 0.f));
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {     // r = fc0_0(x) + fc2_0.b  (second half of the table row)
-                ta[q] = __ldg(TA + 8 + q);
-                tb[q] = __ldg(TB + 8 + q);
-            }
-            CPPF_TC_STEP((issue3<32, 32>(tm + 64, sA, sAl, sW + kOffW2_0 * 4)));
-            tmem_ld32(tml + 32, R);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                R[4 * q] += ta[q].x + tb[q].x;
-                R[4 * q + 1] += ta[q].y + tb[q].y;
-                R[4 * q + 2] += ta[q].z + tb[q].z;
-                R[4 * q + 3] += ta[q].w + tb[q].w;
-            }
+        for (int q = 0; q < 8; ++q) {
+            ta[q] = __ldg(TA + q * ts);
+            tb[q] = __ldg(TB + q * ts);
         }
-        float x[32];
-        // ---- x1 = fc2_0(h) + r                                                          models/model.py:30-31
+        CPPF_TC_STEP((issue3<96, 8>(tm, sA, sAl, sW + kOffWp * 4)));
+        tmem_ld32(tml, x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            st_chunk(a_hi, q, tg, fmaxf(ta[q].x + tb[q].x + x[4 * q], 0.f), fmaxf(ta[q].y + tb[q].y + x[4 * q + 1], 0.f),
+                     fmaxf(ta[q].z + tb[q].z + x[4 * q + 2], 0.f), fmaxf(ta[q].w + tb[q].w + x[4 * q + 3], 0.f));
+        // ---- step 1: [W1_1 W2_0 ; W10_2 W2_0] h accumulated onto q1 | q2 -> u = relu(fc1_1(x1))
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            ta[q] = __ldg(TA + (8 + q) * ts);
+            tb[q] = __ldg(TB + (8 + q) * ts);
+        }
+        CPPF_TC_STEP((issue3<64, 32, true>(tm + 32, sA, sAl, sW + kOffWs1 * 4)));
+        tmem_ld32(tml + 32, x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            st_chunk(a_hi, q, tg, fmaxf(ta[q].x + tb[q].x + x[4 * q], 0.f), fmaxf(ta[q].y + tb[q].y + x[4 * q + 1], 0.f),
+                     fmaxf(ta[q].z + tb[q].z + x[4 * q + 2], 0.f), fmaxf(ta[q].w + tb[q].w + x[4 * q + 3], 0.f));
+        // ---- step 2: (W10_2 W2_1) u accumulated onto q2 + (W10_2 W2_0) h -> t = [fc1_2(x2) ; fc0_2(x2) + fc2_2.b]
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            ta[q] = __ldg(TA + (16 + q) * ts);
+            tb[q] = __ldg(TB + (16 + q) * ts);
+        }
+        CPPF_TC_STEP((issue3<32, 32, true>(tm + 64, sA, sAl, sW + kOffWs2 * 4)));
         tmem_ld32(tml + 64, x);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) R[i] += x[i];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) st_chunk(a_hi, q, tg, R[4 * q], R[4 * q + 1], R[4 * q + 2], R[4 * q + 3]);
-        // ---- u = relu(fc1_1(x1))
-        CPPF_TC_STEP((issue3<32, 32>(tm, sA, sAl, sW + kOffW1_1 * 4)));
-        tmem_ld32(tml, x);
-#pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const float4 bq = sbias[kBiasB1_1 / 4 + q];
-            st_chunk(a_hi, q, tg, fmaxf(x[4 * q] + bq.x, 0.f), fmaxf(x[4 * q + 1] + bq.y, 0.f), fmaxf(x[4 * q + 2] + bq.z, 0.f),
-                     fmaxf(x[4 * q + 3] + bq.w, 0.f));
+            x[4 * q] += ta[q].x + tb[q].x;
+            x[4 * q + 1] += ta[q].y + tb[q].y;
+            x[4 * q + 2] += ta[q].z + tb[q].z;
+            x[4 * q + 3] += ta[q].w + tb[q].w;
         }
-        // ---- x2 = fc2_1(u) + x1   (identity skip)
-        CPPF_TC_STEP((issue3<32, 32>(tm, sA, sAl, sW + kOffW2_1 * 4)));
-        tmem_ld32(tml, x);
+        if (prm.dbg_t != nullptr && valid) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 bq = sbias[kBiasB2_1 / 4 + q];
-            R[4 * q] += x[4 * q] + bq.x;
-            R[4 * q + 1] += x[4 * q + 1] + bq.y;
-            R[4 * q + 2] += x[4 * q + 2] + bq.z;
-            R[4 * q + 3] += x[4 * q + 3] + bq.w;
-            st_chunk(a_hi, q, tg, R[4 * q], R[4 * q + 1], R[4 * q + 2], R[4 * q + 3]);
-        }
-        // ---- [u ; r] = [relu(fc1_2(x2)) ; fc0_2(x2) + fc2_2.b]
-        CPPF_TC_STEP((issue3<32, 32>(tm, sA, sAl, sW + kOffW10_2 * 4)));
-        tmem_ld32(tml, x);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 bq = sbias[kBiasB10_2 / 4 + q];
-            st_chunk(a_hi, q, tg, fmaxf(x[4 * q] + bq.x, 0.f), fmaxf(x[4 * q + 1] + bq.y, 0.f), fmaxf(x[4 * q + 2] + bq.z, 0.f),
-                     fmaxf(x[4 * q + 3] + bq.w, 0.f));
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(prm.dbg_t + p * 32)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 bq = sbias[kBiasB10_2 / 4 + 4 + q];
-            R[4 * q] = x[16 + 4 * q] + bq.x;
-            R[4 * q + 1] = x[16 + 4 * q + 1] + bq.y;
-            R[4 * q + 2] = x[16 + 4 * q + 2] + bq.z;
-            R[4 * q + 3] = x[16 + 4 * q + 3] + bq.w;
-        }
-        // ---- x3 = fc2_2(u) + r
-        CPPF_TC_STEP((issue3<16, 16>(tm, sA, sAl, sW + kOffW2_2 * 4)));
-        {
-            float y[16];
-            tmem_ld16(tml, y);
+        for (int q = 0; q < 4; ++q)           // u2 = relu(t[0:16])   (k 0..15 of the head operand)
+            st_chunk(a_hi, q, tg, fmaxf(x[4 * q], 0.f), fmaxf(x[4 * q + 1], 0.f), fmaxf(x[4 * q + 2], 0.f), fmaxf(x[4 * q + 3], 0.f));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] += R[i];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) st_chunk(a_hi, q, tg, y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-            if (prm.dbg_x3 != nullptr && valid) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    reinterpret_cast<float4*>(prm.dbg_x3 + p * 16)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-            }
-        }
-        // ---- `final`, head by head (models/model.py:137): [mu | nu] -> columns 0:64, [up | tail] -> 64:112
-        CPPF_TC_STEP((issue3<64, 16>(tm, sA, sAl, sW + kOffHB1 * 4), issue3<48, 16>(tm + 64, sA, sAl, sW + kOffHB2 * 4)));
+        for (int q = 4; q < 8; ++q)           // r2 = t[16:32]        (k 16..31)
+            st_chunk(a_hi, q, tg, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        // ---- step 3: `final` o fc2_2 on [u2 ; r2] (models/model.py:31,137): mu | nu | up | tail -> columns 0:112
+        CPPF_TC_STEP((issue3<112, 32>(tm, sA, sAl, sW + kOffWh * 4)));
         uchar4 bins = make_uchar4(0, 0, 0, 0);
         if (prm.heads & 1) {
             tmem_ld32(tml, x);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 bq = sbias[kBiasH1 / 4 + q];
+                const float4 bq = sbias[kBiasH / 4 + q];
                 x[4 * q] += bq.x; x[4 * q + 1] += bq.y; x[4 * q + 2] += bq.z; x[4 * q + 3] += bq.w;
             }
             bins.x = (unsigned char)sample_regs<32>(x, u4.x);
             tmem_ld32(tml + 32, x);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 bq = sbias[kBiasH1 / 4 + 8 + q];
+                const float4 bq = sbias[kBiasH / 4 + 8 + q];
                 x[4 * q] += bq.x; x[4 * q + 1] += bq.y; x[4 * q + 2] += bq.z; x[4 * q + 3] += bq.w;
             }
             bins.y = (unsigned char)sample_regs<32>(x, u4.y);
@@ -374,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
             tmem_ld16(tml + 96, y);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 bq = sbias[kBiasH2 / 4 + 8 + q];
+                const float4 bq = sbias[kBiasH / 4 + 24 + q];
                 y[4 * q] += bq.x; y[4 * q + 1] += bq.y; y[4 * q + 2] += bq.z; y[4 * q + 3] += bq.w;
             }
             if ((prm.heads & 8) && valid) {
@@ -388,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
                     tmem_ld32(tml + 64, z);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 bq = sbias[kBiasH2 / 4 + q];
+                        const float4 bq = sbias[kBiasH / 4 + 16 + q];
                         l[4 * q] = z[4 * q] + bq.x; l[4 * q + 1] = z[4 * q + 1] + bq.y;
                         l[4 * q + 2] = z[4 * q + 2] + bq.z; l[4 * q + 3] = z[4 * q + 3] + bq.w;
                     }
@@ -398,20 +382,20 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
             }
         }
         if (prm.heads & 4) {                   // right head: one more MMA into columns 0:48 (mu/nu already consumed)
-            CPPF_TC_STEP((issue3<48, 16>(tm, sA, sAl, sW + kOffHB3 * 4)));
+            CPPF_TC_STEP((issue3<48, 32>(tm, sA, sAl, sW + kOffWr * 4)));
             float l[36];
             {
                 float z[32];
                 tmem_ld32(tml, z);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float4 bq = sbias[kBiasH3 / 4 + q];
+                    const float4 bq = sbias[kBiasR / 4 + q];
                     l[4 * q] = z[4 * q] + bq.x; l[4 * q + 1] = z[4 * q + 1] + bq.y;
                     l[4 * q + 2] = z[4 * q + 2] + bq.z; l[4 * q + 3] = z[4 * q + 3] + bq.w;
                 }
                 float y[16];
                 tmem_ld16(tml + 32, y);
-                const float4 bq = sbias[kBiasH3 / 4 + 8];
+                const float4 bq = sbias[kBiasR / 4 + 8];
                 l[32] = y[0] + bq.x; l[33] = y[1] + bq.y; l[34] = y[2] + bq.z; l[35] = y[3] + bq.w;
             }
             bins.w = (unsigned char)sample_regs<36>(l, u4.w);
@@ -426,20 +410,44 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
                      : "memory");
 }
 
+// Per-point projection of the feature columns of v1 | q1 | q2 (chain algebra above): column c of point n =
+// feat[n] . M[:, c] + bias[c]; columns 0:96 are read by pairs whose point a is n, 96:192 by pairs whose point b
+// is n.  Stored planar in float4 chunks: table4[(c/4) * N + n] (see the gather in the kernel).
+__global__ void __launch_bounds__(kTabCols) tc_preproject_kernel(const float* __restrict__ feat, const float* __restrict__ blob,
+                                                                 float* __restrict__ table, int n_points) {
+    __shared__ float f[40];
+    const int n = blockIdx.x;
+    if (threadIdx.x < 40) f[threadIdx.x] = feat[(int64_t)n * 40 + threadIdx.x];
+    __syncthreads();
+    const int c = threadIdx.x;
+    float acc = blob[kOffPreB + c];
+#pragma unroll 8
+    for (int k = 0; k < 40; ++k) acc = fmaf(f[k], __ldg(blob + kOffPreW + k * kTabCols + c), acc);
+    table[((int64_t)(c >> 2) * n_points + n) * 4 + (c & 3)] = acc;
+}
+
 }  // namespace tc
 }  // namespace cppf
 
 using namespace cppf;
 
 extern "C" int cppf_tc_blob_floats(void) { return tc::kBlobFloats; }
+extern "C" int cppf_tc_table_cols(void) { return tc::kTabCols; }
+
+extern "C" int cppf_tc_preproject(const float* feat, const float* tc_blob, float* table, int n_points, void* stream) {
+    if (n_points <= 0) return 0;
+    tc::tc_preproject_kernel<<<n_points, tc::kTabCols, 0, (cudaStream_t)stream>>>(feat, tc_blob, table, n_points);
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int cppf_encode_sample_tc(const float* pc, const float* nrm, const float* table, const float* tc_blob,
                                      const void* idx, int idx_is_64, int n_points, int64_t n_pairs, const float* uniforms,
-                                     uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_x3, void* stream) {
+                                     uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_t, void* stream) {
     if (n_pairs <= 0) return 0;
     if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     if ((heads & 8) && tail == nullptr) return (int)cudaErrorInvalidValue;
-    tc::Params prm{pc, nrm, table, tc_blob, idx, uniforms, seed, bins, tail, dbg_x3, n_points, (long long)n_pairs, heads};
+    tc::Params prm{pc, nrm, table, tc_blob, idx, uniforms, seed, bins, tail, dbg_t, n_points, (long long)n_pairs, heads};
     const long long n_tiles = (n_pairs + tc::kTile - 1) / tc::kTile;
     long long ctas = (n_tiles + tc::kGroups - 1) / tc::kGroups;
     if (ctas > sm_count()) ctas = sm_count();

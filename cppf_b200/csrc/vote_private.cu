@@ -203,7 +203,39 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
             const f3 y = cross3(x, ab);
             const int n = adaptive_rots(nu, prm.res, prm.n_rots);              // :97
             const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
-            for (int i = 0; i < n; ++i) {
+            // The reference walks i = 0..n-1 and stops at the first candidate within `tol` of the centre; only
+            // whether such a candidate EXISTS is consumed (nocs/inference.py:229-230).  The candidates lie on a
+            // circle (centre c, radius nu, plane normal ab), so the ones within tol of T form one arc around the
+            // angle of T's in-plane projection: bound that arc analytically (with generous slack), then test only
+            // its candidates -- each with the reference's own arithmetic, so the mask is unchanged.
+            int i_lo = 0, i_cnt = n;
+            if (n > 12) {
+                const f3 v = {tx - c.x, ty - c.y, tz - c.z};
+                const f3 ey = cross3(ex, ab);
+                const float dpl = dot3(v, ab), px = dot3(v, ex), py = dot3(v, ey);
+                const float rho = sqrtf(px * px + py * py);
+                const float tol2 = prm.tol * prm.tol * 1.01f + 1e-12f;
+                const float room = tol2 - dpl * dpl - (nu - rho) * (nu - rho);   // >= 2 nu rho (1 - cos d) for a hit
+                const float two_nr = 2.f * fabsf(nu) * rho;
+                if (room < 0.f) {
+                    i_cnt = 0;
+                } else if (room < 1.9f * two_nr) {
+                    const float dmax = acosf(1.f - room / two_nr);               // half-width of the arc (rad)
+                    const float step = 6.2831853f / (float)n;
+                    float th = atan2f(py, px);
+                    if (nu < 0.f) th += 3.14159265f;                             // x, y carry the sign of nu
+                    if (th < 0.f) th += 6.2831853f;
+                    const int w = (int)(dmax / step) + 2;
+                    if (2 * w + 1 < n) {
+                        i_lo = (int)(th / step + 0.5f) - w;
+                        i_cnt = 2 * w + 1;
+                    }
+                }
+            }
+            for (int k = 0; k < i_cnt; ++k) {
+                int i = i_lo + k;
+                i = i < 0 ? i + n : (i >= n ? i - n : i);
+                i = i < 0 ? i + n : (i >= n ? i - n : i);
                 const float2 cs = tab[i];
                 const f3 off = x * cs.x + y * cs.y;
                 const f3 pc = c + off;
@@ -214,7 +246,7 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
                 const float gzf = div_by(pc.z - cz, prm.res, prm.inv_res);
                 if (gxf < 0.f || gyf < 0.f || gzf < 0.f || gxf >= prm.hx || gyf >= prm.hy || gzf >= prm.hz) continue;
                 hit = off.x != 0.f || off.y != 0.f || off.z != 0.f;            // inference.py:230 any(oc != 0)
-                break;
+                if (hit) break;
             }
         }
         prm.out_mask[p] = hit ? 1 : 0;

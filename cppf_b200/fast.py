@@ -35,7 +35,7 @@ def decode_lut(vote_range, tr_bins=TR_BINS, rot_bins=ROT_BINS) -> torch.Tensor:
 
 
 def encode_sample(ppf_encoder, pc, nrm, table, idxs, *, heads, uniforms=None, seed=0, bins=None, tail=None, impl="tc",
-                  dbg_x3=None):
+                  dbg_t=None):
     """-> (bins uint8 [P,4], tail f32 [5,P] | None).  impl "tc": tcgen05 tensor-core encoder (3xTF32);
     "simt": fp32 FFMA warp-tile encoder."""
     dev = pc.device
@@ -49,14 +49,17 @@ def encode_sample(ppf_encoder, pc, nrm, table, idxs, *, heads, uniforms=None, se
     if uniforms is not None:
         assert uniforms.shape == (n_pairs, 4) and uniforms.is_contiguous() and uniforms.dtype == torch.float32
     if impl == "tc":
+        assert table.dim() == 3 and table.shape[0] * 4 == _lib.lib().cppf_tc_table_cols() and table.shape[1] == n, \
+            "impl='tc' needs ppf_encoder.tc_preproject(feat)"
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().cppf_encode_sample_tc(
                 pc.data_ptr(), nrm.data_ptr(), table.data_ptr(), ppf_encoder.tc_blob(dev).data_ptr(), ip, is64, n, n_pairs,
                 uniforms.data_ptr() if uniforms is not None else None, int(seed), int(heads), bins.data_ptr(),
-                tail.data_ptr() if tail is not None else None, dbg_x3.data_ptr() if dbg_x3 is not None else None,
+                tail.data_ptr() if tail is not None else None, dbg_t.data_ptr() if dbg_t is not None else None,
                 _sp(dev)), "cppf_encode_sample_tc")
         return bins, tail
     assert impl == "simt", impl
+    assert table.dim() == 2 and table.shape[1] == 128, "impl='simt' needs ppf_encoder.preproject(feat)"
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().cppf_encode_sample(
             pc.data_ptr(), nrm.data_ptr(), table.data_ptr(), ppf_encoder.weight_blob(dev).data_ptr(),

@@ -115,33 +115,46 @@ def _canon_hi_lo(w: np.ndarray, n_pad: int, k_pad: int) -> list:
 
 
 def pack_tc_weights(sd) -> np.ndarray:
-    """Pack a PPFEncoder ``state_dict`` for the tcgen05 encoder (layout: csrc/encode_tc.cu, kOff*)."""
-    g = lambda k: sd[k].detach().to("cpu", torch.float32).numpy()
-    w1_0, w0_0 = g("res_layers.0.fc1.weight"), g("res_layers.0.fc0.weight")
-    wf, bf = g("final.weight"), g("final.bias")
-    if w1_0.shape != (32, 2 * _F + 4) or wf.shape != (HEAD_OUT_DIM, 16):
+    """Pack a PPFEncoder ``state_dict`` for the tcgen05 encoder (csrc/encode_tc.cu, "chain algebra"):
+    adjacent linear maps of models/model.py:26-31,134-137 are composed here in float64 and rounded once
+    to fp32, so the kernel runs 4 MMA steps per tile instead of 8.  Layout = the kOff* constants there."""
+    g = lambda k: sd[k].detach().to("cpu", torch.float64).numpy()
+    W1_0, b1_0 = g("res_layers.0.fc1.weight"), g("res_layers.0.fc1.bias")
+    W0_0, b0_0 = g("res_layers.0.fc0.weight"), g("res_layers.0.fc0.bias")
+    W2_0, b2_0 = g("res_layers.0.fc2.weight"), g("res_layers.0.fc2.bias")
+    W1_1, b1_1 = g("res_layers.1.fc1.weight"), g("res_layers.1.fc1.bias")
+    W2_1, b2_1 = g("res_layers.1.fc2.weight"), g("res_layers.1.fc2.bias")
+    W1_2, b1_2 = g("res_layers.2.fc1.weight"), g("res_layers.2.fc1.bias")
+    W0_2, b0_2 = g("res_layers.2.fc0.weight"), g("res_layers.2.fc0.bias")
+    W2_2, b2_2 = g("res_layers.2.fc2.weight"), g("res_layers.2.fc2.bias")
+    Wf, bf = g("final.weight"), g("final.bias")
+    if W1_0.shape != (32, 2 * _F + 4) or W1_1.shape != (32, 32) or W1_2.shape != (16, 32) or Wf.shape != (HEAD_OUT_DIM, 16):
         raise NotImplementedError("the tcgen05 pair encoder is specialised to ppffcs=[84,32,32,16], "
                                   f"out_dim={HEAD_OUT_DIM} (nocs/inference.py:83)")
+    W10_2 = np.concatenate([W1_2, W0_2], 0)                           # [32,32]
+    b10_2 = np.concatenate([b1_2, b0_2 + b2_2])
+    br = b0_0 + b2_0                                                  # bias of r = fc0_0(x) + b2_0
+    # rows of the three front-end quantities as functions of x = [feat_a(40) feat_b(40) ppf(4)]
+    V1, Q1, Q2 = W1_0, W1_1 @ W0_0, W10_2 @ W0_0                      # each [32,84]
+    bV1, bQ1, bQ2 = b1_0, W1_1 @ br + b1_1, W10_2 @ (br + b2_1) + b10_2
+    front = np.concatenate([V1, Q1, Q2], 0)                           # [96,84]
+    pre_w = np.concatenate([front[:, :_F].T, front[:, _F:2 * _F].T], 1)          # [40,192]: A side | B side
+    pre_b = np.concatenate([bV1, bQ1, bQ2, np.zeros(96)])
     r_up, r_rt, r_tail = 2 * TR_BINS, 2 * TR_BINS + ROT_BINS, 2 * TR_BINS + 2 * ROT_BINS
-    parts = []
-    parts += _canon_hi_lo(np.concatenate([w1_0[:, 2 * _F:], w0_0[:, 2 * _F:]], 0), 64, 8)            # WPPF
-    parts += _canon_hi_lo(g("res_layers.0.fc2.weight"), 32, 32)
-    parts += _canon_hi_lo(g("res_layers.1.fc1.weight"), 32, 32)
-    parts += _canon_hi_lo(g("res_layers.1.fc2.weight"), 32, 32)
-    parts += _canon_hi_lo(np.concatenate([g("res_layers.2.fc1.weight"), g("res_layers.2.fc0.weight")], 0), 32, 32)
-    parts += _canon_hi_lo(g("res_layers.2.fc2.weight"), 16, 16)
-    parts += _canon_hi_lo(wf[:r_up], 64, 16)                                                         # HB1 mu | nu
-    parts += _canon_hi_lo(np.concatenate([wf[r_up:r_rt], wf[r_tail:]], 0), 48, 16)                   # HB2 up | tail
-    parts += _canon_hi_lo(wf[r_rt:r_tail], 48, 16)                                                   # HB3 right
+    head_rows = np.concatenate([Wf[:r_rt], Wf[r_tail:]], 0)           # mu | nu | up | tail  (105 rows)
+    WH = np.concatenate([head_rows @ W2_2, head_rows], 1)             # acts on [u2 ; r2]  [105,32]
+    WR = np.concatenate([Wf[r_rt:r_tail] @ W2_2, Wf[r_rt:r_tail]], 1)            # right head [36,32]
+    f32 = lambda a: np.asarray(a, np.float64).astype(np.float32)
+    parts = [f32(pre_w).reshape(-1), f32(pre_b)]
+    parts += _canon_hi_lo(f32(front[:, 2 * _F:]), 96, 8)              # Wp : ppf columns
+    parts += _canon_hi_lo(f32(np.concatenate([W1_1 @ W2_0, W10_2 @ W2_0], 0)), 64, 32)    # Ws1
+    parts += _canon_hi_lo(f32(W10_2 @ W2_1), 32, 32)                  # Ws2
+    parts += _canon_hi_lo(f32(WH), 112, 32)
+    parts += _canon_hi_lo(f32(WR), 48, 32)
     bias = np.zeros(256, np.float32)
-    bias[0:32] = g("res_layers.1.fc1.bias")
-    bias[32:64] = g("res_layers.1.fc2.bias")
-    bias[64:80] = g("res_layers.2.fc1.bias")
-    bias[80:96] = g("res_layers.2.fc0.bias") + g("res_layers.2.fc2.bias")
-    bias[96:160] = bf[:r_up]
-    bias[160:196] = bf[r_up:r_rt]
-    bias[196:201] = bf[r_tail:]
-    bias[208:244] = bf[r_rt:r_tail]
+    bias[0:r_rt] = f32(bf[:r_rt])
+    bias[r_rt:r_rt + 5] = f32(bf[r_tail:])
+    bias[112:112 + ROT_BINS] = f32(bf[r_rt:r_tail])
     parts.append(bias)
     blob = np.concatenate([np.ascontiguousarray(q, dtype=np.float32).reshape(-1) for q in parts])
     assert blob.size == _lib.lib().cppf_tc_blob_floats(), blob.size
@@ -225,6 +238,16 @@ class PPFEncoder(nn.Module):
             self._tcblob = torch.from_numpy(pack_tc_weights(self.state_dict())).to(device)
             self._tcblob_key = key
         return self._tcblob
+
+    def tc_preproject(self, feat: torch.Tensor) -> torch.Tensor:
+        """Per-point table of the tcgen05 encoder's front end (cppf_tc_preproject): 192 columns per point,
+        stored planar as [48 float4 chunks][N][4] so that dense-mode gathers are coalesced."""
+        n = feat.shape[0]
+        L = _lib.lib()
+        table = torch.empty((L.cppf_tc_table_cols() // 4, n, 4), dtype=torch.float32, device=feat.device)
+        _lib.check(L.cppf_tc_preproject(feat.data_ptr(), self.tc_blob(feat.device).data_ptr(), table.data_ptr(), n,
+                                        _stream_ptr(feat.device)), "cppf_tc_preproject")
+        return table
 
     def preproject(self, feat: torch.Tensor) -> torch.Tensor:
         """Per-point table of ResLayer-0's feature columns (cppf_ppf_preproject)."""

@@ -273,7 +273,7 @@ class PoseEstimator:
             idxs = torch.as_tensor(idxs).to(dev).contiguous()
         with self._timed("point_encoder"):
             feat = self.point_features(pc, nrm)
-        table = self.ppf.preproject(feat)
+        table = self.ppf.tc_preproject(feat) if self.encoder_impl == "tc" else self.ppf.preproject(feat)
         heads = fast.HEAD_TR | fast.HEAD_UP | fast.HEAD_TAIL | (fast.HEAD_RIGHT if cfg.regress_right else 0)
         with self._timed("encode_sample"):
             bins, tail = fast.encode_sample(self.ppf, pc, nrm, table, idxs, heads=heads, uniforms=uniforms, seed=seed,

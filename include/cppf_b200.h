@@ -145,12 +145,17 @@ int cppf_encode_sample(const float* pc, const float* nrm, const float* table, co
 
 /* The same contract as cppf_encode_sample with the dense layers on the 5th-generation tensor cores
  * (tcgen05.mma kind::tf32, accumulators in TMEM, 3xTF32 operand splitting for fp32-grade logits;
- * csrc/encode_tc.cu).  tc_blob: cppf_tc_blob_floats() floats packed by cppf_b200/model.py:pack_tc_weights.
- * dbg_x3 (optional, [n_pairs,16]) receives the output of the third ResLayer (models/model.py:136). */
+ * csrc/encode_tc.cu).  Adjacent linear maps of models/model.py:26-31,134-137 are composed on the host
+ * (cppf_b200/model.py:pack_tc_weights -> tc_blob, cppf_tc_blob_floats() floats), so `table` here is the
+ * per-point projection written by cppf_tc_preproject (feat [n_points,40]): cppf_tc_table_cols() columns per
+ * point, stored planar as [cols/4][n_points][4] floats so dense-mode gathers are coalesced.
+ * dbg_t (optional, [n_pairs,32]) receives [fc1_2(x2) ; fc0_2(x2) + fc2_2.b], the last pre-activation. */
 int cppf_tc_blob_floats(void);
+int cppf_tc_table_cols(void);
+int cppf_tc_preproject(const float* feat, const float* tc_blob, float* table, int n_points, void* stream);
 int cppf_encode_sample_tc(const float* pc, const float* nrm, const float* table, const float* tc_blob,
                           const void* idx, int idx_is_64, int n_points, int64_t n_pairs, const float* uniforms,
-                          uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_x3, void* stream);
+                          uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_t, void* stream);
 
 /* models/voting.py:8-66 with prob == 1 (nocs/inference.py:201): votes accumulate in a
  * shared-memory-privatised fixed-point grid (weights rounded to 2^-14, exact integer sums,

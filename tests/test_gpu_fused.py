@@ -34,7 +34,7 @@ def test_encode_sample_matches_oracle(n, p, seed, impl):
     idxs = synth.sample_pairs(n, p, seed).astype(np.int32)
     u = torch.rand(p, 4, generator=torch.Generator().manual_seed(seed + 9))
     with torch.no_grad():
-        table = m.preproject(feat.to(DEV))
+        table = _table(m, feat, impl)
         bins, tail = fast.encode_sample(m, _t(pc), _t(nrm), table, _t(idxs, torch.int32), heads=15, uniforms=u.to(DEV),
                                         impl=impl)
     sd = {k: v.cpu() for k, v in m.state_dict().items()}
@@ -48,16 +48,17 @@ def test_encode_sample_matches_oracle(n, p, seed, impl):
     np.testing.assert_allclose(tail.cpu().numpy().T, logits[:, 136:].numpy(), rtol=1e-4, atol=2e-5)
 
 
-def test_encode_tc_third_reslayer_matches_oracle():
-    """x3 (input of `final`, models/model.py:134-136) from the tcgen05 chain vs the oracle's fp32 stack:
-    checks the 3xTF32 layers before any sampling is involved, incl. a ragged last tile (p % 128 != 0)."""
+def test_encode_tc_last_preactivation_matches_oracle():
+    """t = [fc1_2(x2) ; fc0_2(x2) + fc2_2.b] (models/model.py:27-28 of the third ResLayer) from the tcgen05 chain
+    -- three composed 3xTF32 MMA steps, no sampling involved -- vs the oracle's layer-by-layer fp32 stack,
+    incl. a ragged last tile (p % 128 != 0)."""
     n, p = 300, 128 * 37 + 5
     m, pc, nrm, feat = _setup(n, 3)
     idxs = synth.sample_pairs(n, p, 3).astype(np.int64)
-    x3 = torch.full((p, 16), float("nan"), device=DEV)
+    t_dev = torch.full((p, 32), float("nan"), device=DEV)
     with torch.no_grad():
-        table = m.preproject(feat.to(DEV))
-        fast.encode_sample(m, _t(pc), _t(nrm), table, _t(idxs, torch.int64), heads=15, seed=5, impl="tc", dbg_x3=x3)
+        fast.encode_sample(m, _t(pc), _t(nrm), _table(m, feat, "tc"), _t(idxs, torch.int64), heads=15, seed=5, impl="tc",
+                           dbg_t=t_dev)
     sd = {k: v.cpu() for k, v in m.state_dict().items()}
     tpc, tn = torch.from_numpy(pc), torch.from_numpy(nrm)
     ia, ib = torch.from_numpy(idxs[:, 0]), torch.from_numpy(idxs[:, 1])
@@ -66,9 +67,12 @@ def test_encode_tc_third_reslayer_matches_oracle():
     dh = d / (dn[:, None] + 1e-7)
     x = torch.cat([feat[ia], feat[ib], (tn[ia] * dh).sum(-1, keepdim=True), (tn[ib] * dh).sum(-1, keepdim=True),
                    (tn[ia] * tn[ib]).sum(-1, keepdim=True), dn[:, None]], -1)
-    for i in range(3):
+    for i in range(2):
         x = ref_model.res_layer(x, sd, f"res_layers.{i}")
-    np.testing.assert_allclose(x3.cpu().numpy(), x.numpy(), rtol=1e-4, atol=2e-5)
+    F = torch.nn.functional
+    want = torch.cat([F.linear(x, sd["res_layers.2.fc1.weight"], sd["res_layers.2.fc1.bias"]),
+                      F.linear(x, sd["res_layers.2.fc0.weight"], sd["res_layers.2.fc0.bias"] + sd["res_layers.2.fc2.bias"])], -1)
+    np.testing.assert_allclose(t_dev.cpu().numpy(), want.numpy(), rtol=1e-4, atol=3e-5)
 
 
 @pytest.mark.parametrize("impl", ["tc", "simt"])
@@ -76,7 +80,7 @@ def test_encode_sample_dense_philox_and_head_mask(impl):
     n = 96
     m, pc, nrm, feat = _setup(n, 4)
     with torch.no_grad():
-        table = m.preproject(feat.to(DEV))
+        table = _table(m, feat, impl)
         b_seed, t_seed = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, seed=1234567890123, impl=impl)
         u = philox.pair_uniforms(1234567890123, n * n)
         b_inj, t_inj = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, uniforms=_t(u), impl=impl)
@@ -86,6 +90,10 @@ def test_encode_sample_dense_philox_and_head_mask(impl):
     assert torch.equal(b_seed, b_inj) and torch.equal(t_seed, t_inj)       # kernel Philox == oracle Philox
     assert torch.equal(b_idx, b_inj)                                        # dense enumeration == explicit list
     assert none_tail is None and torch.equal(b_tr[:, :2], b_inj[:, :2]) and not b_tr[:, 2:].any()
+
+
+def _table(m, feat, impl):
+    return m.tc_preproject(feat.to(DEV)) if impl == "tc" else m.preproject(feat.to(DEV))
 
 
 def _vote_case(n, p, seed, dense=False):

@@ -83,3 +83,66 @@ def test_unsupported_architecture_fails_loudly():
     m = model.PPFEncoder(ppffcs=[84, 64, 32, 16], out_dim=141)
     with pytest.raises(NotImplementedError):
         m.weight_blob(torch.device("cpu"))
+
+
+# ---------------------------------------------------------------------------------------
+# tcgen05 encoder blob (cppf_b200/model.py:pack_tc_weights, csrc/encode_tc.cu "chain algebra"): emulate the
+# kernel's 4 steps in numpy straight from the packed blob and compare with the oracle's layer-by-layer stack.
+def _uncanon(block, n, k):
+    """[K/4][N][4] -> [N, K]"""
+    return block.reshape(k // 4, n, 4).transpose(1, 0, 2).reshape(n, k)
+
+
+def _tc_operand(blob, off, n, k):
+    hi = _uncanon(blob[off:off + n * k], n, k)
+    lo = _uncanon(blob[off + n * k:off + 2 * n * k], n, k)
+    assert not (hi.view(np.uint32) & 0x1FFF).any()                 # hi is exactly representable in tf32
+    return hi.astype(np.float64) + lo.astype(np.float64)
+
+
+def test_tc_blob_chain_algebra_matches_oracle():
+    import torch
+
+    from cppf_b200 import model
+    from oracle import ref_model
+
+    torch.manual_seed(3)
+    m = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.7)
+    sd = m.state_dict()
+    blob = model.pack_tc_weights(sd)
+    rng = np.random.default_rng(0)
+    n, p = 50, 400
+    feat = rng.standard_normal((n, 40)).astype(np.float32)
+    ppf = rng.standard_normal((p, 4)).astype(np.float32)
+    ia, ib = rng.integers(0, n, p), rng.integers(0, n, p)
+    TAB, OFF_S = 192, 40 * 192 + 192
+    pre_w = blob[:40 * TAB].reshape(40, TAB).astype(np.float64)
+    pre_b = blob[40 * TAB:40 * TAB + TAB].astype(np.float64)
+    table = feat.astype(np.float64) @ pre_w + pre_b
+    ta, tb = table[ia, :96], table[ib, 96:]
+    o = OFF_S
+    wp = _tc_operand(blob, o, 96, 8); o += 2 * 96 * 8
+    ws1 = _tc_operand(blob, o, 64, 32); o += 2 * 64 * 32
+    ws2 = _tc_operand(blob, o, 32, 32); o += 2 * 32 * 32
+    wh = _tc_operand(blob, o, 112, 32); o += 2 * 112 * 32
+    wr = _tc_operand(blob, o, 48, 32); o += 2 * 48 * 32
+    bias = blob[o:o + 256].astype(np.float64)
+    assert o + 256 == blob.size
+    assert not wp[:, 4:].any()                                      # K padding of the ppf operand
+    d = np.concatenate([ppf, np.zeros((p, 4), np.float32)], 1).astype(np.float64) @ wp.T          # step 0
+    h = np.maximum(d[:, :32] + ta[:, :32] + tb[:, :32], 0)
+    d[:, 32:96] += h @ ws1.T                                                                      # step 1
+    u = np.maximum(d[:, 32:64] + ta[:, 32:64] + tb[:, 32:64], 0)
+    d[:, 64:96] += u @ ws2.T                                                                      # step 2
+    t = d[:, 64:96] + ta[:, 64:96] + tb[:, 64:96]
+    a3 = np.concatenate([np.maximum(t[:, :16], 0), t[:, 16:]], 1)
+    heads = a3 @ wh.T + bias[:112]                                                                # step 3
+    right = a3 @ wr.T + bias[112:160]
+    got = np.concatenate([heads[:, :100], right[:, :36], heads[:, 100:105]], 1)                   # reference column order
+    x = torch.from_numpy(np.concatenate([feat[ia], feat[ib], ppf], 1))
+    want = ref_model.pair_mlp(x, {k: v for k, v in sd.items()}).numpy()
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+    assert not heads[:, 105:].any() and not right[:, 36:].any()     # zero padding columns stay zero
