@@ -54,12 +54,40 @@ struct VotePParams {
     int n_rots, gx, gy, gz, adaptive;
 };
 
+constexpr int kVoteThreads = 1024;
+constexpr int kVoteQueue = 64;                     // per-warp ring of in-bounds candidates (float4 slots)
+
+// trilinear splat of one in-bounds candidate at grid coordinates g -- models/voting.py:40-63 with
+// prob == 1 (nocs/inference.py:201), weights rounded to 2^-14
+__device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float gxf, float gyf, float gzf, int gyz, int gz) {
+    const int fx = (int)gxf, fy = (int)gyf, fz = (int)gzf;                     // :40
+    const float rx = gxf - floorf(gxf), ry = gyf - floorf(gyf), rz = gzf - floorf(gzf);
+    const float wx0 = 1.f - rx, wy0 = 1.f - ry, wz0 = 1.f - rz;
+    unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
+    atomicAdd(cell, __float2uint_rn(wx0 * wy0 * wz0 * kFixScale));
+    atomicAdd(cell + 1, __float2uint_rn(wx0 * wy0 * rz * kFixScale));
+    atomicAdd(cell + gz, __float2uint_rn(wx0 * ry * wz0 * kFixScale));
+    atomicAdd(cell + gz + 1, __float2uint_rn(wx0 * ry * rz * kFixScale));
+    atomicAdd(cell + gyz, __float2uint_rn(rx * wy0 * wz0 * kFixScale));
+    atomicAdd(cell + gyz + 1, __float2uint_rn(rx * wy0 * rz * kFixScale));
+    atomicAdd(cell + gyz + gz, __float2uint_rn(rx * ry * wz0 * kFixScale));
+    atomicAdd(cell + gyz + gz + 1, __float2uint_rn(rx * ry * rz * kFixScale));
+}
+
+// Two phases per warp, decoupled by a shared-memory ring:
+//   phase 1 (one lane = one pair, all lanes walk their circle together): candidate position and the
+//            reference's in-bounds test; the ~45 % of candidates that pass are appended to the warp's ring
+//            with a ballot + popc prefix;
+//   phase 2 (whenever 32 candidates are queued): one lane = one queued candidate -> 8 shared-memory atomics.
+// Without the ring the splat runs under the divergence of the in-bounds test (about a third of the lanes
+// active); with it the atomics always issue from full warps.
 template <bool IDX64, bool BINS>
-__global__ void __launch_bounds__(1024, 1) vote_private_kernel(const VotePParams prm) {
+__global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const VotePParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tab = reinterpret_cast<float2*>(smem_raw);
     float* s_lut = reinterpret_cast<float*>(s_tab + kRotTabP);
-    unsigned* s_grid = reinterpret_cast<unsigned*>(s_lut + 64);
+    float4* s_queue = reinterpret_cast<float4*>(s_lut + 64);
+    unsigned* s_grid = reinterpret_cast<unsigned*>(s_queue + (kVoteThreads / 32) * kVoteQueue);
     __shared__ unsigned s_tally;
     const int cells = prm.gx * prm.gy * prm.gz;
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
@@ -69,13 +97,17 @@ __global__ void __launch_bounds__(1024, 1) vote_private_kernel(const VotePParams
     __syncthreads();
 
     const int gyz = prm.gy * prm.gz, gz = prm.gz;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float4* queue = s_queue + (threadIdx.x >> 5) * kVoteQueue;
     const float cx = __ldg(prm.corner), cy = __ldg(prm.corner + 1), cz = __ldg(prm.corner + 2);
     const unsigned worst_batch = (unsigned)blockDim.x * (unsigned)prm.n_rots;
     const long long n_batches = (prm.n_pairs + blockDim.x - 1) / blockDim.x;
 
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
         const long long p = batch * blockDim.x + threadIdx.x;
-        unsigned voted = 0;
+        int n = 0;
+        f3 c = {0.f, 0.f, 0.f}, x = c, y = c;
         if (p < prm.n_pairs) {
             int ia, ib;
             pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
@@ -92,40 +124,48 @@ __global__ void __launch_bounds__(1024, 1) vote_private_kernel(const VotePParams
             const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
             f3 ab, ex;
             if (pair_frame(a, b, ab, ex)) {                                    // voting.py:21
-                const f3 c = a - ab * mu;                                      // :23
-                const f3 x = ex * nu;                                          // :28
-                const f3 y = cross3(x, ab);                                    // :29
-                int n = prm.n_rots;
+                c = a - ab * mu;                                               // :23
+                x = ex * nu;                                                   // :28
+                y = cross3(x, ab);                                             // :29
+                n = prm.n_rots;
                 if (prm.adaptive) n = adaptive_rots(nu, prm.res, prm.n_rots);  // :31
-                const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
-                for (int i = 0; i < n; ++i) {
-                    const float2 cs = tab[i];
-                    const f3 off = x * cs.x + y * cs.y;                        // :34
-                    const float gxf = div_by(c.x + off.x - cx, prm.res, prm.inv_res);   // :35
-                    const float gyf = div_by(c.y + off.y - cy, prm.res, prm.inv_res);
-                    const float gzf = div_by(c.z + off.z - cz, prm.res, prm.inv_res);
-                    if (gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= prm.hx || gyf >= prm.hy || gzf >= prm.hz)
-                        continue;                                              // :36-39
-                    const int fx = (int)gxf, fy = (int)gyf, fz = (int)gzf;     // :40
-                    const float rx = gxf - floorf(gxf), ry = gyf - floorf(gyf), rz = gzf - floorf(gzf);
-                    const float wx0 = 1.f - rx, wy0 = 1.f - ry, wz0 = 1.f - rz;
-                    unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
-                    // :47-63, weights rounded to 2^-14 (prob == 1: nocs/inference.py:201)
-                    atomicAdd(cell, __float2uint_rn(wx0 * wy0 * wz0 * kFixScale));
-                    atomicAdd(cell + 1, __float2uint_rn(wx0 * wy0 * rz * kFixScale));
-                    atomicAdd(cell + gz, __float2uint_rn(wx0 * ry * wz0 * kFixScale));
-                    atomicAdd(cell + gz + 1, __float2uint_rn(wx0 * ry * rz * kFixScale));
-                    atomicAdd(cell + gyz, __float2uint_rn(rx * wy0 * wz0 * kFixScale));
-                    atomicAdd(cell + gyz + 1, __float2uint_rn(rx * wy0 * rz * kFixScale));
-                    atomicAdd(cell + gyz + gz, __float2uint_rn(rx * ry * wz0 * kFixScale));
-                    atomicAdd(cell + gyz + gz + 1, __float2uint_rn(rx * ry * rz * kFixScale));
-                    ++voted;
-                }
+                if (n < 0) n = 0;
             }
         }
+        const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
+        const int n_max = __reduce_max_sync(0xffffffffu, n);
+        unsigned q_head = 0, q_tail = 0, voted = 0;                            // warp-uniform
+        for (int i = 0; i < n_max; ++i) {
+            bool inb = false;
+            float gxf = 0.f, gyf = 0.f, gzf = 0.f;
+            if (i < n) {
+                const float2 cs = tab[i];
+                const f3 off = x * cs.x + y * cs.y;                            // :34
+                gxf = div_by(c.x + off.x - cx, prm.res, prm.inv_res);          // :35
+                gyf = div_by(c.y + off.y - cy, prm.res, prm.inv_res);
+                gzf = div_by(c.z + off.z - cz, prm.res, prm.inv_res);
+                inb = !(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= prm.hx || gyf >= prm.hy || gzf >= prm.hz);   // :36-39
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, inb);
+            if (inb) queue[(q_tail + __popc(m & lt_mask)) & (kVoteQueue - 1)] = make_float4(gxf, gyf, gzf, 0.f);
+            q_tail += __popc(m);
+            if (q_tail - q_head >= 32u) {
+                __syncwarp();
+                const float4 g = queue[(q_head + lane) & (kVoteQueue - 1)];
+                splat_fixed(s_grid, g.x, g.y, g.z, gyz, gz);
+                q_head += 32u;
+                voted += 32u;
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        if (lane < (int)(q_tail - q_head)) {
+            const float4 g = queue[(q_head + lane) & (kVoteQueue - 1)];
+            splat_fixed(s_grid, g.x, g.y, g.z, gyz, gz);
+        }
+        voted += q_tail - q_head;
         // overflow guard: a cell can have received at most `tally` whole votes since the last flush
-        voted = __reduce_add_sync(0xffffffffu, voted);
-        if ((threadIdx.x & 31) == 0 && voted) atomicAdd(&s_tally, voted);
+        if (lane == 0 && voted) atomicAdd(&s_tally, voted);
         __syncthreads();
         const bool flush = s_tally + worst_batch + worst_batch / 8 > kFixBudget;   // (+1/8: rounding slack)
         __syncthreads();
@@ -416,7 +456,7 @@ using namespace cppf;
 extern "C" int64_t cppf_vote_scratch_bytes(int gx, int gy, int gz) { return (int64_t)gx * gy * gz * 8; }
 
 extern "C" int cppf_vote_private_max_cells(void) {
-    return (int)((220 * 1024 - kRotTabP * 8 - 64 * 4 - 64) / 4);
+    return (int)((220 * 1024 - kRotTabP * 8 - 64 * 4 - (kVoteThreads / 32) * kVoteQueue * 16 - 64) / 4);
 }
 
 extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut,
@@ -439,8 +479,8 @@ extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uin
                     (float)(1.0 / (double)res), float_ceil_p(0.01), float_ceil_p((double)gx - 1.01),
                     float_ceil_p((double)gy - 1.01), float_ceil_p((double)gz - 1.01), n_points, (long long)n_pairs,
                     n_rots, gx, gy, gz, adaptive};
-    const size_t smem = (size_t)kRotTabP * 8 + 64 * 4 + (size_t)cells * 4;
-    const int threads = 1024;
+    const size_t smem = (size_t)kRotTabP * 8 + 64 * 4 + (size_t)(kVoteThreads / 32) * kVoteQueue * 16 + (size_t)cells * 4;
+    const int threads = kVoteThreads;
     long long blocks = (n_pairs + threads - 1) / threads;
     if (blocks > sm_count()) blocks = sm_count();
     void (*kern)(const VotePParams);
