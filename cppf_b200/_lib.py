@@ -41,6 +41,9 @@ SIGNATURES = {
     "cppf_tc_table_cols": (_i, []),
     "cppf_tc_preproject": (_i, [_p, _p, _p, _i, _p]),
     "cppf_encode_sample_tc": (_i, [_p, _p, _p, _p, _p, _i, _i, _i64, _p, C.c_uint64, _i, _p, _p, _p, _p]),
+    "cppf_pe_blob_floats": (_i, []),
+    "cppf_knn": (_i, [_p, _i, _i, _p, _p]),
+    "cppf_point_encode": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "cppf_vote_scratch_bytes": (_i64, [_i, _i, _i]),
     "cppf_vote_private_max_cells": (_i, []),
     "cppf_vote_fast": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),

@@ -1,0 +1,397 @@
+// Point encoder: exact k-nearest-neighbour selection and the SPRIN
+// rotation-invariant convolution of models/model.py:46-77 + models/sprin.py:40-107, one warp per point.
+//
+//   cppf_knn            : for each point the k smallest exact squared distances (self included, like
+//                         torch.topk(dist, k, largest=False) at models/model.py:47), by a 4 x 8-bit radix
+//                         select on the float bits -- 5 sweeps over the cloud per query, no N x N matrix.
+//   cppf_point_encode   : models/model.py:63-77 for one neighbour list: neighbour features
+//                         [|p_k - p|, n_k . n] (:49-53), rifeat invariants (sprin.py:40-60), the kernel MLP
+//                         6 -> 32 -> 64 -> 32 -> 32 -> 32 with LayerNorm + ReLU between layers (sprin.py:63-71)
+//                         on 32-row warp tiles (register-tiled FFMA, activations in the warp's private
+//                         shared-memory buffers), the rank-32 contraction over the k neighbours (:98), the
+//                         64 -> 32 output Linear + LayerNorm (:99-101), GlobalInfoProp's 32 -> 8 Linear and the
+//                         max over all points (sprin.py:74-83, ordered-int atomic max: exact and order-free).
+//   cppf_point_glob     : writes the 8 global-max columns into every row of feat[N, 40].
+#include "encode.cuh"
+
+#include "../../include/cppf_b200.h"
+
+#include <math.h>
+
+namespace cppf {
+namespace pe {
+
+// ---- weight blob (floats); Linear matrices are K-MAJOR with columns permuted for the warp tile
+// (column j = og + 8c stored at og*NO + c, NO = cols/8; mlp_layout.h), biases permuted the same way
+constexpr int kW1 = 0;                       // [6][32]
+constexpr int kB1 = kW1 + 6 * 32;
+constexpr int kG1 = kB1 + 32;                // LayerNorm gamma / beta in natural order
+constexpr int kE1 = kG1 + 32;
+constexpr int kW2 = kE1 + 32;                // [32][64]
+constexpr int kB2 = kW2 + 32 * 64;
+constexpr int kG2 = kB2 + 64;
+constexpr int kE2 = kG2 + 64;
+constexpr int kW3 = kE2 + 64;                // [64][32]
+constexpr int kB3 = kW3 + 64 * 32;
+constexpr int kG3 = kB3 + 32;
+constexpr int kE3 = kG3 + 32;
+constexpr int kW4 = kE3 + 32;                // [32][32]
+constexpr int kB4 = kW4 + 32 * 32;
+constexpr int kG4 = kB4 + 32;
+constexpr int kE4 = kG4 + 32;
+constexpr int kW5 = kE4 + 32;                // [32][32]
+constexpr int kB5 = kW5 + 32 * 32;
+constexpr int kWo = kB5 + 32;                // outnet [64][32] k-major, natural columns (k = rank*2 + nbr feature)
+constexpr int kBo = kWo + 64 * 32;
+constexpr int kGo = kBo + 32;
+constexpr int kEo = kGo + 32;
+constexpr int kWa = kEo + 32;                // GlobalInfoProp linear [32][8] k-major
+constexpr int kBa = kWa + 32 * 8;
+constexpr int kBlobFloats = kBa + 8;
+
+constexpr int kWarps = 8;
+constexpr int kWarpFloats = 32 * XS + 64 * XS + 64 + 64;      // P[32][XS], Q[64][XS], nbr feats [2][32], contraction [64]
+constexpr float kLnEps = 1e-5f;                               // torch.nn.LayerNorm default
+
+__device__ __forceinline__ void load8(const float* w, float (&v)[8]) {
+    const float4 t0 = *reinterpret_cast<const float4*>(w);
+    const float4 t1 = *reinterpret_cast<const float4*>(w + 4);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+}
+
+// acc[i][c] += sum_k X[k][i] * W[k][c] for a 64-column layer (NO = 8)
+template <int K>
+__device__ __forceinline__ void tile_gemm8(const float* __restrict__ X, const float* __restrict__ W, float (&acc)[8][8]) {
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(X + k * XS);
+        const float4 a1 = *reinterpret_cast<const float4*>(X + k * XS + 4);
+        float w[8];
+        load8(W + k * 64, w);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(a[i], w[c], acc[i][c]);
+    }
+}
+
+// LayerNorm over the NF features of each row (lane = row) followed by ReLU, in place -- sprin.py:67-68
+template <int NF>
+__device__ __forceinline__ void layer_norm_relu(float* __restrict__ buf, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, int lane) {
+    float v[NF];
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+        v[j] = buf[j * XS + lane];
+        mean += v[j];
+    }
+    mean *= 1.f / NF;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+        const float d = v[j] - mean;
+        var = fmaf(d, d, var);
+    }
+    const float rstd = rsqrtf(var * (1.f / NF) + kLnEps);
+#pragma unroll
+    for (int j = 0; j < NF; ++j) buf[j * XS + lane] = fmaxf(fmaf((v[j] - mean) * rstd, gamma[j], beta[j]), 0.f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+struct Params {
+    const float* pc;
+    const float* nrm;
+    const long long* nbrs;     // [N][k] int64 (torch.topk indices)
+    const float* blob;
+    float* feat;               // [N][40]: columns 0:32 written here
+    float* glob;               // [8], pre-set to -inf
+    int n_points;
+    int k;
+};
+
+__global__ void __launch_bounds__(kWarps * 32, 1) point_encode_kernel(const Params prm) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW = smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* P = smem + kBlobFloats + warp * kWarpFloats;
+    float* Q = P + 32 * XS;
+    float* NF = Q + 64 * XS;                  // [2][32]
+    float* CT = NF + 64;                      // [64]
+    {
+        const float4* src = reinterpret_cast<const float4*>(prm.blob);
+        float4* dst = reinterpret_cast<float4*>(sW);
+        for (int i = threadIdx.x; i < kBlobFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int og = lane & 7, pb = (lane >> 3) * 8;
+    const float inv_k = 1.f / (float)prm.k;
+
+    for (int n = blockIdx.x * kWarps + warp; n < prm.n_points; n += gridDim.x * kWarps) {
+        const f3 ctr = ld3(prm.pc, n), nc = ld3(prm.nrm, n);
+        // neighbours lane and 32 + lane of this point (models/model.py:48,52: absolute coordinates, normals)
+        long long id[2];
+        f3 nb[2], nn[2];
+        bool ok[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            ok[h] = h * 32 + lane < prm.k;
+            id[h] = ok[h] ? __ldg(prm.nbrs + (long long)n * prm.k + h * 32 + lane) : 0;
+            nb[h] = ld3(prm.pc, id[h]);
+            nn[h] = ld3(prm.nrm, id[h]);
+        }
+        f3 mean;                              // sprin.py:51 torch.mean over the k neighbours
+        mean.x = warp_sum((ok[0] ? nb[0].x : 0.f) + (ok[1] ? nb[1].x : 0.f)) * inv_k;
+        mean.y = warp_sum((ok[0] ? nb[0].y : 0.f) + (ok[1] ? nb[1].y : 0.f)) * inv_k;
+        mean.z = warp_sum((ok[0] ? nb[0].z : 0.f) + (ok[1] ? nb[1].z : 0.f)) * inv_k;
+        float c0 = 0.f, c1 = 0.f;             // contraction accumulators of rank `lane`
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            if (h * 32 >= prm.k) break;
+            {   // rifeat (sprin.py:52-60) and the two neighbour features (models/model.py:49-53), lane = row
+                const f3 l1 = mean - nb[h], l2 = nb[h] - ctr, l3 = ctr - mean;
+                const float n1 = len3(l1), n2 = len3(l2), n3 = len3(l3);
+                float ri[6] = {n1, n2, n3, dot3(l1, l2) / (n1 * n2 + 1e-7f), dot3(l2, l3) / (n2 * n3 + 1e-7f),
+                               dot3(l3, l1) / (n3 * n1 + 1e-7f)};
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 6; ++q) Q[q * XS + lane] = ok[h] ? ri[q] : 0.f;
+                NF[lane] = ok[h] ? n2 : 0.f;                          // |p_k - p|   (rows beyond k contribute 0)
+                NF[32 + lane] = ok[h] ? dot3(nn[h], nc) : 0.f;        // n_k . n
+            }
+            __syncwarp();
+            {   // Linear(6, 32) -> LN -> ReLU
+                float acc[8][4];
+                zero_acc(acc);
+                tile_gemm<6, 4>(Q + pb, sW + kW1 + og * 4, 32, acc);
+                float bias[4];
+                WVec<4>::load(sW + kB1 + og * 4, bias);
+                tile_store<4>(P + pb, og, acc, bias, nullptr, 0, 0);
+                __syncwarp();
+                layer_norm_relu<32>(P, sW + kG1, sW + kE1, lane);
+                __syncwarp();
+            }
+            {   // Linear(32, 64) -> LN -> ReLU
+                float acc[8][8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+                tile_gemm8<32>(P + pb, sW + kW2 + og * 8, acc);
+                float bias[8];
+                load8(sW + kB2 + og * 8, bias);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = og + 8 * c;
+                    *reinterpret_cast<float4*>(Q + pb + j * XS) =
+                        make_float4(acc[0][c] + bias[c], acc[1][c] + bias[c], acc[2][c] + bias[c], acc[3][c] + bias[c]);
+                    *reinterpret_cast<float4*>(Q + pb + j * XS + 4) =
+                        make_float4(acc[4][c] + bias[c], acc[5][c] + bias[c], acc[6][c] + bias[c], acc[7][c] + bias[c]);
+                }
+                __syncwarp();
+                layer_norm_relu<64>(Q, sW + kG2, sW + kE2, lane);
+                __syncwarp();
+            }
+            {   // Linear(64, 32) -> LN -> ReLU
+                float acc[8][4];
+                zero_acc(acc);
+                tile_gemm<64, 4>(Q + pb, sW + kW3 + og * 4, 32, acc);
+                float bias[4];
+                WVec<4>::load(sW + kB3 + og * 4, bias);
+                tile_store<4>(P + pb, og, acc, bias, nullptr, 0, 0);
+                __syncwarp();
+                layer_norm_relu<32>(P, sW + kG3, sW + kE3, lane);
+                __syncwarp();
+            }
+            {   // Linear(32, 32) -> LN -> ReLU
+                float acc[8][4];
+                zero_acc(acc);
+                tile_gemm<32, 4>(P + pb, sW + kW4 + og * 4, 32, acc);
+                float bias[4];
+                WVec<4>::load(sW + kB4 + og * 4, bias);
+                tile_store<4>(Q + pb, og, acc, bias, nullptr, 0, 0);
+                __syncwarp();
+                layer_norm_relu<32>(Q, sW + kG4, sW + kE4, lane);
+                __syncwarp();
+            }
+            {   // Linear(32, 32): the rank-32 kernel of each neighbour
+                float acc[8][4];
+                zero_acc(acc);
+                tile_gemm<32, 4>(Q + pb, sW + kW5 + og * 4, 32, acc);
+                float bias[4];
+                WVec<4>::load(sW + kB5 + og * 4, bias);
+                tile_store<4>(P + pb, og, acc, bias, nullptr, 0, 0);
+                __syncwarp();
+            }
+            // einsum('bnkr,bnki->bnri') (sprin.py:98): lane = rank r, sum over this tile's rows
+#pragma unroll 8
+            for (int row = 0; row < 32; ++row) {
+                const float kv = P[lane * XS + row];
+                c0 = fmaf(kv, NF[row], c0);
+                c1 = fmaf(kv, NF[32 + row], c1);
+            }
+        }
+        __syncwarp();
+        CT[2 * lane] = c0;                    // flatten(-2): index r*2 + i
+        CT[2 * lane + 1] = c1;
+        __syncwarp();
+        float o = sW[kBo + lane];             // outnet Linear(64, 32), lane = output column   (sprin.py:99)
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) o = fmaf(CT[k], sW[kWo + k * 32 + lane], o);
+        const float m = warp_sum(o) * (1.f / 32.f);          // LayerNorm(32) across the lanes   (sprin.py:100-101)
+        const float d = o - m;
+        const float var = warp_sum(d * d) * (1.f / 32.f);
+        const float y = fmaf(d * rsqrtf(var + kLnEps), sW[kGo + lane], sW[kEo + lane]);
+        prm.feat[(long long)n * 40 + lane] = y;
+        // GlobalInfoProp (sprin.py:80-82): 8 columns, max over all points
+        float t = lane < 8 ? sW[kBa + lane] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const float yk = __shfl_sync(0xffffffffu, y, k);
+            if (lane < 8) t = fmaf(yk, sW[kWa + k * 8 + lane], t);
+        }
+        if (lane < 8) atomic_max_float(prm.glob + lane, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) point_glob_kernel(float* __restrict__ feat, const float* __restrict__ glob, int n_points) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_points * 8) feat[(long long)(i >> 3) * 40 + 32 + (i & 7)] = glob[i & 7];
+}
+
+__global__ void glob_init_kernel(float* glob) {
+    if (threadIdx.x < 8) glob[threadIdx.x] = -INFINITY;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k nearest neighbours by radix select on the bits of the exact squared distance (>= 0, so the float order is
+// the unsigned-integer order of the bits).  One warp per query; every sweep recomputes the distances with the
+// same expression, so the passes agree bit for bit.
+__device__ __forceinline__ unsigned d2_bits(f3 q, const float* __restrict__ pc, int j) {
+    const f3 p = ld3(pc, j);
+    const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+    return __float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+}
+
+constexpr int kKnnWarps = 8;
+
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __restrict__ pc, int n_points, int k,
+                                                              long long* __restrict__ out_idx) {
+    __shared__ unsigned s_hist[kKnnWarps][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned* hist = s_hist[warp];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int qi = blockIdx.x * kKnnWarps + warp; qi < n_points; qi += gridDim.x * kKnnWarps) {
+        const f3 q = ld3(pc, qi);
+        unsigned prefix = 0;                  // the bits of the k-th smallest distance found so far
+        int need = k;                         // rank of the wanted element among those matching the prefix
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0u;
+            __syncwarp();
+            for (int j = lane; j < n_points; j += 32) {
+                const unsigned b = d2_bits(q, pc, j);
+                if (pass == 0 || (b >> (shift + 8)) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+            }
+            __syncwarp();
+            unsigned cnt[8], mine = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cnt[i] = hist[lane * 8 + i];
+                mine += cnt[i];
+            }
+            unsigned incl = mine;             // inclusive scan of the per-lane totals
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned excl = incl - mine;
+            const bool here = (unsigned)need > excl && (unsigned)need <= incl;   // exactly one lane
+            int digit = 0, below = 0;
+            if (here) {
+                unsigned run = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if ((unsigned)need > run && (unsigned)need <= run + cnt[i]) {
+                        digit = lane * 8 + i;
+                        below = (int)run;
+                    }
+                    run += cnt[i];
+                }
+            }
+            const unsigned src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+            digit = __shfl_sync(0xffffffffu, digit, src);
+            below = __shfl_sync(0xffffffffu, below, src);
+            prefix = (prefix << 8) | (unsigned)digit;
+            need -= below;
+            __syncwarp();
+        }
+        // collection sweep: everything strictly below the threshold, then the first `need` ties in index order
+        const unsigned thr = prefix;
+        int n_lt = 0, n_eq = 0;
+        const int base_eq = k - need;         // ties are written after the strictly-smaller ones
+        long long* out = out_idx + (long long)qi * k;
+        for (int j0 = 0; j0 < n_points; j0 += 32) {
+            const int j = j0 + lane;
+            const unsigned b = j < n_points ? d2_bits(q, pc, j) : 0xFFFFFFFFu;
+            const bool lt = b < thr, eq = b == thr;
+            const unsigned m_lt = __ballot_sync(0xffffffffu, lt), m_eq = __ballot_sync(0xffffffffu, eq);
+            if (lt) out[n_lt + __popc(m_lt & lt_mask)] = j;
+            const int e = n_eq + __popc(m_eq & lt_mask);
+            if (eq && e < need) out[base_eq + e] = j;
+            n_lt += __popc(m_lt);
+            n_eq += __popc(m_eq);
+        }
+    }
+}
+
+}  // namespace pe
+}  // namespace cppf
+
+using namespace cppf;
+
+extern "C" int cppf_pe_blob_floats(void) { return pe::kBlobFloats; }
+
+extern "C" int cppf_knn(const float* pc, int n_points, int k, int64_t* out_idx, void* stream) {
+    if (n_points <= 0) return 0;
+    if (k <= 0 || k > n_points) return (int)cudaErrorInvalidValue;
+    int blocks = (n_points + pe::kKnnWarps - 1) / pe::kKnnWarps;
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    pe::knn_kernel<<<blocks, pe::kKnnWarps * 32, 0, (cudaStream_t)stream>>>(pc, n_points, k,
+                                                                             reinterpret_cast<long long*>(out_idx));
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cppf_point_encode(const float* pc, const float* nrm, const int64_t* nbrs, const float* pe_blob, float* feat,
+                                 float* glob_scratch, int n_points, int k, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_points <= 0) return 0;
+    if (k <= 0 || k > 64) return (int)cudaErrorInvalidValue;
+    pe::glob_init_kernel<<<1, 32, 0, stream>>>(glob_scratch);
+    CPPF_LAUNCH_CHECK();
+    pe::Params prm{pc, nrm, reinterpret_cast<const long long*>(nbrs), pe_blob, feat, glob_scratch, n_points, k};
+    const size_t smem = sizeof(float) * ((size_t)pe::kBlobFloats + (size_t)pe::kWarps * pe::kWarpFloats);
+    int blocks = (n_points + pe::kWarps - 1) / pe::kWarps;
+    if (blocks > sm_count()) blocks = sm_count();
+    CPPF_RETURN_IF(cudaFuncSetAttribute(pe::point_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pe::point_encode_kernel<<<blocks, pe::kWarps * 32, smem, stream>>>(prm);
+    CPPF_LAUNCH_CHECK();
+    pe::point_glob_kernel<<<(n_points * 8 + 255) / 256, 256, 0, stream>>>(feat, glob_scratch, n_points);
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}

@@ -58,20 +58,34 @@ constexpr int kVoteThreads = 1024;
 constexpr int kVoteQueue = 64;                     // per-warp ring of in-bounds candidates (float4 slots)
 
 // trilinear splat of one in-bounds candidate at grid coordinates g -- models/voting.py:40-63 with
-// prob == 1 (nocs/inference.py:201), weights rounded to 2^-14
+// prob == 1 (nocs/inference.py:201).  Each corner weight is rounded ONCE to 2^-14: the last product is an
+// FFMA onto 2^23, whose low mantissa bits are then the rounded fixed-point weight (no F2I on the XU pipe).
 __device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float gxf, float gyf, float gzf, int gyz, int gz) {
     const int fx = (int)gxf, fy = (int)gyf, fz = (int)gzf;                     // :40
     const float rx = gxf - floorf(gxf), ry = gyf - floorf(gyf), rz = gzf - floorf(gzf);
-    const float wx0 = 1.f - rx, wy0 = 1.f - ry, wz0 = 1.f - rz;
+    const float wx0 = 1.f - rx, wy0 = 1.f - ry;
+    const float z1 = rz * kFixScale, z0 = (1.f - rz) * kFixScale;
+    const float w00 = wx0 * wy0, w01 = wx0 * ry, w10 = rx * wy0, w11 = rx * ry;
+    constexpr float kMagic = 8388608.f;                                        // 2^23
+    constexpr unsigned kMagicBits = 0x4B000000u;
     unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
-    atomicAdd(cell, __float2uint_rn(wx0 * wy0 * wz0 * kFixScale));
-    atomicAdd(cell + 1, __float2uint_rn(wx0 * wy0 * rz * kFixScale));
-    atomicAdd(cell + gz, __float2uint_rn(wx0 * ry * wz0 * kFixScale));
-    atomicAdd(cell + gz + 1, __float2uint_rn(wx0 * ry * rz * kFixScale));
-    atomicAdd(cell + gyz, __float2uint_rn(rx * wy0 * wz0 * kFixScale));
-    atomicAdd(cell + gyz + 1, __float2uint_rn(rx * wy0 * rz * kFixScale));
-    atomicAdd(cell + gyz + gz, __float2uint_rn(rx * ry * wz0 * kFixScale));
-    atomicAdd(cell + gyz + gz + 1, __float2uint_rn(rx * ry * rz * kFixScale));
+    atomicAdd(cell, __float_as_uint(fmaf(w00, z0, kMagic)) - kMagicBits);
+    atomicAdd(cell + 1, __float_as_uint(fmaf(w00, z1, kMagic)) - kMagicBits);
+    atomicAdd(cell + gz, __float_as_uint(fmaf(w01, z0, kMagic)) - kMagicBits);
+    atomicAdd(cell + gz + 1, __float_as_uint(fmaf(w01, z1, kMagic)) - kMagicBits);
+    atomicAdd(cell + gyz, __float_as_uint(fmaf(w10, z0, kMagic)) - kMagicBits);
+    atomicAdd(cell + gyz + 1, __float_as_uint(fmaf(w10, z1, kMagic)) - kMagicBits);
+    atomicAdd(cell + gyz + gz, __float_as_uint(fmaf(w11, z0, kMagic)) - kMagicBits);
+    atomicAdd(cell + gyz + gz + 1, __float_as_uint(fmaf(w11, z1, kMagic)) - kMagicBits);
+}
+
+__device__ __forceinline__ void st_shared_f4(unsigned addr, float x, float y, float z) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // Two phases per warp, decoupled by a shared-memory ring:
@@ -99,7 +113,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     const int gyz = prm.gy * prm.gz, gz = prm.gz;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    float4* queue = s_queue + (threadIdx.x >> 5) * kVoteQueue;
+    const unsigned q_addr = (unsigned)__cvta_generic_to_shared(s_queue + (threadIdx.x >> 5) * kVoteQueue);
     const float cx = __ldg(prm.corner), cy = __ldg(prm.corner + 1), cz = __ldg(prm.corner + 2);
     const unsigned worst_batch = (unsigned)blockDim.x * (unsigned)prm.n_rots;
     const long long n_batches = (prm.n_pairs + blockDim.x - 1) / blockDim.x;
@@ -132,26 +146,23 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
                 if (n < 0) n = 0;
             }
         }
-        const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
+        const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);     // row n; reads past column n stay inside the table
         const int n_max = __reduce_max_sync(0xffffffffu, n);
         unsigned q_head = 0, q_tail = 0, voted = 0;                            // warp-uniform
         for (int i = 0; i < n_max; ++i) {
-            bool inb = false;
-            float gxf = 0.f, gyf = 0.f, gzf = 0.f;
-            if (i < n) {
-                const float2 cs = tab[i];
-                const f3 off = x * cs.x + y * cs.y;                            // :34
-                gxf = div_by(c.x + off.x - cx, prm.res, prm.inv_res);          // :35
-                gyf = div_by(c.y + off.y - cy, prm.res, prm.inv_res);
-                gzf = div_by(c.z + off.z - cz, prm.res, prm.inv_res);
-                inb = !(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= prm.hx || gyf >= prm.hy || gzf >= prm.hz);   // :36-39
-            }
+            const float2 cs = tab[i];
+            const f3 off = x * cs.x + y * cs.y;                                // :34
+            const float gxf = div_by(c.x + off.x - cx, prm.res, prm.inv_res);  // :35
+            const float gyf = div_by(c.y + off.y - cy, prm.res, prm.inv_res);
+            const float gzf = div_by(c.z + off.z - cz, prm.res, prm.inv_res);
+            const bool inb = i < n && !(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= prm.hx || gyf >= prm.hy ||
+                                        gzf >= prm.hz);                        // :36-39
             const unsigned m = __ballot_sync(0xffffffffu, inb);
-            if (inb) queue[(q_tail + __popc(m & lt_mask)) & (kVoteQueue - 1)] = make_float4(gxf, gyf, gzf, 0.f);
+            if (inb) st_shared_f4(q_addr + (((q_tail + __popc(m & lt_mask)) & (kVoteQueue - 1)) << 4), gxf, gyf, gzf);
             q_tail += __popc(m);
             if (q_tail - q_head >= 32u) {
                 __syncwarp();
-                const float4 g = queue[(q_head + lane) & (kVoteQueue - 1)];
+                const float4 g = ld_shared_f4(q_addr + (((q_head + lane) & (kVoteQueue - 1)) << 4));
                 splat_fixed(s_grid, g.x, g.y, g.z, gyz, gz);
                 q_head += 32u;
                 voted += 32u;
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
         }
         __syncwarp();
         if (lane < (int)(q_tail - q_head)) {
-            const float4 g = queue[(q_head + lane) & (kVoteQueue - 1)];
+            const float4 g = ld_shared_f4(q_addr + (((q_head + lane) & (kVoteQueue - 1)) << 4));
             splat_fixed(s_grid, g.x, g.y, g.z, gyz, gz);
         }
         voted += q_tail - q_head;

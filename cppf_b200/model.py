@@ -339,6 +339,30 @@ class SparseSO3Conv(nn.Module):
         self.layer_norm = nn.LayerNorm(n_out) if layer_norm else None
 
 
+def pack_pe_weights(sd) -> np.ndarray:
+    """Pack a PointEncoder ``state_dict`` (spfcs=[32,64,32,32], rank 32, 2 neighbour features, out_dim 32) for the
+    fused kNN+SPRIN kernel; layout = the k* constants of csrc/point_encoder.cu."""
+    g = lambda k: sd[k].detach().to("cpu", torch.float32).numpy()
+    parts = []
+    dims = [(6, 32), (32, 64), (64, 32), (32, 32), (32, 32)]
+    for li, (seq, (din, dout)) in enumerate(zip((0, 3, 6, 9, 12), dims)):
+        w, b = g(f"spconvs.0.kernel.{seq}.weight"), g(f"spconvs.0.kernel.{seq}.bias")
+        if w.shape != (dout, din):
+            raise NotImplementedError(f"fused point encoder needs spfcs=[32,64,32,32], rank 32; kernel.{seq} is {w.shape}")
+        no = dout // 8
+        parts += [_perm_cols(w.T, no), _perm_cols(b[None], no)]
+        if li < 4:
+            parts += [g(f"spconvs.0.kernel.{seq + 1}.weight"), g(f"spconvs.0.kernel.{seq + 1}.bias")]
+    wo = g("spconvs.0.outnet.weight")
+    if wo.shape != (32, 64) or "spconvs.0.layer_norm.weight" not in sd or g("aggrs.0.linear.weight").shape != (8, 32):
+        raise NotImplementedError("fused point encoder needs num_nbr_feats=2, out_dim=32 with layer_norm")
+    parts += [wo.T, g("spconvs.0.outnet.bias"), g("spconvs.0.layer_norm.weight"), g("spconvs.0.layer_norm.bias"),
+              g("aggrs.0.linear.weight").T, g("aggrs.0.linear.bias")]
+    blob = np.concatenate([np.ascontiguousarray(q, dtype=np.float32).reshape(-1) for q in parts])
+    assert blob.size == _lib.lib().cppf_pe_blob_floats(), blob.size
+    return blob
+
+
 class PointEncoder(nn.Module):
     """Drop-in for reference ``models/model.py:34-77`` (num_layers=1 as at every call site,
     nocs/inference.py:82).  O(N k) work; this round it is composed from torch CUDA ops on
@@ -349,8 +373,52 @@ class PointEncoder(nn.Module):
         if num_layers != 1:
             raise NotImplementedError("every reference call site uses num_layers=1 (nocs/inference.py:82)")
         self.k = k
+        self.use_fused = True           # False forces the torch-op composition (used by tests as a cross-check)
         self.spconvs = nn.ModuleList([SparseSO3Conv(32, num_nbr_feats, out_dim, *spfcs)])
         self.aggrs = nn.ModuleList([GlobalInfoProp(out_dim, out_dim // 4)])
+
+    # ---- fused sm_100a path (csrc/point_encoder.cu)
+    def _fused_ok(self):
+        c = self.spconvs[0]
+        return (self.k <= 64 and c.rank == 32 and c.layer_norm is not None and tuple(c.outnet.weight.shape) == (32, 64)
+                and [tuple(m.weight.shape) for m in c.kernel if isinstance(m, nn.Linear)] ==
+                [(32, 6), (64, 32), (32, 64), (32, 32), (32, 32)])
+
+    def pe_blob(self, device) -> torch.Tensor:
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if getattr(self, "_peblob", None) is None or self._peblob_key != key:
+            self._peblob = torch.from_numpy(pack_pe_weights(self.state_dict())).to(device)
+            self._peblob_key = key
+        return self._peblob
+
+    def knn(self, pc: torch.Tensor) -> torch.Tensor:
+        """Exact k nearest neighbours of every point (self included), [N,k] int64, unordered -- the index set of
+        torch.topk(dist, k, largest=False, sorted=False) (models/model.py:47) computed without the N x N matrix."""
+        n = pc.shape[0]
+        out = torch.empty((n, self.k), dtype=torch.int64, device=pc.device)
+        with torch.cuda.device(pc.device):
+            _lib.check(_lib.lib().cppf_knn(pc.data_ptr(), n, self.k, out.data_ptr(), _stream_ptr(pc.device)), "cppf_knn")
+        return out
+
+    def encode_fused(self, pc: torch.Tensor, pc_normal: torch.Tensor, nbrs_idx: torch.Tensor = None) -> torch.Tensor:
+        """pc, pc_normal [N,3] CUDA float32, nbrs_idx [N,k] int64 (None -> exact kNN) -> feat [N,40]."""
+        _no_grad_only(pc, pc_normal, *self.parameters())
+        if pc.device.type != "cuda":
+            raise RuntimeError("cppf_b200.PointEncoder's fused path runs on CUDA tensors only (no CPU fallback)")
+        pc, pc_normal = _f32c(pc, pc.device), _f32c(pc_normal, pc.device)
+        n = pc.shape[0]
+        if nbrs_idx is None:
+            nbrs_idx = self.knn(pc)
+        nbrs_idx = nbrs_idx.to(torch.int64).contiguous()
+        if nbrs_idx.shape != (n, self.k):
+            raise ValueError(f"nbrs_idx must be [N,{self.k}]")
+        feat = torch.empty((n, 40), dtype=torch.float32, device=pc.device)
+        glob = torch.empty(8, dtype=torch.float32, device=pc.device)
+        with torch.cuda.device(pc.device):
+            _lib.check(_lib.lib().cppf_point_encode(pc.data_ptr(), pc_normal.data_ptr(), nbrs_idx.data_ptr(),
+                                                    self.pe_blob(pc.device).data_ptr(), feat.data_ptr(), glob.data_ptr(), n,
+                                                    self.k, _stream_ptr(pc.device)), "cppf_point_encode")
+        return feat
 
     def forward(self, pc, pc_normal, dist):
         """models/model.py:46-61: k nearest (self included) from the caller's distance matrix."""
@@ -361,7 +429,9 @@ class PointEncoder(nn.Module):
     def forward_nbrs(self, pc, pc_normal, nbrs_idx):
         """models/model.py:63-77.  pc,pc_normal [B,N,3], nbrs_idx [B,N,K] -> [B,N,out+out//4]."""
         _no_grad_only(pc, pc_normal)
-        with torch.no_grad():
+        if self.use_fused and pc.is_cuda and pc.shape[0] == 1 and self._fused_ok():
+            return self.encode_fused(pc[0], pc_normal[0], nbrs_idx[0])[None]
+        with torch.no_grad():       # generic shapes (other spfcs / k > 64 / batches): composed from torch ops on the device
             conv, aggr = self.spconvs[0], self.aggrs[0]
             b_idx = torch.arange(pc.shape[0], device=pc.device)[:, None, None]
             nb = pc[b_idx, nbrs_idx]                                             # [B,N,K,3] absolute coords

@@ -92,8 +92,14 @@ class PoseEstimator:
     # ------------------------------------------------------------------ stages
     @torch.no_grad()
     def point_features(self, pc, nrm):
-        dist = torch.cdist(pc[None], pc[None])                                      # nocs/inference.py:180
-        return self.pe(pc[None], nrm[None], dist)[0]                                # :181
+        """nocs/inference.py:180-181.  The reference materialises torch.cdist (N x N) and takes topk of it; the
+        fused path selects the same k neighbours from exact distances in-kernel (cppf_knn) and runs the SPRIN
+        convolution in one kernel.  Neighbour sets can differ from cdist's only on near-ties of the k-th
+        distance (cdist uses the less accurate |x|^2 + |y|^2 - 2 x.y form, SURVEY.md section 8a notes)."""
+        if self.pe._fused_ok():
+            return self.pe.encode_fused(pc, nrm)
+        dist = torch.cdist(pc[None], pc[None])
+        return self.pe(pc[None], nrm[None], dist)[0]
 
     @torch.no_grad()
     def estimate(self, pc_host: np.ndarray, nrm_host: np.ndarray, seed: int = 0, idxs=None, noise=None,

@@ -123,6 +123,19 @@ int cppf_sphere_count(const float* cand, int64_t n_cand, const float* sphere, in
  * literal == 0 is the intended 6-neighbour second difference. */
 int cppf_findpeak(const float* grid, float* out, int width, int gx, int gy, int gz, int literal, void* stream);
 
+/* ---- point encoder (models/model.py:34-77 PointEncoder, models/sprin.py:40-107) -------------------
+ * cppf_knn replaces torch.cdist + torch.topk(dist, k, largest=False, sorted=False) (nocs/inference.py:180,
+ * models/model.py:47): out_idx [n_points, k] int64, the k points with the smallest exact squared distance
+ * (self included), unordered; ties at the k-th distance resolve to the lowest indices.
+ * cppf_point_encode replaces PointEncoder.forward_nbrs (models/model.py:63-77) for the reference
+ * configuration (spfcs=[32,64,32,32], rank 32, 2 neighbour features, out_dim 32, k <= 64): feat
+ * [n_points, 40] = [SPRIN conv + LayerNorm (32) | global max of the 8-column GlobalInfoProp linear].
+ * pe_blob: cppf_pe_blob_floats() floats (cppf_b200/model.py:pack_pe_weights); glob_scratch: 8 floats. */
+int cppf_pe_blob_floats(void);
+int cppf_knn(const float* pc, int n_points, int k, int64_t* out_idx, void* stream);
+int cppf_point_encode(const float* pc, const float* nrm, const int64_t* nbrs, const float* pe_blob, float* feat,
+                      float* glob_scratch, int n_points, int k, void* stream);
+
 /* ==== fused per-object path ==================================================
  * The same reference lines, re-cut so that logits, (mu,nu) floats and the [P,72,3]
  * candidate dump never reach HBM.  Per pair the path keeps 4 bin bytes and 5 tail floats.
