@@ -18,6 +18,7 @@ the timed region.
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -43,7 +44,7 @@ TRAFFIC_NCU = {"encode_sample": 2.608128e6 + 347.031296e6, "vote": 67.345152e6 +
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-points", type=int, default=4096)
@@ -73,7 +74,9 @@ def workload_config(args):
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms in the background; started before the warm-up steps (the tool needs ~100 ms to
+    come up) and filtered to the samples whose timestamp falls inside the timed region [t0, t1]."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -81,12 +84,13 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -98,18 +102,23 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, all_sm = [], [], set(), []
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                c, m = float(r[1]), float(r[2])
             except Exception:
                 continue
+            all_sm.append(c)
+            if t0 is not None and not (t0 <= ts <= t1):
+                continue
+            sm.append(c); mx.append(m)
             for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if "Active" in cell and "Not" not in cell:
                     reasons.add(name)
         if sm:
-            hi = [v for v in sm if v >= 0.5 * max(sm)]
-            out = {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                   "samples_total": len(all_sm)}
         return out
 
 
@@ -230,45 +239,74 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    cells = [int(np.prod(synth.vote_grid_geometry(p, synth.BOTTLE["res"])[1])) for p, _ in clouds]
     inject = [None] * n_obj
     if args.votes == "trained_like" and args.path == "fused":
         inject = [synth.trained_like_bins_dense_torch(torch.from_numpy(p).to(dev), synth.BOTTLE) for p, _ in clouds]
 
+    L = _lib.lib()
+    timing = L.cppf_timing_create() if args.path == "fused" else None
+    stage_names = [L.cppf_timing_stage_name(i).decode() for i in range(L.cppf_timing_stages())]
+
     def run(leg, votes_injected=True):
-        """leg 'hbm': clouds already on the device; leg 'e2e': pinned host buffers in, pose record out."""
+        """leg 'hbm': clouds already on the device; leg 'e2e': pinned host buffers in, pose record out.
+        The fused path enqueues every step with ONE library call (cppf_pose_fused) and never waits for the GPU
+        inside the loop: the records come back through pinned buffers and are read after the last enqueue."""
         records = []
+        sampler = ClockSampler(local) if rank == 0 else None
         resident = [(p.to(dev), q.to(dev)) for p, q in pinned] if leg == "hbm" else None
         timers = {}
-        est.timers = timers
         if args.path == "fused":
-            step = lambda a, b, seed: est.estimate_fused(a, b, seed=seed, inject_bins=inject[seed] if votes_injected else None)
+            def step(a, b, seed):
+                return est.enqueue_fused(a, b, seed=seed, inject_bins=inject[seed] if votes_injected else None,
+                                         max_cells=cells[seed])
         else:
+            est.timers = timers
             step = lambda a, b, seed: est.estimate(a, b, seed=seed)
         for s in range(args.warmup):
             src = resident[s] if leg == "hbm" else pinned[s]
-            step(src[0], src[1], seed=s)
+            r = step(src[0], src[1], seed=s)
+            if args.path == "fused":
+                r.result()
         timers.clear()
+        if timing:
+            L.cppf_timing_collect(timing, (C.c_float * len(stage_names))())      # drop the warm-up marks
+        est.timing = timing
         barrier()
         l0 = _lib.launch_count()
-        sampler = ClockSampler(local) if rank == 0 else None
+        t0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        pend = []
         for s in range(args.warmup, n_obj):
             src = resident[s] if leg == "hbm" else pinned[s]
-            records.append(step(src[0], src[1], seed=s)["record"])
+            pend.append(step(src[0], src[1], seed=s))
+        records = [(p.result() if args.path == "fused" else p)["record"] for p in pend]
         rec = np.stack(records)
         ids = [rank * args.steps + i for i in range(args.steps)]
         shard.gather_records(ids, rec, world * args.steps, device=dev)    # the one collective: pose hypotheses
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t0, time.time()) if sampler else None
         launches = _lib.launch_count() - l0
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if dist_on:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         est.timers = None
-        return float(t.item()), launches, clocks, timers
+        est.timing = None
+        stage_ms = {}
+        if timing:
+            acc = (C.c_float * len(stage_names))()
+            calls = L.cppf_timing_collect(timing, acc)
+            if calls > 0:
+                stage_ms = {nm: {"avg_ms": acc[i] / calls, "launches": calls} for i, nm in enumerate(stage_names)}
+        else:
+            for name, evs in timers.items():
+                durs = [a.elapsed_time(b) for a, b in evs]
+                if durs:
+                    stage_ms[name] = {"avg_ms": sum(durs) / len(durs), "launches": len(durs)}
+        return float(t.item()), launches, clocks, stage_ms
 
     ms_hbm, launches, clocks, timers = run("hbm")
     ms_e2e, _, _, _ = run("e2e")
@@ -288,11 +326,7 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))      # kernels are timed inside a long step
         peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
-        kern = {}
-        for name, evs in timers.items():
-            durs = [a.elapsed_time(b) for a, b in evs]
-            if durs:
-                kern[name] = {"avg_ms": sum(durs) / len(durs), "launches": len(durs)}
+        kern = dict(timers)
         # Algorithmic work per launch.  Dense pairs are enumerated in-kernel (no index read).
         #   encode_sample : 24 B/pair written (4 bin bytes + 5 tail floats); 23 968 FLOP/pair canonical pair MLP
         #                   (models/model.py:12-23,87; 13.9 k executed after the per-point pre-projection of layer 0)

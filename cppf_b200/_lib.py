@@ -50,7 +50,28 @@ SIGNATURES = {
     "cppf_backvote_bins": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _f, _f, _i, _i64, _i, _i, _i, _i, _p]),
     "cppf_rot_hist": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i64, C.c_uint64, _f, _p]),
     "cppf_survivor_stats": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i64, _p]),
+    "cppf_pose_record_doubles": (_i, []),
+    "cppf_pose_workspace_bytes": (_i64, [_i, _i64, _i, _i, _i]),
+    "cppf_pose_fused": (_i, [_p, _p]),
+    "cppf_timing_create": (_p, []),
+    "cppf_timing_destroy": (None, [_p]),
+    "cppf_timing_stages": (_i, []),
+    "cppf_timing_stage_name": (C.c_char_p, [_i]),
+    "cppf_timing_collect": (_i, [_p, _p]),
 }
+
+
+class PoseArgs(C.Structure):
+    """struct cppf_pose_args of include/cppf_b200.h, field for field."""
+    _fields_ = [
+        ("struct_bytes", _i64),
+        ("pc", _p), ("nrm", _p), ("idx", _p), ("pe_blob", _p), ("tc_blob", _p), ("lut", _p), ("sphere", _p),
+        ("uniforms", _p), ("inject_bins", _p), ("workspace", _p), ("record", _p), ("timing", _p),
+        ("n_pairs", _i64), ("workspace_bytes", _i64), ("rot_subsample", _i64), ("seed", C.c_uint64),
+        ("n_points", _i), ("idx_is_64", _i), ("knn", _i), ("n_rots", _i), ("adaptive", _i), ("regress_right", _i),
+        ("n_sphere", _i), ("inject_cols", _i), ("max_cells", _i),
+        ("res", _f), ("tol", _f), ("cos_thr", _f),
+    ]
 
 
 def lib():

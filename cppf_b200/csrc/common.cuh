@@ -48,6 +48,17 @@ __device__ __forceinline__ f3 ld3(const float* __restrict__ p, int64_t i) {
     return {__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)};
 }
 
+// Vote-grid geometry of one object when it is derived on the device (cppf_pose_fused): the kernels of the
+// fused path read it from here instead of from their launch parameters, so the host never waits for it.
+struct Geom {
+    float corner[3];         // nocs/inference.py:194: pc.min(0)
+    int gx, gy, gz, cells;   // :195: int((max - min) / res) + 1
+    float hx, hy, hz;        // exact upper bounds of models/voting.py:36-39: float_ceil(dim - 1.01)
+    float dhx, dhy, dhz;     // conservative upper bounds on (candidate - corner), before the division by res
+    float bx, by, bz;        // float(dim - 1): bounds of the back-vote test (models/voting.py:104-107)
+    int status;              // 0 ok, 1 = the grid exceeds the capacity the caller provided
+};
+
 // (a, b) of pair p: from an int32/int64 index list, or row-major dense enumeration.
 template <bool IDX64>
 __device__ __forceinline__ void pair_ab(const void* __restrict__ idx, int64_t p, int n_points, int& a, int& b) {

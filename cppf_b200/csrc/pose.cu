@@ -1,0 +1,300 @@
+// One call per object: the whole script body of nocs/inference.py:174-339 (sunrgbd/inference.py:142-287)
+// between "cloud on the device" and "pose record", enqueued on one stream without a host round trip.
+//
+//   geometry (min / max / grid dims, :194-195)  ->  kNN + SPRIN point encoder (:180-181)
+//   -> per-point projection -> pair MLP + sampling (:182-188, :236-256)  -> centre vote (:191-205)
+//   -> argmax (:207-211) -> back-vote + compaction (:216-231) -> orientation histogram(s) (:258-284)
+//   -> aux sign / scale sums (:286-302, :335) -> 16-double record.
+//
+// The vote-grid geometry is derived on the device (struct Geom) and read by the kernels that need it, so the
+// host never waits for the grid dimensions and successive objects queue back to back; the Python mirror
+// (cppf_b200/pipeline.py) turns the record into RT / scales exactly like nocs/inference.py:305-339.
+#include "common.cuh"
+
+#include "../../include/cppf_b200.h"
+
+#include <math.h>
+
+#include <vector>
+
+namespace cppf {
+
+int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, const void* idx,
+                     int idx_is_64, float* grid, void* scratch, const float* corner, float res, int n_points,
+                     int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, const Geom* geom, int max_cells,
+                     cudaStream_t stream);
+int backvote_bins_launch(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                         uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
+                         int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, const Geom* geom,
+                         cudaStream_t stream);
+int grid_argmax_launch(const float* grid, int64_t n_cells, const int* n_cells_dev, int64_t* out_index, float* out_value,
+                       cudaStream_t stream);
+
+// ---- geometry: nocs/inference.py:194-195 in float32 like numpy (pc is float32, `res` a weak Python scalar)
+__global__ void __launch_bounds__(1024) geom_kernel(const float* __restrict__ pc, int n_points, float res, int max_cells,
+                                                    Geom* __restrict__ out) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
+        const f3 p = ld3(pc, i);
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+    __shared__ float s_lo[32][3], s_hi[32][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_lo[threadIdx.x >> 5][k] = lo[k];
+            s_hi[threadIdx.x >> 5][k] = hi[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        int dims[3];
+        for (int k = 0; k < 3; ++k) {
+            float a = s_lo[0][k], b = s_hi[0][k];
+            for (int w = 1; w < nw; ++w) {
+                a = fminf(a, s_lo[w][k]);
+                b = fmaxf(b, s_hi[w][k]);
+            }
+            out->corner[k] = a;
+            dims[k] = (int)((b - a) / res) + 1;                                   // :195
+        }
+        out->gx = dims[0]; out->gy = dims[1]; out->gz = dims[2];
+        const long long cells = (long long)dims[0] * dims[1] * dims[2];
+        out->cells = cells > 0x7FFFFFFF ? 0x7FFFFFFF : (int)cells;
+        out->status = cells > (long long)max_cells ? 1 : 0;
+        float h[3], dh[3];
+        for (int k = 0; k < 3; ++k) {
+            h[k] = __double2float_ru((double)dims[k] - 1.01);                      // models/voting.py:37-39
+            dh[k] = nextafterf((float)((double)h[k] * (double)res * (1.0 + 1e-6)), INFINITY);
+        }
+        out->hx = h[0]; out->hy = h[1]; out->hz = h[2];
+        out->dhx = dh[0]; out->dhy = dh[1]; out->dhz = dh[2];
+        out->bx = (float)(dims[0] - 1); out->by = (float)(dims[1] - 1); out->bz = (float)(dims[2] - 1);
+    }
+}
+
+// benchmark / test aid: overwrite the first `cols` bin columns of every pair (bins [n,4], src [n,cols])
+__global__ void __launch_bounds__(256) inject_bins_kernel(uint8_t* __restrict__ bins, const uint8_t* __restrict__ src, int cols,
+                                                          long long n) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        uchar4 b = reinterpret_cast<uchar4*>(bins)[p];
+        const uint8_t* s = src + p * cols;
+        if (cols > 0) b.x = s[0];
+        if (cols > 1) b.y = s[1];
+        if (cols > 2) b.z = s[2];
+        if (cols > 3) b.w = s[3];
+        reinterpret_cast<uchar4*>(bins)[p] = b;
+    }
+}
+
+// record[16] (double): 0 argmax flat | 1 best up bin | 2 best right bin (-1) | 3..5 sum log-scale | 6 survivors |
+//                      7 S_up | 8 S_right | 9..11 corner | 12..14 grid dims | 15 status
+__global__ void pack_record_kernel(const Geom* geom, const long long* flat, const long long* best, const double* stats,
+                                   int n_dirs, double* rec) {
+    rec[0] = (double)*flat;
+    rec[1] = (double)best[0];
+    rec[2] = n_dirs > 1 ? (double)best[1] : -1.0;
+    rec[3] = stats[0]; rec[4] = stats[1]; rec[5] = stats[2];
+    rec[6] = stats[3]; rec[7] = stats[4]; rec[8] = stats[5];
+    rec[9] = geom->corner[0]; rec[10] = geom->corner[1]; rec[11] = geom->corner[2];
+    rec[12] = geom->gx; rec[13] = geom->gy; rec[14] = geom->gz;
+    rec[15] = geom->status;
+}
+
+// ---- workspace carving -------------------------------------------------------------------------------------
+struct Carver {
+    unsigned char* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct Workspace {
+    Geom* geom;
+    long long* nbrs;
+    float* feat;
+    float* glob;
+    float* table;
+    uint8_t* bins;
+    float* tail;
+    uint8_t* mask;
+    long long* pos;
+    void* compact_scratch;
+    float* grid;
+    unsigned long long* acc;
+    long long* flat;
+    float* counts;
+    long long* best;
+    double* stats;
+    long long* count;
+    size_t bytes;
+};
+
+static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int max_cells, int n_sphere) {
+    Carver c{reinterpret_cast<unsigned char*>(base)};
+    Workspace w;
+    w.geom = c.take<Geom>(1);
+    w.nbrs = c.take<long long>((size_t)n_points * knn);
+    w.feat = c.take<float>((size_t)n_points * 40);
+    w.glob = c.take<float>(8);
+    w.table = c.take<float>((size_t)n_points * cppf_tc_table_cols());
+    w.bins = c.take<uint8_t>((size_t)n_pairs * 4);
+    w.tail = c.take<float>((size_t)n_pairs * 5);
+    w.mask = c.take<uint8_t>((size_t)n_pairs);
+    w.pos = c.take<long long>((size_t)n_pairs);
+    w.compact_scratch = c.take<unsigned char>((size_t)cppf_compact_scratch_bytes(n_pairs));
+    w.grid = c.take<float>((size_t)max_cells);
+    w.acc = c.take<unsigned long long>((size_t)max_cells);
+    w.flat = c.take<long long>(2);
+    w.counts = c.take<float>((size_t)n_sphere * 2);
+    w.best = c.take<long long>(2);
+    w.stats = c.take<double>(6);
+    w.count = c.take<long long>(1);
+    w.bytes = (c.off + 255) & ~(size_t)255;
+    return w;
+}
+
+// ---- stage timing (CUDA events on the launching stream) -------------------------------------------------------
+static const char* kStageNames[] = {"geometry", "point_encoder", "preproject", "encode_sample", "vote", "argmax",
+                                    "backvote", "compact", "rot_hist", "stats"};
+constexpr int kStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
+
+struct Timing {
+    std::vector<cudaEvent_t> pool;     // kStages + 1 events per recorded call
+    size_t used = 0;
+    cudaEvent_t next() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+};
+
+}  // namespace cppf
+
+using namespace cppf;
+
+extern "C" int cppf_pose_record_doubles(void) { return 16; }
+
+extern "C" int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int n_sphere) {
+    if (n_pairs <= 0) n_pairs = (int64_t)n_points * n_points;
+    return (int64_t)carve(nullptr, n_points, n_pairs, knn, max_cells, n_sphere).bytes;
+}
+
+extern "C" void* cppf_timing_create(void) { return new Timing(); }
+extern "C" void cppf_timing_destroy(void* t) {
+    if (!t) return;
+    Timing* tm = reinterpret_cast<Timing*>(t);
+    for (cudaEvent_t e : tm->pool) cudaEventDestroy(e);
+    delete tm;
+}
+extern "C" int cppf_timing_stages(void) { return kStages; }
+extern "C" const char* cppf_timing_stage_name(int i) { return (i >= 0 && i < kStages) ? kStageNames[i] : ""; }
+// h_ms_sum[kStages] += elapsed per stage over every call recorded since the last collect; returns the number
+// of calls (negative: CUDA error).  Synchronises on the last recorded event.
+extern "C" int cppf_timing_collect(void* t, float* h_ms_sum) {
+    Timing* tm = reinterpret_cast<Timing*>(t);
+    const size_t per = kStages + 1;
+    const size_t calls = tm->used / per;
+    if (calls == 0) return 0;
+    if (cudaEventSynchronize(tm->pool[tm->used - 1]) != cudaSuccess) return -1;
+    for (size_t c = 0; c < calls; ++c)
+        for (int s = 0; s < kStages; ++s) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, tm->pool[c * per + s], tm->pool[c * per + s + 1]) != cudaSuccess) return -1;
+            h_ms_sum[s] += ms;
+        }
+    tm->used = 0;
+    return (int)calls;
+}
+
+extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (a == nullptr || a->struct_bytes != sizeof(cppf_pose_args)) return (int)cudaErrorInvalidValue;
+    const int n = a->n_points;
+    const int64_t n_pairs = a->idx ? a->n_pairs : (int64_t)n * n;
+    if (n <= 0 || n_pairs <= 0 || a->knn <= 0 || a->knn > 64 || a->knn > n) return (int)cudaErrorInvalidValue;
+    if (a->max_cells <= 0 || a->max_cells > cppf_vote_private_max_cells()) return (int)cudaErrorInvalidValue;
+    if (a->n_sphere <= 0 || a->record == nullptr || a->workspace == nullptr) return (int)cudaErrorInvalidValue;
+    const Workspace w = carve(a->workspace, n, n_pairs, a->knn, a->max_cells, a->n_sphere);
+    if ((int64_t)w.bytes > a->workspace_bytes) return (int)cudaErrorInvalidValue;
+    Timing* tm = reinterpret_cast<Timing*>(a->timing);
+    auto mark = [&]() -> int {
+        if (!tm) return 0;
+        cudaEvent_t e = tm->next();
+        if (!e) return (int)cudaErrorMemoryAllocation;
+        return (int)cudaEventRecord(e, stream);
+    };
+#define CPPF_TRY(expr)          \
+    do {                        \
+        const int _r = (expr);  \
+        if (_r != 0) return _r; \
+    } while (0)
+
+    CPPF_TRY(mark());
+    geom_kernel<<<1, 1024, 0, stream>>>(a->pc, n, a->res, a->max_cells, w.geom);
+    CPPF_LAUNCH_CHECK();
+    CPPF_TRY(mark());
+    CPPF_TRY(cppf_knn(a->pc, n, a->knn, reinterpret_cast<int64_t*>(w.nbrs), stream));
+    CPPF_TRY(cppf_point_encode(a->pc, a->nrm, reinterpret_cast<const int64_t*>(w.nbrs), a->pe_blob, w.feat, w.glob, n, a->knn,
+                               stream));
+    CPPF_TRY(mark());
+    CPPF_TRY(cppf_tc_preproject(w.feat, a->tc_blob, w.table, n, stream));
+    CPPF_TRY(mark());
+    const int n_dirs = a->regress_right ? 2 : 1;
+    const int heads = 1 | 2 | 8 | (a->regress_right ? 4 : 0);
+    CPPF_TRY(cppf_encode_sample_tc(a->pc, a->nrm, w.table, a->tc_blob, a->idx, a->idx_is_64, n, n_pairs, a->uniforms, a->seed,
+                                   heads, w.bins, w.tail, nullptr, stream));
+    if (a->inject_bins != nullptr && a->inject_cols > 0) {
+        inject_bins_kernel<<<sm_count() * 8, 256, 0, stream>>>(w.bins, a->inject_bins, a->inject_cols, (long long)n_pairs);
+        CPPF_LAUNCH_CHECK();
+    }
+    CPPF_TRY(mark());
+    CPPF_RETURN_IF(cudaMemsetAsync(w.grid, 0, (size_t)a->max_cells * 4, stream));
+    CPPF_TRY(vote_fast_launch(a->pc, nullptr, w.bins, a->lut, a->idx, a->idx_is_64, w.grid, w.acc, nullptr, a->res, n, n_pairs,
+                              a->n_rots, 0, 0, 0, a->adaptive, w.geom, a->max_cells, stream));
+    CPPF_TRY(mark());
+    CPPF_TRY(grid_argmax_launch(w.grid, a->max_cells, &w.geom->cells, reinterpret_cast<int64_t*>(w.flat), nullptr, stream));
+    CPPF_TRY(mark());
+    CPPF_TRY(backvote_bins_launch(a->pc, w.bins, a->lut, a->idx, a->idx_is_64, w.mask, nullptr,
+                                  reinterpret_cast<const int64_t*>(w.flat), a->res, a->tol, n, n_pairs, a->n_rots, 0, 0, 0,
+                                  w.geom, stream));
+    CPPF_TRY(mark());
+    CPPF_TRY(cppf_compact_pairs(w.mask, a->idx, a->idx_is_64, n, n_pairs, nullptr, reinterpret_cast<int64_t*>(w.pos),
+                                reinterpret_cast<int64_t*>(w.count), w.compact_scratch, stream));
+    CPPF_TRY(mark());
+    CPPF_RETURN_IF(cudaMemsetAsync(w.counts, 0, (size_t)a->n_sphere * 2 * sizeof(float), stream));
+    const int64_t max_samples = a->rot_subsample > 0 ? a->rot_subsample : n_pairs;
+    for (int j = 0; j < n_dirs; ++j) {
+        CPPF_TRY(cppf_rot_hist(a->pc, w.bins, a->lut, a->idx, a->idx_is_64, reinterpret_cast<const int64_t*>(w.pos),
+                               reinterpret_cast<const int64_t*>(w.count), a->sphere, w.counts + (size_t)j * a->n_sphere, n,
+                               a->n_rots, a->n_sphere, j, max_samples < n_pairs ? max_samples : n_pairs,
+                               a->seed * 7919ull + (uint64_t)j, a->cos_thr, stream));
+        CPPF_TRY(grid_argmax_launch(w.counts + (size_t)j * a->n_sphere, a->n_sphere, nullptr,
+                                    reinterpret_cast<int64_t*>(w.best + j), nullptr, stream));
+    }
+    CPPF_TRY(mark());
+    CPPF_TRY(cppf_survivor_stats(a->pc, a->nrm, w.tail, a->idx, a->idx_is_64, reinterpret_cast<const int64_t*>(w.pos),
+                                 reinterpret_cast<const int64_t*>(w.count), a->sphere, reinterpret_cast<const int64_t*>(w.best),
+                                 n_dirs > 1 ? reinterpret_cast<const int64_t*>(w.best + 1) : nullptr, w.stats, n, n_pairs,
+                                 stream));
+    pack_record_kernel<<<1, 1, 0, stream>>>(w.geom, w.flat, w.best, w.stats, n_dirs, a->record);
+    CPPF_LAUNCH_CHECK();
+    CPPF_TRY(mark());
+#undef CPPF_TRY
+    return 0;
+}

@@ -150,7 +150,9 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, uint32_t i) {
 }
 
 __global__ void __launch_bounds__(256) grid_argmax_kernel(const float* __restrict__ grid, long long n,
-                                                          unsigned long long* __restrict__ key_out) {
+                                                          unsigned long long* __restrict__ key_out,
+                                                          const int* __restrict__ n_dev) {
+    if (n_dev != nullptr) n = *n_dev < n ? *n_dev : n;      // cell count derived on the device (cppf_pose_fused)
     unsigned long long best = 0ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const unsigned long long k = argmax_key(__ldg(grid + i), (uint32_t)i);
@@ -569,16 +571,23 @@ extern "C" int cppf_ppf_vote(const float* points, const float* mu_nu, const floa
     return 0;
 }
 
-extern "C" int cppf_grid_argmax(const float* grid, int64_t n_cells, int64_t* out_index, float* out_value, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace cppf {
+int grid_argmax_launch(const float* grid, int64_t n_cells, const int* n_cells_dev, int64_t* out_index, float* out_value,
+                       cudaStream_t stream) {
     if (n_cells <= 0 || n_cells > 0xFFFFFFFFll) return (int)cudaErrorInvalidValue;
     CPPF_RETURN_IF(cudaMemsetAsync(out_index, 0, sizeof(int64_t), stream));
     grid_argmax_kernel<<<blocks_for(n_cells, 256, 4), 256, 0, stream>>>(grid, (long long)n_cells,
-                                                                       reinterpret_cast<unsigned long long*>(out_index));
+                                                                       reinterpret_cast<unsigned long long*>(out_index),
+                                                                       n_cells_dev);
     CPPF_LAUNCH_CHECK();
     grid_argmax_finish_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(out_index), out_value);
     CPPF_LAUNCH_CHECK();
     return 0;
+}
+}  // namespace cppf
+
+extern "C" int cppf_grid_argmax(const float* grid, int64_t n_cells, int64_t* out_index, float* out_value, void* stream_) {
+    return grid_argmax_launch(grid, n_cells, nullptr, out_index, out_value, (cudaStream_t)stream_);
 }
 
 extern "C" int cppf_backvote(const float* points, const float* mu_nu, float* out_offsets, uint8_t* out_mask,

@@ -48,14 +48,23 @@ struct VotePParams {
     unsigned long long* acc;   // [cells] fixed-point accumulator (global)
     const float* corner;
     float res, inv_res;
-    float lo, hx, hy, hz;
+    float lo, hx, hy, hz;      // exact bounds on g = d / res (models/voting.py:36-39, double literals rounded up)
+    float dlo, dhx, dhy, dhz;  // conservative bounds on d = candidate - corner (phase 1, before the division)
     int n_points;
     long long n_pairs;
     int n_rots, gx, gy, gz, adaptive;
+    const Geom* geom;          // optional: device-side geometry overrides corner / dims / upper bounds
+    int max_cells;             // capacity of the shared-memory grid of this launch
 };
 
 constexpr int kVoteThreads = 1024;
+constexpr int kVoteBatch = 2 * kVoteThreads;       // pairs sorted and voted between two block barriers
 constexpr int kVoteQueue = 64;                     // per-warp ring of in-bounds candidates (float4 slots)
+constexpr int kVoteKeys = kMaxRotsP + 1;           // sort key = rotation count of the pair (0..72)
+// Overflow guard: after every batch each cell holding >= 2^30 units is flushed to the global u64 accumulator.
+// A batch adds at most kVoteBatch * 72 candidates * 2^14 units = 2.42e9 < 2^32 - 2^30 to any one cell.
+constexpr unsigned kFlushAt = 1u << 30;
+static_assert((unsigned long long)kVoteBatch * kMaxRotsP * (1ull << kFixShift) < (1ull << 32) - kFlushAt, "guard");
 
 // trilinear splat of one in-bounds candidate at grid coordinates g -- models/voting.py:40-63 with
 // prob == 1 (nocs/inference.py:201).  Each corner weight is rounded ONCE to 2^-14: the last product is an
@@ -88,111 +97,200 @@ __device__ __forceinline__ float4 ld_shared_f4(unsigned addr) {
     return v;
 }
 
-// Two phases per warp, decoupled by a shared-memory ring:
-//   phase 1 (one lane = one pair, all lanes walk their circle together): candidate position and the
-//            reference's in-bounds test; the ~45 % of candidates that pass are appended to the warp's ring
-//            with a ballot + popc prefix;
-//   phase 2 (whenever 32 candidates are queued): one lane = one queued candidate -> 8 shared-memory atomics.
+// Per batch of 2048 pairs a CTA
+//   (1) counting-sorts the pairs by their rotation count n (adaptive voting, models/voting.py:31: n depends
+//       on nu, so a warp of unsorted pairs walks max(n) = 66 steps for a mean n of 49) -- largest n first;
+//   (2) lets its warps pull 32 sorted pairs at a time from a shared counter (longest chunks first, so the
+//       warps reach the batch barrier together);
+// and every warp works in two phases decoupled by a shared-memory ring:
+//   phase 1 (one lane = one pair, all lanes walk their circle together): candidate offset from the grid
+//            corner and a conservative in-bounds test on it (no division); the ~45 % of candidates that
+//            pass are appended to the warp's ring with a ballot + popc prefix;
+//   phase 2 (whenever 32 candidates are queued): one lane = one queued candidate -> the reference's `/ res`
+//            and exact in-bounds test (models/voting.py:35-39), then 8 shared-memory atomics.
 // Without the ring the splat runs under the divergence of the in-bounds test (about a third of the lanes
-// active); with it the atomics always issue from full warps.
+// active); with it the atomics always issue from full warps.  Integer sums are order-independent, so neither
+// the sort nor the dynamic chunk assignment changes the result.
 template <bool IDX64, bool BINS>
 __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const VotePParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tab = reinterpret_cast<float2*>(smem_raw);
     float* s_lut = reinterpret_cast<float*>(s_tab + kRotTabP);
     float4* s_queue = reinterpret_cast<float4*>(s_lut + 64);
-    unsigned* s_grid = reinterpret_cast<unsigned*>(s_queue + (kVoteThreads / 32) * kVoteQueue);
-    __shared__ unsigned s_tally;
-    const int cells = prm.gx * prm.gy * prm.gz;
+    unsigned short* s_perm = reinterpret_cast<unsigned short*>(s_queue + (kVoteThreads / 32) * kVoteQueue);
+    unsigned* s_grid = reinterpret_cast<unsigned*>(s_perm + kVoteBatch);
+    __shared__ int s_hist[kVoteKeys + 3], s_start[kVoteKeys + 3], s_nlut[32];
+    __shared__ int s_total, s_next;
+    int gx = prm.gx, gy = prm.gy, gzd = prm.gz;
+    float hx = prm.hx, hy = prm.hy, hz = prm.hz, dhx = prm.dhx, dhy = prm.dhy, dhz = prm.dhz;
+    const float* corner = prm.corner;
+    if (prm.geom != nullptr) {
+        const Geom g = *prm.geom;
+        if (g.status != 0 || g.cells > prm.max_cells) return;
+        gx = g.gx; gy = g.gy; gzd = g.gz;
+        hx = g.hx; hy = g.hy; hz = g.hz; dhx = g.dhx; dhy = g.dhy; dhz = g.dhz;
+        corner = prm.geom->corner;
+    }
+    const int cells = gx * gy * gzd;
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
     if (BINS && threadIdx.x < 64) s_lut[threadIdx.x] = __ldg(prm.lut + threadIdx.x);
+    if (BINS && threadIdx.x < 32) {
+        int n = prm.n_rots;
+        if (prm.adaptive) n = adaptive_rots(__ldg(prm.lut + 32 + threadIdx.x), prm.res, prm.n_rots);   // :31
+        s_nlut[threadIdx.x] = n < 0 ? 0 : n;
+    }
     for (int i = threadIdx.x; i < cells; i += blockDim.x) s_grid[i] = 0u;
-    if (threadIdx.x == 0) s_tally = 0u;
+    if (threadIdx.x < kVoteKeys + 3) s_hist[threadIdx.x] = 0;
     __syncthreads();
 
-    const int gyz = prm.gy * prm.gz, gz = prm.gz;
+    const int gyz = gy * gzd, gz = gzd;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned q_addr = (unsigned)__cvta_generic_to_shared(s_queue + (threadIdx.x >> 5) * kVoteQueue);
-    const float cx = __ldg(prm.corner), cy = __ldg(prm.corner + 1), cz = __ldg(prm.corner + 2);
-    const unsigned worst_batch = (unsigned)blockDim.x * (unsigned)prm.n_rots;
-    const long long n_batches = (prm.n_pairs + blockDim.x - 1) / blockDim.x;
+    const float cx = __ldg(corner), cy = __ldg(corner + 1), cz = __ldg(corner + 2);
+    const long long n_batches = (prm.n_pairs + kVoteBatch - 1) / kVoteBatch;
 
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-        const long long p = batch * blockDim.x + threadIdx.x;
-        int n = 0;
-        f3 c = {0.f, 0.f, 0.f}, x = c, y = c;
-        if (p < prm.n_pairs) {
-            int ia, ib;
-            pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
-            float mu, nu;
-            if (BINS) {
-                const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
-                mu = s_lut[bn.x];
-                nu = s_lut[32 + bn.y];
-            } else {
-                const float2 mn = __ldg(reinterpret_cast<const float2*>(prm.mu_nu) + p);
-                mu = mn.x;
-                nu = mn.y;
-            }
-            const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
-            f3 ab, ex;
-            if (pair_frame(a, b, ab, ex)) {                                    // voting.py:21
-                c = a - ab * mu;                                               // :23
-                x = ex * nu;                                                   // :28
-                y = cross3(x, ab);                                             // :29
-                n = prm.n_rots;
-                if (prm.adaptive) n = adaptive_rots(nu, prm.res, prm.n_rots);  // :31
-                if (n < 0) n = 0;
+        const long long base = batch * kVoteBatch;
+        // ---- (1a) keys + ranks: n of each of this thread's two pairs
+        int key[2], rank[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long p = base + threadIdx.x + j * kVoteThreads;
+            key[j] = -1;
+            if (p < prm.n_pairs) {
+                int n;
+                if (BINS) {
+                    n = s_nlut[__ldg(prm.bins + 4 * p + 1) & 31];
+                } else {
+                    n = prm.n_rots;
+                    if (prm.adaptive) n = adaptive_rots(__ldg(prm.mu_nu + 2 * p + 1), prm.res, prm.n_rots);
+                    n = n < 0 ? 0 : n;
+                }
+                key[j] = n;
+                rank[j] = atomicAdd(&s_hist[n], 1);
             }
         }
-        const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);     // row n; reads past column n stay inside the table
-        const int n_max = __reduce_max_sync(0xffffffffu, n);
-        unsigned q_head = 0, q_tail = 0, voted = 0;                            // warp-uniform
-        for (int i = 0; i < n_max; ++i) {
-            const float2 cs = tab[i];
-            const f3 off = x * cs.x + y * cs.y;                                // :34
-            const float gxf = div_by(c.x + off.x - cx, prm.res, prm.inv_res);  // :35
-            const float gyf = div_by(c.y + off.y - cy, prm.res, prm.inv_res);
-            const float gzf = div_by(c.z + off.z - cz, prm.res, prm.inv_res);
-            const bool inb = i < n && !(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= prm.hx || gyf >= prm.hy ||
-                                        gzf >= prm.hz);                        // :36-39
-            const unsigned m = __ballot_sync(0xffffffffu, inb);
-            if (inb) st_shared_f4(q_addr + (((q_tail + __popc(m & lt_mask)) & (kVoteQueue - 1)) << 4), gxf, gyf, gzf);
-            q_tail += __popc(m);
-            if (q_tail - q_head >= 32u) {
-                __syncwarp();
-                const float4 g = ld_shared_f4(q_addr + (((q_head + lane) & (kVoteQueue - 1)) << 4));
-                splat_fixed(s_grid, g.x, g.y, g.z, gyz, gz);
-                q_head += 32u;
-                voted += 32u;
-                __syncwarp();
+        // ---- overflow guard on the votes of the previous batches (nobody is voting now)
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+            const unsigned v = s_grid[i];
+            if (v >= kFlushAt) {
+                atomicAdd(prm.acc + i, (unsigned long long)v);
+                s_grid[i] = 0u;
+            }
+        }
+        __syncthreads();
+        // ---- (1b) exclusive scan of the histogram, largest n first
+        if (threadIdx.x < 32) {
+            int v[3], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int e = 3 * lane + k;                      // e = 72 - n
+                v[k] = e < kVoteKeys ? s_hist[kMaxRotsP - e] : 0;
+                sum += v[k];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int e = 3 * lane + k;
+                if (e < kVoteKeys) {
+                    s_start[kMaxRotsP - e] = run;
+                    s_hist[kMaxRotsP - e] = 0;
+                }
+                run += v[k];
+            }
+            if (lane == 31) {
+                s_total = incl;
+                s_next = 0;
+            }
+        }
+        __syncthreads();
+        // ---- (1c) permutation
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (key[j] >= 0) s_perm[s_start[key[j]] + rank[j]] = (unsigned short)(threadIdx.x + j * kVoteThreads);
+        __syncthreads();
+        const int total = s_total;
+
+        // ---- (2) warps pull chunks of 32 sorted pairs
+        unsigned q_head = 0, q_tail = 0;                                       // warp-uniform
+        while (true) {
+            int chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&s_next, 1);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk * 32 >= total) break;
+            const int item = chunk * 32 + lane;
+            int n = 0;
+            f3 c = {0.f, 0.f, 0.f}, x = c, y = c;
+            if (item < total) {
+                const long long p = base + s_perm[item];
+                int ia, ib;
+                pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
+                float mu, nu;
+                if (BINS) {
+                    const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
+                    mu = s_lut[bn.x];
+                    nu = s_lut[32 + bn.y];
+                    n = s_nlut[bn.y & 31];
+                } else {
+                    const float2 mn = __ldg(reinterpret_cast<const float2*>(prm.mu_nu) + p);
+                    mu = mn.x;
+                    nu = mn.y;
+                    n = prm.n_rots;
+                    if (prm.adaptive) n = adaptive_rots(nu, prm.res, prm.n_rots);  // :31
+                    if (n < 0) n = 0;
+                }
+                const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
+                f3 ab, ex;
+                if (pair_frame(a, b, ab, ex)) {                                // voting.py:21
+                    c = a - ab * mu;                                           // :23
+                    x = ex * nu;                                               // :28
+                    y = cross3(x, ab);                                         // :29
+                } else {
+                    n = 0;
+                }
+            }
+            const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);     // row n; reads past column n stay inside the table
+            const int n_max = __reduce_max_sync(0xffffffffu, n);
+            for (int i = 0; i < n_max; ++i) {
+                const float2 cs = tab[i];
+                const f3 off = x * cs.x + y * cs.y;                            // :34
+                const float dx = c.x + off.x - cx, dy = c.y + off.y - cy, dz = c.z + off.z - cz;   // :35 before `/ res`
+                // conservative: every candidate the exact test of phase 2 accepts passes here
+                const bool inb = i < n && dx >= prm.dlo && dy >= prm.dlo && dz >= prm.dlo && dx < dhx && dy < dhy && dz < dhz;
+                const unsigned m = __ballot_sync(0xffffffffu, inb);
+                if (inb) st_shared_f4(q_addr + (((q_tail + __popc(m & lt_mask)) & (kVoteQueue - 1)) << 4), dx, dy, dz);
+                q_tail += __popc(m);
+                if (q_tail - q_head >= 32u) {
+                    __syncwarp();
+                    const float4 d = ld_shared_f4(q_addr + (((q_head + lane) & (kVoteQueue - 1)) << 4));
+                    const float gxf = div_by(d.x, prm.res, prm.inv_res);       // :35
+                    const float gyf = div_by(d.y, prm.res, prm.inv_res);
+                    const float gzf = div_by(d.z, prm.res, prm.inv_res);
+                    if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz))
+                        splat_fixed(s_grid, gxf, gyf, gzf, gyz, gz);           // :36-63
+                    q_head += 32u;
+                    __syncwarp();
+                }
             }
         }
         __syncwarp();
         if (lane < (int)(q_tail - q_head)) {
-            const float4 g = ld_shared_f4(q_addr + (((q_head + lane) & (kVoteQueue - 1)) << 4));
-            splat_fixed(s_grid, g.x, g.y, g.z, gyz, gz);
+            const float4 d = ld_shared_f4(q_addr + (((q_head + lane) & (kVoteQueue - 1)) << 4));
+            const float gxf = div_by(d.x, prm.res, prm.inv_res);
+            const float gyf = div_by(d.y, prm.res, prm.inv_res);
+            const float gzf = div_by(d.z, prm.res, prm.inv_res);
+            if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz))
+                splat_fixed(s_grid, gxf, gyf, gzf, gyz, gz);
         }
-        voted += q_tail - q_head;
-        // overflow guard: a cell can have received at most `tally` whole votes since the last flush
-        if (lane == 0 && voted) atomicAdd(&s_tally, voted);
         __syncthreads();
-        const bool flush = s_tally + worst_batch + worst_batch / 8 > kFixBudget;   // (+1/8: rounding slack)
-        __syncthreads();
-        if (flush) {
-            for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-                const unsigned v = s_grid[i];
-                if (v) {
-                    atomicAdd(prm.acc + i, (unsigned long long)v);
-                    s_grid[i] = 0u;
-                }
-            }
-            if (threadIdx.x == 0) s_tally = 0u;
-            __syncthreads();
-        }
     }
-    __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
         const unsigned v = s_grid[i];
         if (v) atomicAdd(prm.acc + i, (unsigned long long)v);
@@ -201,7 +299,8 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
 
 // grid[i] += acc[i] * 2^-14   (exact integer sum -> one rounding; deterministic run to run)
 __global__ void __launch_bounds__(256) vote_finalize_kernel(const unsigned long long* __restrict__ acc,
-                                                            float* __restrict__ grid, int cells) {
+                                                            float* __restrict__ grid, int cells, const Geom* geom) {
+    if (geom != nullptr) cells = geom->status == 0 ? geom->cells : 0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cells) grid[i] += (float)((double)acc[i] * (1.0 / 16384.0));
 }
@@ -222,6 +321,7 @@ struct BackvotePParams {
     int n_points;
     long long n_pairs;
     int n_rots, gx, gy, gz;
+    const Geom* geom;                // optional: device-side geometry overrides corner / dims / bounds
 };
 
 template <bool IDX64>
@@ -231,11 +331,20 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
     if (threadIdx.x < 64) s_lut[threadIdx.x] = __ldg(prm.lut + threadIdx.x);
     __syncthreads();
-    const float cx = __ldg(prm.corner), cy = __ldg(prm.corner + 1), cz = __ldg(prm.corner + 2);
+    int gy = prm.gy, gz = prm.gz;
+    float hx = prm.hx, hy = prm.hy, hz = prm.hz;
+    const float* corner = prm.corner;
+    if (prm.geom != nullptr) {
+        if (prm.geom->status != 0) return;
+        gy = prm.geom->gy; gz = prm.geom->gz;
+        hx = prm.geom->bx; hy = prm.geom->by; hz = prm.geom->bz;
+        corner = prm.geom->corner;
+    }
+    const float cx = __ldg(corner), cy = __ldg(corner + 1), cz = __ldg(corner + 2);
     // nocs/inference.py:208-209: T = corner + cell * res in float64, cast to float32 for the kernel (:226)
     const long long flat = *prm.argmax_flat;
-    const int gyz = prm.gy * prm.gz;
-    const int ix = (int)(flat / gyz), iy = (int)((flat % gyz) / prm.gz), iz = (int)(flat % prm.gz);
+    const int gyz = gy * gz;
+    const int ix = (int)(flat / gyz), iy = (int)((flat % gyz) / gz), iz = (int)(flat % gz);
     const float tx = (float)((double)cx + (double)ix * (double)prm.res);
     const float ty = (float)((double)cy + (double)iy * (double)prm.res);
     const float tz = (float)((double)cz + (double)iz * (double)prm.res);
@@ -295,7 +404,7 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
                 const float gxf = div_by(pc.x - cx, prm.res, prm.inv_res);
                 const float gyf = div_by(pc.y - cy, prm.res, prm.inv_res);
                 const float gzf = div_by(pc.z - cz, prm.res, prm.inv_res);
-                if (gxf < 0.f || gyf < 0.f || gzf < 0.f || gxf >= prm.hx || gyf >= prm.hy || gzf >= prm.hz) continue;
+                if (gxf < 0.f || gyf < 0.f || gzf < 0.f || gxf >= hx || gyf >= hy || gzf >= hz) continue;
                 hit = off.x != 0.f || off.y != 0.f || off.z != 0.f;            // inference.py:230 any(oc != 0)
                 if (hit) break;
             }
@@ -308,8 +417,15 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
 // Orientation voting on a sub-sample of the survivors, fused with the sphere histogram:
 // models/voting.py:119-147 + nocs/inference.py:276-284.  Survivor j of the sub-sample is
 // pos[(offset + j*stride) mod count] (stride coprime with count: a sample without
-// replacement, like the reference's shuffle).  A 512-thread block takes 16 pairs: frames ->
-// 16 x n_rots candidates in shared memory -> thread s accumulates bin s.
+// replacement, like the reference's shuffle).
+//
+// The reference multiplies every candidate with every sphere bin ([720 000,3] x [3,480]) and counts
+// dot > cos(1.5 deg).  A candidate c (|c| <= 1) and a bin s (|s| = 1) with c.s > thr are closer than
+// d = sqrt(2 - 2 thr) (0.0262 for 1.5 deg), so their y coordinates differ by less than d; the Fibonacci
+// sphere of utils/util.py:102-118 has y strictly decreasing in the bin index, so only the ~14 bins of the
+// window |y_s - c_y| <= d can count.  Each thread takes candidates, binary-searches that window in shared
+// memory and tests its bins with the same dot-product expression as the full scan -> identical counts at
+// 1/35 of the work.  A sphere whose y is not monotone (any other `sphere` array) falls back to the full scan.
 struct RotHistParams {
     const float2* rot_tab;
     const float* points;
@@ -324,14 +440,18 @@ struct RotHistParams {
     long long max_samples;
     unsigned long long offset_seed;
     float thr;
+    float ywin;                  // half-width of the y window (>= 2: scan every bin)
 };
 
-constexpr int kRotHistPairs = 16;
+constexpr int kRotHistPairs = 64;
+constexpr int kRotHistThreads = 512;
 
 template <bool IDX64>
-__global__ void __launch_bounds__(512) rot_hist_kernel(const RotHistParams prm) {
+__global__ void __launch_bounds__(kRotHistThreads) rot_hist_kernel(const RotHistParams prm) {
+    extern __shared__ __align__(16) unsigned char rh_smem[];
+    float4* s_sph = reinterpret_cast<float4*>(rh_smem);                       // [n_bins] (x, y, z, -)
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sph + prm.n_bins);         // [n_bins]
     __shared__ float s_frame[kRotHistPairs][12];
-    __shared__ float4 s_cand[kRotHistPairs * kMaxRotsP];
     const long long count = *prm.count;
     const long long m = count < prm.max_samples ? count : prm.max_samples;
     const long long j0 = (long long)blockIdx.x * kRotHistPairs;
@@ -341,6 +461,13 @@ __global__ void __launch_bounds__(512) rot_hist_kernel(const RotHistParams prm) 
     if (count % 1000003ll == 0) stride = 999983ull;
     if (m == count) stride = 1ull;
     const unsigned long long off = m == count ? 0ull : prm.offset_seed % (unsigned long long)count;
+    int mono = 1;
+    for (int s = threadIdx.x; s < prm.n_bins; s += blockDim.x) {
+        const float sy = __ldg(prm.sphere + 3 * s + 1);
+        s_sph[s] = make_float4(__ldg(prm.sphere + 3 * s), sy, __ldg(prm.sphere + 3 * s + 2), 0.f);
+        s_cnt[s] = 0u;
+        if (s + 1 < prm.n_bins && !(__ldg(prm.sphere + 3 * (s + 1) + 1) < sy)) mono = 0;
+    }
     if (threadIdx.x < kRotHistPairs) {
         float* fr = s_frame[threadIdx.x];
         fr[10] = 0.f;
@@ -363,35 +490,49 @@ __global__ void __launch_bounds__(512) rot_hist_kernel(const RotHistParams prm) 
             }
         }
     }
-    __syncthreads();
+    mono = __syncthreads_and(mono);
+    const bool windowed = mono && prm.ywin < 2.f;
     const float2* tab = prm.rot_tab + prm.n_rots * (prm.n_rots - 1) / 2;
     const int total = kRotHistPairs * prm.n_rots;
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
         const int lp = t / prm.n_rots, i = t - lp * prm.n_rots;
         const float* fr = s_frame[lp];
-        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);       // zero vector never exceeds thr (> 0)
+        if (j0 + lp >= m) break;                           // lp is non-decreasing in t
+        f3 up = {0.f, 0.f, 0.f};                           // degenerate pair: the zero vector, as rot_voting leaves it
         if (fr[10] != 0.f) {
             const float2 cs = __ldg(tab + i);
             const f3 ab = {fr[0], fr[1], fr[2]}, x = {fr[3], fr[4], fr[5]}, y = {fr[6], fr[7], fr[8]};
             const float tn = fr[9];
             const f3 o = x * cs.x + y * cs.y;
             const f3 axis = tn > 0.f ? ab : f3{-ab.x, -ab.y, -ab.z};
-            f3 up = o * tn + axis;
+            up = o * tn + axis;
             up = up / (float)((double)len3(up) + 1e-7);
-            cv = make_float4(up.x, up.y, up.z, 0.f);
         }
-        s_cand[t] = cv;
+        int lo = 0, hi = prm.n_bins;
+        if (windowed) {
+            const float y_hi = up.y + prm.ywin, y_lo = up.y - prm.ywin;
+            int a0 = 0, a1 = prm.n_bins;                   // first s with y_s <= y_hi
+            while (a0 < a1) {
+                const int mid = (a0 + a1) >> 1;
+                if (s_sph[mid].y > y_hi) a0 = mid + 1; else a1 = mid;
+            }
+            lo = a0;
+            a1 = prm.n_bins;                               // first s with y_s < y_lo
+            while (a0 < a1) {
+                const int mid = (a0 + a1) >> 1;
+                if (s_sph[mid].y >= y_lo) a0 = mid + 1; else a1 = mid;
+            }
+            hi = a0;
+        }
+        for (int s = lo; s < hi; ++s) {
+            const float4 sp = s_sph[s];
+            if (fmaf(up.z, sp.z, fmaf(up.y, sp.y, up.x * sp.x)) > prm.thr) atomicAdd(s_cnt + s, 1u);
+        }
     }
     __syncthreads();
     for (int s = threadIdx.x; s < prm.n_bins; s += blockDim.x) {
-        const float sx = __ldg(prm.sphere + 3 * s), sy = __ldg(prm.sphere + 3 * s + 1), sz = __ldg(prm.sphere + 3 * s + 2);
-        int cnt = 0;
-#pragma unroll 4
-        for (int i = 0; i < total; ++i) {
-            const float4 c = s_cand[i];
-            cnt += fmaf(c.z, sz, fmaf(c.y, sy, c.x * sx)) > prm.thr ? 1 : 0;
-        }
-        if (cnt) atomicAdd(prm.counts + s, (float)cnt);
+        const unsigned c = s_cnt[s];
+        if (c) atomicAdd(prm.counts + s, (float)c);
     }
 }
 
@@ -425,29 +566,38 @@ __global__ void __launch_bounds__(256) survivor_stats_kernel(const StatsParams p
         const long long br = *prm.best_right;
         dr = {__ldg(prm.sphere + 3 * br), __ldg(prm.sphere + 3 * br + 1), __ldg(prm.sphere + 3 * br + 2)};
     }
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (long long)gridDim.x * blockDim.x) {
-        const long long p = prm.pos[j];
-        int ia, ib;
-        pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
-        const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
-        const f3 ab = a - b;
-        const float inv = sqrtf(dot3(ab, ab)) + 1e-7f;                         // :288-289 (float32 numpy)
-        const f3 abn = {ab.x / inv, ab.y / inv, ab.z / inv};
-        f3 n = ld3(prm.nrm, ia);
-        if (dot3(n, abn) < 0.f) n = {-n.x, -n.y, -n.z};                        // :291-292
-        const float tu = dot3(n, du) > 0.f ? 1.f : -1.f;                       // :295
-        acc[0] += prm.tail[2 * prm.n_pairs + p];
-        acc[1] += prm.tail[3 * prm.n_pairs + p];
-        acc[2] += prm.tail[4 * prm.n_pairs + p];
-        acc[3] += 1.0;
-        acc[4] += (double)(prm.tail[p] * tu);
-        if (prm.best_right) acc[5] += (double)(prm.tail[prm.n_pairs + p] * (dot3(n, dr) > 0.f ? 1.f : -1.f));
+    // fp32 partial sums per thread (a thread sees <= a few hundred survivors), widened to double for the
+    // cross-thread reduction; 4 survivors in flight per thread hide the pos -> tail gather latency
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; j0 < count; j0 += 4 * stride) {
+        long long p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = j0 + u * stride < count ? prm.pos[j0 + u * stride] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p[u] < 0) continue;
+            int ia, ib;
+            pair_ab<IDX64>(prm.idx, p[u], prm.n_points, ia, ib);
+            const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
+            const f3 ab = a - b;
+            const float inv = sqrtf(dot3(ab, ab)) + 1e-7f;                     // :288-289 (float32 numpy)
+            const f3 abn = {ab.x / inv, ab.y / inv, ab.z / inv};
+            f3 n = ld3(prm.nrm, ia);
+            if (dot3(n, abn) < 0.f) n = {-n.x, -n.y, -n.z};                    // :291-292
+            const float tu = dot3(n, du) > 0.f ? 1.f : -1.f;                   // :295
+            acc[0] += __ldg(prm.tail + 2 * prm.n_pairs + p[u]);
+            acc[1] += __ldg(prm.tail + 3 * prm.n_pairs + p[u]);
+            acc[2] += __ldg(prm.tail + 4 * prm.n_pairs + p[u]);
+            acc[3] += 1.f;
+            acc[4] += __ldg(prm.tail + p[u]) * tu;
+            if (prm.best_right) acc[5] += __ldg(prm.tail + prm.n_pairs + p[u]) * (dot3(n, dr) > 0.f ? 1.f : -1.f);
+        }
     }
     __shared__ double s[8][6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        double v = acc[k];
+        double v = (double)acc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5][k] = v;
@@ -466,16 +616,24 @@ using namespace cppf;
 
 extern "C" int64_t cppf_vote_scratch_bytes(int gx, int gy, int gz) { return (int64_t)gx * gy * gz * 8; }
 
-extern "C" int cppf_vote_private_max_cells(void) {
-    return (int)((220 * 1024 - kRotTabP * 8 - 64 * 4 - (kVoteThreads / 32) * kVoteQueue * 16 - 64) / 4);
+static size_t vote_private_fixed_smem() {
+    return (size_t)kRotTabP * 8 + 64 * 4 + (size_t)(kVoteThreads / 32) * kVoteQueue * 16 + (size_t)kVoteBatch * 2;
 }
 
-extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut,
-                              const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
-                              int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
-                              void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const long long cells = (long long)gx * gy * gz;
+extern "C" int cppf_vote_private_max_cells(void) { return (int)((225 * 1024 - vote_private_fixed_smem() - 1024) / 4); }
+
+// Host side of the conservative phase-1 bounds: d / res rounds to within 2^-24 of the quotient, so d below
+// lo*res*(1 - 1e-6) can never reach lo (and likewise above the upper bounds).
+static float vote_bound_below(float g, float res) { return nextafterf((float)((double)g * (double)res * (1.0 - 1e-6)), -INFINITY); }
+
+namespace cppf {
+// Launch of the privatised vote with the geometry either in the arguments (geom == nullptr) or in device
+// memory (geom != nullptr: gx/gy/gz are ignored and max_cells sizes the shared-memory grid).
+int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, const void* idx,
+                     int idx_is_64, float* grid, void* scratch, const float* corner, float res, int n_points,
+                     int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, const Geom* geom, int max_cells,
+                     cudaStream_t stream) {
+    const long long cells = geom ? (long long)max_cells : (long long)gx * gy * gz;
     if (cells <= 0 || cells > cppf_vote_private_max_cells() || n_rots > kMaxRotsP || n_rots <= 0)
         return (int)cudaErrorInvalidValue;
     if ((mu_nu == nullptr) == (bins == nullptr)) return (int)cudaErrorInvalidValue;
@@ -486,13 +644,19 @@ extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uin
     const float2* rot_tab = rot_table_device(stream, &terr);
     if (terr) return terr;
     CPPF_RETURN_IF(cudaMemsetAsync(scratch, 0, (size_t)cells * 8, stream));
+    const float lo = float_ceil_p(0.01);
+    float hx = 0.f, hy = 0.f, hz = 0.f, dhx = 0.f, dhy = 0.f, dhz = 0.f;
+    if (!geom) {
+        hx = float_ceil_p((double)gx - 1.01), hy = float_ceil_p((double)gy - 1.01), hz = float_ceil_p((double)gz - 1.01);
+        auto above = [&](float g) { return nextafterf((float)((double)g * (double)res * (1.0 + 1e-6)), INFINITY); };
+        dhx = above(hx), dhy = above(hy), dhz = above(hz);
+    }
     VotePParams prm{rot_tab, points, mu_nu, bins, lut, idx, reinterpret_cast<unsigned long long*>(scratch), corner, res,
-                    (float)(1.0 / (double)res), float_ceil_p(0.01), float_ceil_p((double)gx - 1.01),
-                    float_ceil_p((double)gy - 1.01), float_ceil_p((double)gz - 1.01), n_points, (long long)n_pairs,
-                    n_rots, gx, gy, gz, adaptive};
-    const size_t smem = (size_t)kRotTabP * 8 + 64 * 4 + (size_t)(kVoteThreads / 32) * kVoteQueue * 16 + (size_t)cells * 4;
+                    (float)(1.0 / (double)res), lo, hx, hy, hz, vote_bound_below(lo, res), dhx, dhy, dhz, n_points,
+                    (long long)n_pairs, n_rots, gx, gy, gz, adaptive, geom, (int)cells};
+    const size_t smem = vote_private_fixed_smem() + (size_t)cells * 4;
     const int threads = kVoteThreads;
-    long long blocks = (n_pairs + threads - 1) / threads;
+    long long blocks = (n_pairs + kVoteBatch - 1) / kVoteBatch;
     if (blocks > sm_count()) blocks = sm_count();
     void (*kern)(const VotePParams);
     if (bins) kern = idx_is_64 ? vote_private_kernel<true, true> : vote_private_kernel<false, true>;
@@ -501,16 +665,15 @@ extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uin
     kern<<<(int)blocks, threads, smem, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     vote_finalize_kernel<<<(int)((cells + 255) / 256), 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(scratch),
-                                                                        grid, (int)cells);
+                                                                        grid, (int)cells, geom);
     CPPF_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, const float* lut, const void* idx,
-                                  int idx_is_64, uint8_t* out_mask, const float* corner, const int64_t* argmax_flat,
-                                  float res, float tol, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz,
-                                  void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+int backvote_bins_launch(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                         uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
+                         int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, const Geom* geom,
+                         cudaStream_t stream) {
     if (n_pairs <= 0) return 0;
     if (n_rots > kMaxRotsP || n_rots <= 0) return (int)cudaErrorInvalidValue;
     if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
@@ -519,7 +682,7 @@ extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, cons
     if (terr) return terr;
     BackvotePParams prm{rot_tab, points, bins, lut, idx, out_mask, corner, reinterpret_cast<const long long*>(argmax_flat), res,
                         (float)(1.0 / (double)res), tol, (float)(gx - 1), (float)(gy - 1), (float)(gz - 1), n_points,
-                        (long long)n_pairs, n_rots, gx, gy, gz};
+                        (long long)n_pairs, n_rots, gx, gy, gz, geom};
     long long blocks = (n_pairs + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
@@ -527,6 +690,23 @@ extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, cons
     else backvote_bins_kernel<false><<<(int)blocks, 256, 0, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     return 0;
+}
+}  // namespace cppf
+
+extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut,
+                              const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
+                              int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
+                              void* stream_) {
+    return vote_fast_launch(points, mu_nu, bins, lut, idx, idx_is_64, grid, scratch, corner, res, n_points, n_pairs, n_rots,
+                            gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_);
+}
+
+extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, const float* lut, const void* idx,
+                                  int idx_is_64, uint8_t* out_mask, const float* corner, const int64_t* argmax_flat,
+                                  float res, float tol, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz,
+                                  void* stream_) {
+    return backvote_bins_launch(points, bins, lut, idx, idx_is_64, out_mask, corner, argmax_flat, res, tol, n_points, n_pairs,
+                                n_rots, gx, gy, gz, nullptr, (cudaStream_t)stream_);
 }
 
 extern "C" int cppf_rot_hist(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
@@ -538,13 +718,18 @@ extern "C" int cppf_rot_hist(const float* points, const uint8_t* bins, const flo
     int terr = 0;
     const float2* rot_tab = rot_table_device(stream, &terr);
     if (terr) return terr;
+    // half-width of the y window: |c - s|^2 < |c|^2 + |s|^2 - 2 thr with |c|, |s| <= 1 + 2e-6, plus slack
+    const float ywin = thr > 0.f ? sqrtf(fmaxf(0.f, 2.00002f - 2.f * thr)) + 1e-4f : 4.f;
     RotHistParams prm{rot_tab, points, bins, lut, idx, reinterpret_cast<const long long*>(pos),
                       reinterpret_cast<const long long*>(count), sphere, counts, n_points, n_rots, n_bins, which,
-                      (long long)max_samples, offset_seed, thr};
+                      (long long)max_samples, offset_seed, thr, ywin};
     const long long blocks = (max_samples + kRotHistPairs - 1) / kRotHistPairs;
     if (blocks > 0x7FFFFFFF) return (int)cudaErrorInvalidValue;
-    if (idx_is_64) rot_hist_kernel<true><<<(int)blocks, 512, 0, stream>>>(prm);
-    else rot_hist_kernel<false><<<(int)blocks, 512, 0, stream>>>(prm);
+    const size_t smem = (size_t)n_bins * 20;
+    if (smem > 160 * 1024) return (int)cudaErrorInvalidValue;
+    auto kern = idx_is_64 ? rot_hist_kernel<true> : rot_hist_kernel<false>;
+    if (smem > 40 * 1024) CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(int)blocks, kRotHistThreads, smem, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     return 0;
 }
@@ -558,7 +743,7 @@ extern "C" int cppf_survivor_stats(const float* points, const float* nrm, const 
     StatsParams prm{points, nrm, tail, idx, reinterpret_cast<const long long*>(pos),
                     reinterpret_cast<const long long*>(count), sphere, reinterpret_cast<const long long*>(best_up),
                     reinterpret_cast<const long long*>(best_right), out, n_points, (long long)n_pairs};
-    const int blocks = sm_count() * 4;
+    const int blocks = sm_count() * 8;
     if (idx_is_64) survivor_stats_kernel<true><<<blocks, 256, 0, stream>>>(prm);
     else survivor_stats_kernel<false><<<blocks, 256, 0, stream>>>(prm);
     CPPF_LAUNCH_CHECK();

@@ -17,7 +17,9 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from . import fast, voting
+import ctypes as C
+
+from . import _lib, fast, voting
 from .synth import vote_grid_geometry
 
 
@@ -58,6 +60,19 @@ class PoseConfig:
         return cls(**{k: (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in d.items() if k in keys})
 
 
+class PendingPose:
+    """A pose whose kernels are enqueued; .result() waits for its record and runs the host tail."""
+
+    def __init__(self, est, record_host, done, n_dirs, keep=(), staged=False):
+        self.est, self.record_host, self.done, self.n_dirs, self._keep, self.staged = est, record_host, done, n_dirs, keep, staged
+
+    def result(self):
+        self.done.synchronize()
+        r = self.record_host.numpy()
+        self._keep = ()
+        return self.est._pose_from_record(r, self.n_dirs) if self.staged else self.est._pose_from_record16(r, self.n_dirs)
+
+
 class PoseEstimator:
     """One category's encoders + constants.  ``estimate`` handles one object."""
 
@@ -72,6 +87,8 @@ class PoseEstimator:
         self.timers = None            # optional {name: [(start_event, end_event), ...]} filled by estimate()
         self.lut = fast.decode_lut(cfg.vote_range, cfg.tr_num_bins, cfg.rot_num_bins).to(self.device)
         self.encoder_impl = "tc"      # "tc": tcgen05 3xTF32 encoder (csrc/encode_tc.cu); "simt": fp32 FFMA (csrc/fused.cu)
+        self.timing = None            # optional cppf_timing_create() handle passed to cppf_pose_fused
+        self._ws, self._ws_key = None, None
 
     def _timed(self, name):
         est = self
@@ -255,12 +272,108 @@ class PoseEstimator:
                     n_survivors=int(st[3]), argmax_flat=flat, best_bins=bests,
                     record=np.concatenate([[0.0, st[3]], pred_scale, R.reshape(-1), T]).astype(np.float32))
 
+    # ------------------------------------------------------------------ one call per object
+    def _onecall_ok(self, cells=None):
+        lim = _lib.lib().cppf_vote_private_max_cells()
+        return (self.encoder_impl == "tc" and self.pe._fused_ok() and self.cfg.num_rots <= 72 and
+                self.ppf.out_dim == 141 and (cells is None or cells <= lim))
+
+    def _workspace(self, n, n_pairs, max_cells):
+        key = (n, n_pairs, max_cells)
+        if self._ws_key != key:
+            nb = _lib.lib().cppf_pose_workspace_bytes(n, n_pairs, self.cfg.knn, max_cells, self.sphere.shape[0])
+            self._ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
+            self._ws_key = key
+        return self._ws
+
+    @torch.no_grad()
+    def enqueue_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, inject_bins=None, max_cells=None,
+                      record_host=None):
+        """Enqueue the whole per-object path (cppf_pose_fused) on the current stream and return a PendingPose;
+        nothing here waits for the GPU.  pc_in / nrm_in: float32 [N,3], host (numpy or pinned torch) or CUDA.
+        max_cells: capacity of the vote grid (default: the actual cell count when the cloud is on the host, else
+        the largest grid the shared-memory vote supports)."""
+        cfg, dev = self.cfg, self.device
+        L = _lib.lib()
+        n = pc_in.shape[0]
+        on_dev = isinstance(pc_in, torch.Tensor) and pc_in.is_cuda
+        if max_cells is None:
+            if on_dev:
+                max_cells = L.cppf_vote_private_max_cells()
+            else:
+                _, dims = vote_grid_geometry(np.asarray(pc_in), cfg.res)
+                max_cells = dims[0] * dims[1] * dims[2]
+        if not self._onecall_ok(max_cells):
+            raise RuntimeError("cppf_pose_fused needs the tcgen05 encoder, the reference PointEncoder configuration and a "
+                               "vote grid that fits one SM's shared memory; use estimate_fused(staged=True)")
+        pc = torch.as_tensor(pc_in).to(dev, torch.float32, non_blocking=True).contiguous()
+        nrm = torch.as_tensor(nrm_in).to(dev, torch.float32, non_blocking=True).contiguous()
+        if idxs is None and cfg.n_pairs > 0:                                        # nocs/inference.py:177
+            g = torch.Generator(device=dev).manual_seed(seed)
+            idxs = torch.randint(0, n, (cfg.n_pairs, 2), generator=g, device=dev, dtype=torch.int32)
+        elif idxs is not None:
+            idxs = torch.as_tensor(idxs).to(dev).contiguous()
+            assert idxs.dtype in (torch.int32, torch.int64)
+        n_pairs = n * n if idxs is None else idxs.shape[0]
+        if uniforms is not None:
+            assert uniforms.shape == (n_pairs, 4) and uniforms.is_contiguous() and uniforms.dtype == torch.float32
+        if inject_bins is not None:
+            assert inject_bins.dtype == torch.uint8 and inject_bins.is_contiguous() and inject_bins.shape[0] == n_pairs
+        ws = self._workspace(n, n_pairs, int(max_cells))
+        rec = torch.empty(16, dtype=torch.float64, device=dev)
+        a = _lib.PoseArgs()
+        a.struct_bytes = C.sizeof(_lib.PoseArgs)
+        a.pc, a.nrm = pc.data_ptr(), nrm.data_ptr()
+        a.idx = idxs.data_ptr() if idxs is not None else None
+        a.pe_blob, a.tc_blob = self.pe.pe_blob(dev).data_ptr(), self.ppf.tc_blob(dev).data_ptr()
+        a.lut, a.sphere = self.lut.data_ptr(), self.sphere.data_ptr()
+        a.uniforms = uniforms.data_ptr() if uniforms is not None else None
+        a.inject_bins = inject_bins.data_ptr() if inject_bins is not None else None
+        a.workspace, a.record, a.timing = ws.data_ptr(), rec.data_ptr(), self.timing
+        a.n_pairs, a.workspace_bytes = n_pairs, ws.numel()
+        a.rot_subsample, a.seed = int(cfg.rot_subsample or 0), int(seed)
+        a.n_points, a.idx_is_64 = n, int(idxs is not None and idxs.dtype == torch.int64)
+        a.knn, a.n_rots, a.adaptive, a.regress_right = cfg.knn, cfg.num_rots, int(cfg.adaptive_voting), int(cfg.regress_right)
+        a.n_sphere, a.inject_cols, a.max_cells = self.sphere.shape[0], (inject_bins.shape[1] if inject_bins is not None else 0), \
+            int(max_cells)
+        a.res, a.tol, a.cos_thr = float(cfg.res), float(3 * cfg.res), self.cos_thr
+        with torch.cuda.device(dev):
+            _lib.check(L.cppf_pose_fused(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "cppf_pose_fused")
+        if record_host is None:
+            record_host = torch.empty(16, dtype=torch.float64, pin_memory=True)
+        record_host.copy_(rec, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return PendingPose(self, record_host, done, 2 if cfg.regress_right else 1, keep=(pc, nrm, idxs, uniforms, inject_bins, rec))
+
+    def _pose_from_record16(self, r, n_dirs):
+        if r[15] != 0:
+            raise RuntimeError("vote grid larger than the capacity given to cppf_pose_fused (status %d)" % int(r[15]))
+        self._last_dims = tuple(int(v) for v in r[12:15])
+        old = np.concatenate([[r[0]], r[1:1 + n_dirs], r[3:9], r[9:12]])
+        return self._pose_from_record(old, n_dirs)
+
     @torch.no_grad()
     def estimate_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, return_debug: bool = False,
-                       sync: bool = True, inject_bins=None):
+                       sync: bool = True, inject_bins=None, staged: bool = False, max_cells=None):
         """Same pose as `estimate`, through the fused kernels: logits, (mu,nu) floats and rotation
-        candidates never reach HBM; a single ~100-byte record comes back to the host.
-        With sync=False returns the device record (torch tensor) and a finisher callable."""
+        candidates never reach HBM; a single 128-byte record comes back to the host.  By default the whole
+        object is ONE library call (cppf_pose_fused); staged=True / return_debug=True run it kernel by kernel
+        (same kernels) and expose the intermediates.  sync=False returns a PendingPose (.result())."""
+        cells = None
+        if not (isinstance(pc_in, torch.Tensor) and pc_in.is_cuda):
+            _, d = vote_grid_geometry(np.asarray(pc_in), self.cfg.res)
+            cells = d[0] * d[1] * d[2]
+        if not (staged or return_debug) and self._onecall_ok(cells if max_cells is None else max_cells):
+            pend = self.enqueue_fused(pc_in, nrm_in, seed=seed, idxs=idxs, uniforms=uniforms, inject_bins=inject_bins,
+                                      max_cells=max_cells if max_cells is not None else cells)
+            return pend.result() if sync else pend
+        return self._estimate_fused_staged(pc_in, nrm_in, seed=seed, idxs=idxs, uniforms=uniforms, return_debug=return_debug,
+                                           sync=sync, inject_bins=inject_bins)
+
+    @torch.no_grad()
+    def _estimate_fused_staged(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, return_debug: bool = False,
+                               sync: bool = True, inject_bins=None):
         cfg, dev = self.cfg, self.device
         n = pc_in.shape[0]
         pc = torch.as_tensor(pc_in).to(dev, non_blocking=True)
@@ -311,7 +424,11 @@ class PoseEstimator:
         rec_dev = torch.cat([flat.double()] + [b.double() for b in bests] + [stats, corner.double()])
         nd = len(bests)
         if not sync:
-            return rec_dev, (lambda host: self._pose_from_record(host, nd))
+            host = torch.empty(rec_dev.shape, dtype=torch.float64, pin_memory=True)
+            host.copy_(rec_dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            return PendingPose(self, host, done, nd, keep=(rec_dev,), staged=True)
         out = self._pose_from_record(rec_dev.cpu().numpy(), nd)
         if return_debug:
             out.update(grid=grid, bins=bins, tail=tail, mask=mask, pos=pos, count=cnt, feat=feat, idxs=idxs, table=table)

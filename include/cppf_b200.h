@@ -204,6 +204,62 @@ int cppf_survivor_stats(const float* points, const float* nrm, const float* tail
                         const int64_t* pos, const int64_t* count, const float* sphere, const int64_t* best_up,
                         const int64_t* best_right, double* out, int n_points, int64_t n_pairs, void* stream);
 
+/* ==== one call per object ======================================================
+ * The whole script body of nocs/inference.py:174-339 (sunrgbd/inference.py:142-287) between "cloud on the
+ * device" and "pose record": vote-grid geometry (:194-195, derived on the device), kNN + SPRIN point encoder
+ * (:180-181), pair MLP + sampling (:182-188,:236-256), centre vote (:191-205), argmax (:207-211), back-vote +
+ * compaction (:216-231), orientation histogram(s) (:258-284), aux sign / scale sums (:286-302,:335).
+ * Everything is enqueued on `stream` without a host round trip; `record` (device, cppf_pose_record_doubles()
+ * doubles) receives
+ *   [0] argmax flat index | [1] best up bin | [2] best right bin (-1) | [3..5] sum of log-scales |
+ *   [6] survivor count | [7] S_up | [8] S_right | [9..11] grid corner | [12..14] grid dims | [15] status
+ * status 1 = the vote grid has more than max_cells cells (nothing was voted; use the staged entry points).
+ * The host tail (Gram-Schmidt, scale, RT: nocs/inference.py:305-339) is cppf_b200/pipeline.py.
+ * struct_bytes must be sizeof(cppf_pose_args).  All pointers are device pointers. */
+typedef struct cppf_pose_args {
+    int64_t struct_bytes;
+    const float* pc;             /* [n_points,3] */
+    const float* nrm;            /* [n_points,3] */
+    const void* idx;             /* [n_pairs,2] int32/int64 pairs (nocs/inference.py:177), or NULL: all n_points^2 ordered pairs */
+    const float* pe_blob;        /* packed PointEncoder weights (cppf_pe_blob_floats) */
+    const float* tc_blob;        /* packed PPFEncoder weights (cppf_tc_blob_floats) */
+    const float* lut;            /* [136] bin decode table (see "fused per-object path") */
+    const float* sphere;         /* [n_sphere,3] orientation bins (utils/util.py:102-118) */
+    const float* uniforms;       /* optional [n_pairs,4] sampling uniforms; NULL -> Philox keyed by (seed, pair) */
+    const uint8_t* inject_bins;  /* optional [n_pairs,inject_cols]: overwrite the sampled bins (benchmark/test aid) */
+    void* workspace;             /* cppf_pose_workspace_bytes(...) bytes */
+    double* record;              /* out */
+    void* timing;                /* optional cppf_timing_create() handle: CUDA events around every stage */
+    int64_t n_pairs;             /* ignored when idx == NULL */
+    int64_t workspace_bytes;
+    int64_t rot_subsample;       /* nocs/inference.py:279-281 (10000); 0 = every survivor */
+    uint64_t seed;
+    int n_points;
+    int idx_is_64;
+    int knn;                     /* config/config.yaml:21 (60) */
+    int n_rots;                  /* 72 */
+    int adaptive;
+    int regress_right;
+    int n_sphere;
+    int inject_cols;
+    int max_cells;               /* capacity of the vote grid: <= cppf_vote_private_max_cells() */
+    float res;
+    float tol;                   /* back-vote tolerance, float32(3 * res) at nocs/inference.py:226 */
+    float cos_thr;               /* float32(cos(angle_prec)) at :283 */
+} cppf_pose_args;
+int cppf_pose_record_doubles(void);
+int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int n_sphere);
+int cppf_pose_fused(const cppf_pose_args* args, void* stream);
+
+/* Stage timing for cppf_pose_fused: CUDA events recorded on the launching stream around every stage.
+ * cppf_timing_collect adds the elapsed milliseconds per stage of every call recorded since the last collect
+ * to h_ms_sum[cppf_timing_stages()] (HOST array), returns the number of calls and resets the handle. */
+void* cppf_timing_create(void);
+void cppf_timing_destroy(void* timing);
+int cppf_timing_stages(void);
+const char* cppf_timing_stage_name(int stage);
+int cppf_timing_collect(void* timing, float* h_ms_sum);
+
 #ifdef __cplusplus
 }
 #endif

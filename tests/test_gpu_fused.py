@@ -245,3 +245,46 @@ def test_fused_pipeline_equals_two_pass_pipeline(regress_right):
     diff = np.abs(fused["grid"].cpu().numpy() - two["grid"].cpu().numpy())
     assert (diff > 5e-3).mean() < 0.05
     assert np.isfinite(fused["RT"]).all() and abs(np.linalg.norm(fused["up"]) - 1) < 1e-6
+
+
+@pytest.mark.parametrize("regress_right,dense", [(False, False), (True, False), (False, True)])
+def test_one_call_pipeline_equals_staged_pipeline(regress_right, dense):
+    """cppf_pose_fused (one library call, geometry derived on the device, no host round trip) against the same
+    kernels launched stage by stage from Python with host-side geometry: identical record."""
+    torch.manual_seed(0)
+    pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(DEV).eval()
+    ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).to(DEV).eval()
+    n = 300 if dense else 700
+    n_pairs = 0 if dense else 30000
+    cfg = PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=n_pairs, rot_subsample=3000, regress_right=regress_right))
+    est = PoseEstimator(pe, ppf, cfg, DEV)
+    pc, nrm = synth.synth_bottle(n, 13)
+    idxs = None if dense else synth.sample_pairs(n, n_pairs, 13).astype(np.int32)
+    p = n * n if dense else n_pairs
+    u = torch.rand(p, 4, generator=torch.Generator().manual_seed(3)).to(DEV)
+    inj = None
+    if dense:       # trained-like bins, as bench.py injects them
+        inj = synth.trained_like_bins_dense_torch(torch.from_numpy(pc).to(DEV), synth.BOTTLE)
+    staged = est.estimate_fused(pc, nrm, seed=4, idxs=idxs, uniforms=u, inject_bins=inj, staged=True)
+    for src in ((pc, nrm), (torch.from_numpy(pc).to(DEV), torch.from_numpy(nrm).to(DEV))):     # host and resident inputs
+        one = est.estimate_fused(src[0], src[1], seed=4, idxs=idxs, uniforms=u, inject_bins=inj)
+        assert one["argmax_flat"] == staged["argmax_flat"]
+        assert one["best_bins"] == staged["best_bins"]
+        assert one["n_survivors"] == staged["n_survivors"] > 0
+        np.testing.assert_allclose(one["T_host"], staged["T_host"], rtol=0, atol=0)
+        np.testing.assert_allclose(one["pred_scale"], staged["pred_scale"], rtol=1e-6)
+        np.testing.assert_array_equal(one["RT"], staged["RT"])
+    # asynchronous use: several objects in flight, records read afterwards
+    pend = [est.estimate_fused(pc, nrm, seed=4, idxs=idxs, uniforms=u, inject_bins=inj, sync=False) for _ in range(3)]
+    for q in pend:
+        assert q.result()["argmax_flat"] == staged["argmax_flat"]
+
+
+def test_one_call_pipeline_reports_oversized_grid():
+    torch.manual_seed(0)
+    pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(DEV).eval()
+    ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).to(DEV).eval()
+    est = PoseEstimator(pe, ppf, PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=2000)), DEV)
+    pc, nrm = synth.synth_bottle(256, 1)
+    with pytest.raises(RuntimeError, match="capacity"):
+        est.estimate_fused(torch.from_numpy(pc).to(DEV), torch.from_numpy(nrm).to(DEV), max_cells=1000)
