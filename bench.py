@@ -37,8 +37,9 @@ if ROOT not in sys.path:
 METRIC = "point_pairs_per_sec"
 UNIT = "pairs/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1_tc_encoder_ncu.md, profiles/r1_fused_kernels_ncu.md), N=4096 dense
-TRAFFIC_NCU = {"encode_sample": 2.608128e6 + 347.031296e6, "vote": 67.345152e6 + 0.514816e6}
+# (profiles/r1b_fused_kernels_ncu.md, profiles/r1c_vote_sorted_ncu.md), N=4096 dense
+TRAFFIC_NCU = {"encode_sample": 3.485184e6 + 346.669056e6, "vote": 67.346432e6 + 0.404992e6,
+               "backvote": 67.203328e6 + 3.382784e6}
 
 
 def parse():
@@ -218,6 +219,7 @@ def main():
     dist_on = world > 1
     if dist_on:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's banner off stdout (one JSON line there)
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)

@@ -5,9 +5,11 @@
     -> compaction -> pair MLP on survivors -> sample axis angle -> orientation candidates
     -> sphere histogram -> aux sign -> scale -> RT
 
-Everything between the host->device copy of the cloud and the device->host copy of the
-17-float pose record stays on the GPU; the only host round trip inside is the survivor
-count (one int64) that sizes the second pass.
+Three entry points over the same kernels: ``estimate`` (materialised logits, the literal two-pass
+flow of the reference; one host round trip for the survivor count), ``estimate_fused(staged=True)``
+(fused kernels launched one by one, intermediates inspectable) and ``estimate_fused`` /
+``enqueue_fused`` (ONE library call per object, ``cppf_pose_fused``: nothing between the
+host->device copy of the cloud and the device->host copy of the 128-byte record waits for the GPU).
 """
 from __future__ import annotations
 
