@@ -57,6 +57,8 @@ struct Geom {
     float dhx, dhy, dhz;     // conservative upper bounds on (candidate - corner), before the division by res
     float bx, by, bz;        // float(dim - 1): bounds of the back-vote test (models/voting.py:104-107)
     int status;              // 0 ok, 1 = the grid exceeds the capacity the caller provided
+    int mode;                // 0: one shared-memory grid per CTA (vote_private), 1: routed x-slabs (vote_routed)
+    int planes_per_slab, n_slabs;   // mode 1
 };
 
 // (a, b) of pair p: from an int32/int64 index list, or row-major dense enumeration.

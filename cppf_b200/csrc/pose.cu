@@ -10,6 +10,7 @@
 // host never waits for the grid dimensions and successive objects queue back to back; the Python mirror
 // (cppf_b200/pipeline.py) turns the record into RT / scales exactly like nocs/inference.py:305-339.
 #include "common.cuh"
+#include "vote_common.cuh"
 
 #include "../../include/cppf_b200.h"
 
@@ -27,12 +28,20 @@ int backvote_bins_launch(const float* points, const uint8_t* bins, const float* 
                          uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
                          int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, const Geom* geom,
                          cudaStream_t stream);
+int vote_finalize_launch(const unsigned long long* acc, float* grid, int cells, const Geom* geom, int only_mode,
+                         cudaStream_t stream);
+int64_t routed_pool_bytes(int64_t n_pairs, int n_rots);
+long long slab_cap_cells();
+int vote_routed_launch(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, const void* idx,
+                       int idx_is_64, unsigned long long* acc, void* pool_mem, int64_t pool_bytes, const float* corner,
+                       float res, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
+                       const Geom* geom, cudaStream_t stream);
 int grid_argmax_launch(const float* grid, int64_t n_cells, const int* n_cells_dev, int64_t* out_index, float* out_value,
                        cudaStream_t stream);
 
 // ---- geometry: nocs/inference.py:194-195 in float32 like numpy (pc is float32, `res` a weak Python scalar)
 __global__ void __launch_bounds__(1024) geom_kernel(const float* __restrict__ pc, int n_points, float res, int max_cells,
-                                                    Geom* __restrict__ out) {
+                                                    int routed_max_cells, int slab_cap_cells, Geom* __restrict__ out) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
         const f3 p = ld3(pc, i);
@@ -68,7 +77,15 @@ __global__ void __launch_bounds__(1024) geom_kernel(const float* __restrict__ pc
         out->gx = dims[0]; out->gy = dims[1]; out->gz = dims[2];
         const long long cells = (long long)dims[0] * dims[1] * dims[2];
         out->cells = cells > 0x7FFFFFFF ? 0x7FFFFFFF : (int)cells;
-        out->status = cells > (long long)max_cells ? 1 : 0;
+        // one shared-memory grid per CTA if it fits, else x-slabs routed through HBM (vote_routed.cu), else give up
+        int pps = 1, n_slabs = 1;
+        const bool fits = cells <= (long long)max_cells;
+        const bool routed = !fits && cells <= (long long)routed_max_cells &&
+                            routed_plan_hd(dims[0], dims[1], dims[2], slab_cap_cells, &pps, &n_slabs);
+        out->status = (fits || routed) ? 0 : 1;
+        out->mode = routed ? 1 : 0;
+        out->planes_per_slab = pps;
+        out->n_slabs = n_slabs;
         float h[3], dh[3];
         for (int k = 0; k < 3; ++k) {
             h[k] = __double2float_ru((double)dims[k] - 1.01);                      // models/voting.py:37-39
@@ -139,10 +156,14 @@ struct Workspace {
     long long* best;
     double* stats;
     long long* count;
+    unsigned char* pool;
+    size_t pool_bytes;
     size_t bytes;
 };
 
-static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int max_cells, int n_sphere) {
+static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells, int n_rots,
+                       int n_sphere) {
+    const int cap_cells = max_cells > routed_max_cells ? max_cells : routed_max_cells;
     Carver c{reinterpret_cast<unsigned char*>(base)};
     Workspace w;
     w.geom = c.take<Geom>(1);
@@ -155,13 +176,15 @@ static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int m
     w.mask = c.take<uint8_t>((size_t)n_pairs);
     w.pos = c.take<long long>((size_t)n_pairs);
     w.compact_scratch = c.take<unsigned char>((size_t)cppf_compact_scratch_bytes(n_pairs));
-    w.grid = c.take<float>((size_t)max_cells);
-    w.acc = c.take<unsigned long long>((size_t)max_cells);
+    w.grid = c.take<float>((size_t)cap_cells);
+    w.acc = c.take<unsigned long long>((size_t)cap_cells);
     w.flat = c.take<long long>(2);
     w.counts = c.take<float>((size_t)n_sphere * 2);
     w.best = c.take<long long>(2);
     w.stats = c.take<double>(6);
     w.count = c.take<long long>(1);
+    w.pool_bytes = routed_max_cells > 0 ? (size_t)routed_pool_bytes(n_pairs, n_rots) : 0;
+    w.pool = c.take<unsigned char>(w.pool_bytes);
     w.bytes = (c.off + 255) & ~(size_t)255;
     return w;
 }
@@ -190,9 +213,10 @@ using namespace cppf;
 
 extern "C" int cppf_pose_record_doubles(void) { return 16; }
 
-extern "C" int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int n_sphere) {
+extern "C" int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells,
+                                             int n_rots, int n_sphere) {
     if (n_pairs <= 0) n_pairs = (int64_t)n_points * n_points;
-    return (int64_t)carve(nullptr, n_points, n_pairs, knn, max_cells, n_sphere).bytes;
+    return (int64_t)carve(nullptr, n_points, n_pairs, knn, max_cells, routed_max_cells, n_rots, n_sphere).bytes;
 }
 
 extern "C" void* cppf_timing_create(void) { return new Timing(); }
@@ -230,7 +254,9 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     if (n <= 0 || n_pairs <= 0 || a->knn <= 0 || a->knn > 64 || a->knn > n) return (int)cudaErrorInvalidValue;
     if (a->max_cells <= 0 || a->max_cells > cppf_vote_private_max_cells()) return (int)cudaErrorInvalidValue;
     if (a->n_sphere <= 0 || a->record == nullptr || a->workspace == nullptr) return (int)cudaErrorInvalidValue;
-    const Workspace w = carve(a->workspace, n, n_pairs, a->knn, a->max_cells, a->n_sphere);
+    if (a->routed_max_cells < 0 || a->routed_max_cells > kMaxSlabs * slab_cap_cells()) return (int)cudaErrorInvalidValue;
+    const Workspace w = carve(a->workspace, n, n_pairs, a->knn, a->max_cells, a->routed_max_cells, a->n_rots, a->n_sphere);
+    const int cap_cells = a->max_cells > a->routed_max_cells ? a->max_cells : a->routed_max_cells;
     if ((int64_t)w.bytes > a->workspace_bytes) return (int)cudaErrorInvalidValue;
     Timing* tm = reinterpret_cast<Timing*>(a->timing);
     auto mark = [&]() -> int {
@@ -246,7 +272,8 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     } while (0)
 
     CPPF_TRY(mark());
-    geom_kernel<<<1, 1024, 0, stream>>>(a->pc, n, a->res, a->max_cells, w.geom);
+    geom_kernel<<<1, 1024, 0, stream>>>(a->pc, n, a->res, a->max_cells, a->routed_max_cells, (int)slab_cap_cells(),
+                                        w.geom);
     CPPF_LAUNCH_CHECK();
     CPPF_TRY(mark());
     CPPF_TRY(cppf_knn(a->pc, n, a->knn, reinterpret_cast<int64_t*>(w.nbrs), stream));
@@ -264,11 +291,17 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
         CPPF_LAUNCH_CHECK();
     }
     CPPF_TRY(mark());
-    CPPF_RETURN_IF(cudaMemsetAsync(w.grid, 0, (size_t)a->max_cells * 4, stream));
+    CPPF_RETURN_IF(cudaMemsetAsync(w.grid, 0, (size_t)cap_cells * 4, stream));
     CPPF_TRY(vote_fast_launch(a->pc, nullptr, w.bins, a->lut, a->idx, a->idx_is_64, w.grid, w.acc, nullptr, a->res, n, n_pairs,
                               a->n_rots, 0, 0, 0, a->adaptive, w.geom, a->max_cells, stream));
+    if (a->routed_max_cells > 0) {      // grids of up to 8 shared-memory slabs: the kernels return at once unless geom->mode == 1
+        CPPF_RETURN_IF(cudaMemsetAsync(w.acc, 0, (size_t)cap_cells * 8, stream));
+        CPPF_TRY(vote_routed_launch(a->pc, nullptr, w.bins, a->lut, a->idx, a->idx_is_64, w.acc, w.pool, (int64_t)w.pool_bytes,
+                                    nullptr, a->res, n, n_pairs, a->n_rots, 0, 0, 0, a->adaptive, w.geom, stream));
+        CPPF_TRY(vote_finalize_launch(w.acc, w.grid, cap_cells, w.geom, 1, stream));
+    }
     CPPF_TRY(mark());
-    CPPF_TRY(grid_argmax_launch(w.grid, a->max_cells, &w.geom->cells, reinterpret_cast<int64_t*>(w.flat), nullptr, stream));
+    CPPF_TRY(grid_argmax_launch(w.grid, cap_cells, &w.geom->cells, reinterpret_cast<int64_t*>(w.flat), nullptr, stream));
     CPPF_TRY(mark());
     CPPF_TRY(backvote_bins_launch(a->pc, w.bins, a->lut, a->idx, a->idx_is_64, w.mask, nullptr,
                                   reinterpret_cast<const int64_t*>(w.flat), a->res, a->tol, n, n_pairs, a->n_rots, 0, 0, 0,

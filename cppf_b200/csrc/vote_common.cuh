@@ -1,0 +1,75 @@
+// Helpers shared by the shared-memory voting kernels (vote_private.cu, vote_routed.cu).
+#pragma once
+#include "common.cuh"
+
+#include <math.h>
+
+namespace cppf {
+
+constexpr int kMaxRotsP = 72;
+constexpr int kRotTabP = kMaxRotsP * (kMaxRotsP + 1) / 2;
+const float2* rot_table_device(cudaStream_t stream, int* err);   // vote.cu: (cos, sin) of angle(i, n), row n at n(n-1)/2
+
+// x-slabs of the routed vote (vote_routed.cu): as many planes per slab as fit `cap` u32 cells, minus the overlap
+// plane of the x+1 corners.  Shared by the host plan and the device-side geometry kernel (pose.cu).
+constexpr int kMaxSlabs = 8;
+__host__ __device__ inline bool routed_plan_hd(int gx, int gy, int gz, long long cap, int* pps, int* n_slabs) {
+    const long long gyz = (long long)gy * gz;
+    const long long planes = cap / gyz - 1;
+    if (planes < 1 || gx > 1024) return false;
+    *pps = (int)(planes < gx ? planes : gx);
+    *n_slabs = (gx + *pps - 1) / *pps;
+    return *n_slabs <= kMaxSlabs;
+}
+
+constexpr int kFixShift = 14;                      // fixed-point fraction bits of a vote weight
+constexpr float kFixScale = 16384.f;
+constexpr unsigned kFixBudget = 0xFFFFFFFFu >> kFixShift;   // whole votes a u32 cell can absorb between flushes
+
+static inline float float_ceil_p(double d) {
+    float f = (float)d;
+    if ((double)f < d) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+// a / b with b fixed: q0 = a*y, r = a - b*q0 (exact in an FMA), q = q0 + r*y.  With y the correctly
+// rounded reciprocal of b this returns the correctly rounded quotient (Markstein), i.e. the same
+// bits as the reference's `/ res`, in 3 instructions instead of the ~8 of an IEEE divide.
+__device__ __forceinline__ float div_by(float a, float b, float y) {
+    const float q0 = a * y;
+    const float r = fmaf(-b, q0, a);
+    return fmaf(r, y, q0);
+}
+
+// trilinear splat of one in-bounds candidate at grid coordinates g -- models/voting.py:40-63 with
+// prob == 1 (nocs/inference.py:201).  Each corner weight is rounded ONCE to 2^-14: the last product is an
+// FFMA onto 2^23, whose low mantissa bits are then the rounded fixed-point weight (no F2I on the XU pipe).
+__device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float gxf, float gyf, float gzf, int gyz, int gz) {
+    const int fx = (int)gxf, fy = (int)gyf, fz = (int)gzf;                     // :40
+    const float rx = gxf - floorf(gxf), ry = gyf - floorf(gyf), rz = gzf - floorf(gzf);
+    const float wx0 = 1.f - rx, wy0 = 1.f - ry;
+    const float z1 = rz * kFixScale, z0 = (1.f - rz) * kFixScale;
+    const float w00 = wx0 * wy0, w01 = wx0 * ry, w10 = rx * wy0, w11 = rx * ry;
+    constexpr float kMagic = 8388608.f;                                        // 2^23
+    constexpr unsigned kMagicBits = 0x4B000000u;
+    unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
+    atomicAdd(cell, __float_as_uint(fmaf(w00, z0, kMagic)) - kMagicBits);
+    atomicAdd(cell + 1, __float_as_uint(fmaf(w00, z1, kMagic)) - kMagicBits);
+    atomicAdd(cell + gz, __float_as_uint(fmaf(w01, z0, kMagic)) - kMagicBits);
+    atomicAdd(cell + gz + 1, __float_as_uint(fmaf(w01, z1, kMagic)) - kMagicBits);
+    atomicAdd(cell + gyz, __float_as_uint(fmaf(w10, z0, kMagic)) - kMagicBits);
+    atomicAdd(cell + gyz + 1, __float_as_uint(fmaf(w10, z1, kMagic)) - kMagicBits);
+    atomicAdd(cell + gyz + gz, __float_as_uint(fmaf(w11, z0, kMagic)) - kMagicBits);
+    atomicAdd(cell + gyz + gz + 1, __float_as_uint(fmaf(w11, z1, kMagic)) - kMagicBits);
+}
+
+__device__ __forceinline__ void st_shared_f4(unsigned addr, float x, float y, float z) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+}  // namespace cppf

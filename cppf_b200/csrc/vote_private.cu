@@ -8,35 +8,13 @@
 // shared-memory u32 atomics sustain ~2000 G/s (500+ G/s on hot cells) against 90-180 G/s
 // (16 G/s hot) for global fp32 reductions.
 #include "common.cuh"
+#include "vote_common.cuh"
 
 #include "../../include/cppf_b200.h"
 
 #include <math.h>
 
 namespace cppf {
-
-constexpr int kMaxRotsP = 72;
-constexpr int kRotTabP = kMaxRotsP * (kMaxRotsP + 1) / 2;
-const float2* rot_table_device(cudaStream_t stream, int* err);   // vote.cu: (cos, sin) of angle(i, n), row n at n(n-1)/2
-
-constexpr int kFixShift = 14;                      // fixed-point fraction bits of a vote weight
-constexpr float kFixScale = 16384.f;
-constexpr unsigned kFixBudget = 0xFFFFFFFFu >> kFixShift;   // whole votes a u32 cell can absorb between flushes
-
-static float float_ceil_p(double d) {
-    float f = (float)d;
-    if ((double)f < d) f = nextafterf(f, INFINITY);
-    return f;
-}
-
-// a / b with b fixed: q0 = a*y, r = a - b*q0 (exact in an FMA), q = q0 + r*y.  With y the correctly
-// rounded reciprocal of b this returns the correctly rounded quotient (Markstein), i.e. the same
-// bits as the reference's `/ res`, in 3 instructions instead of the ~8 of an IEEE divide.
-__device__ __forceinline__ float div_by(float a, float b, float y) {
-    const float q0 = a * y;
-    const float r = fmaf(-b, q0, a);
-    return fmaf(r, y, q0);
-}
 
 struct VotePParams {
     const float2* rot_tab;
@@ -65,37 +43,6 @@ constexpr int kVoteKeys = kMaxRotsP + 1;           // sort key = rotation count 
 // A batch adds at most kVoteBatch * 72 candidates * 2^14 units = 2.42e9 < 2^32 - 2^30 to any one cell.
 constexpr unsigned kFlushAt = 1u << 30;
 static_assert((unsigned long long)kVoteBatch * kMaxRotsP * (1ull << kFixShift) < (1ull << 32) - kFlushAt, "guard");
-
-// trilinear splat of one in-bounds candidate at grid coordinates g -- models/voting.py:40-63 with
-// prob == 1 (nocs/inference.py:201).  Each corner weight is rounded ONCE to 2^-14: the last product is an
-// FFMA onto 2^23, whose low mantissa bits are then the rounded fixed-point weight (no F2I on the XU pipe).
-__device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float gxf, float gyf, float gzf, int gyz, int gz) {
-    const int fx = (int)gxf, fy = (int)gyf, fz = (int)gzf;                     // :40
-    const float rx = gxf - floorf(gxf), ry = gyf - floorf(gyf), rz = gzf - floorf(gzf);
-    const float wx0 = 1.f - rx, wy0 = 1.f - ry;
-    const float z1 = rz * kFixScale, z0 = (1.f - rz) * kFixScale;
-    const float w00 = wx0 * wy0, w01 = wx0 * ry, w10 = rx * wy0, w11 = rx * ry;
-    constexpr float kMagic = 8388608.f;                                        // 2^23
-    constexpr unsigned kMagicBits = 0x4B000000u;
-    unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
-    atomicAdd(cell, __float_as_uint(fmaf(w00, z0, kMagic)) - kMagicBits);
-    atomicAdd(cell + 1, __float_as_uint(fmaf(w00, z1, kMagic)) - kMagicBits);
-    atomicAdd(cell + gz, __float_as_uint(fmaf(w01, z0, kMagic)) - kMagicBits);
-    atomicAdd(cell + gz + 1, __float_as_uint(fmaf(w01, z1, kMagic)) - kMagicBits);
-    atomicAdd(cell + gyz, __float_as_uint(fmaf(w10, z0, kMagic)) - kMagicBits);
-    atomicAdd(cell + gyz + 1, __float_as_uint(fmaf(w10, z1, kMagic)) - kMagicBits);
-    atomicAdd(cell + gyz + gz, __float_as_uint(fmaf(w11, z0, kMagic)) - kMagicBits);
-    atomicAdd(cell + gyz + gz + 1, __float_as_uint(fmaf(w11, z1, kMagic)) - kMagicBits);
-}
-
-__device__ __forceinline__ void st_shared_f4(unsigned addr, float x, float y, float z) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_f4(unsigned addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
 
 // Per batch of 2048 pairs a CTA
 //   (1) counting-sorts the pairs by their rotation count n (adaptive voting, models/voting.py:31: n depends
@@ -126,7 +73,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     const float* corner = prm.corner;
     if (prm.geom != nullptr) {
         const Geom g = *prm.geom;
-        if (g.status != 0 || g.cells > prm.max_cells) return;
+        if (g.status != 0 || g.mode != 0 || g.cells > prm.max_cells) return;
         gx = g.gx; gy = g.gy; gzd = g.gz;
         hx = g.hx; hy = g.hy; hz = g.hz; dhx = g.dhx; dhy = g.dhy; dhz = g.dhz;
         corner = prm.geom->corner;
@@ -299,8 +246,12 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
 
 // grid[i] += acc[i] * 2^-14   (exact integer sum -> one rounding; deterministic run to run)
 __global__ void __launch_bounds__(256) vote_finalize_kernel(const unsigned long long* __restrict__ acc,
-                                                            float* __restrict__ grid, int cells, const Geom* geom) {
-    if (geom != nullptr) cells = geom->status == 0 ? geom->cells : 0;
+                                                            float* __restrict__ grid, int cells, const Geom* geom,
+                                                            int only_mode) {
+    if (geom != nullptr) {
+        if (only_mode >= 0 && geom->mode != only_mode) return;
+        cells = geom->status == 0 ? min(geom->cells, cells) : 0;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cells) grid[i] += (float)((double)acc[i] * (1.0 / 16384.0));
 }
@@ -665,7 +616,14 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
     kern<<<(int)blocks, threads, smem, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     vote_finalize_kernel<<<(int)((cells + 255) / 256), 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(scratch),
-                                                                        grid, (int)cells, geom);
+                                                                        grid, (int)cells, geom, geom ? 0 : -1);
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}
+
+int vote_finalize_launch(const unsigned long long* acc, float* grid, int cells, const Geom* geom, int only_mode,
+                         cudaStream_t stream) {
+    vote_finalize_kernel<<<(cells + 255) / 256, 256, 0, stream>>>(acc, grid, cells, geom, only_mode);
     CPPF_LAUNCH_CHECK();
     return 0;
 }

@@ -90,6 +90,29 @@ def vote_fast(points, idxs, grid, corner, res, *, mu_nu=None, bins=None, lut=Non
     return grid
 
 
+def vote_routed_supported(dims) -> bool:
+    return bool(_lib.lib().cppf_vote_routed_supported(int(dims[0]), int(dims[1]), int(dims[2])))
+
+
+def vote_routed(points, idxs, grid, corner, res, *, mu_nu=None, bins=None, lut=None, n_rots=72, adaptive=True, scratch=None):
+    """Centre vote for grids of up to eight shared-memory slabs (cppf_vote_routed)."""
+    dev = points.device
+    n = points.shape[0]
+    ip, is64 = _idx_args(idxs)
+    n_pairs = n * n if idxs is None else idxs.shape[0]
+    gx, gy, gz = grid.shape
+    L = _lib.lib()
+    if scratch is None:
+        scratch = torch.empty(L.cppf_vote_routed_scratch_bytes(n_pairs, int(n_rots), gx, gy, gz), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.cppf_vote_routed(
+            points.data_ptr(), mu_nu.data_ptr() if mu_nu is not None else None,
+            bins.data_ptr() if bins is not None else None, lut.data_ptr() if lut is not None else None, ip, is64,
+            grid.data_ptr(), scratch.data_ptr(), scratch.numel(), corner.data_ptr(), float(res), n, n_pairs, int(n_rots),
+            gx, gy, gz, int(bool(adaptive)), _sp(dev)), "cppf_vote_routed")
+    return grid
+
+
 def backvote_bins(points, bins, lut, idxs, dims, corner, argmax_flat, res, tol, n_rots=72, mask=None):
     dev = points.device
     n = points.shape[0]

@@ -62,6 +62,13 @@ class PoseConfig:
         return cls(**{k: (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in d.items() if k in keys})
 
 
+_WORKSPACES = {}          # (device index, stream) -> uint8 workspace of cppf_pose_fused
+
+
+def release_workspaces():
+    _WORKSPACES.clear()
+
+
 class PendingPose:
     """A pose whose kernels are enqueued; .result() waits for its record and runs the host tail."""
 
@@ -71,8 +78,11 @@ class PendingPose:
     def result(self):
         self.done.synchronize()
         r = self.record_host.numpy()
+        if self.staged:
+            self._keep = ()
+            return self.est._pose_from_record(r, self.n_dirs)
         self._keep = ()
-        return self.est._pose_from_record(r, self.n_dirs) if self.staged else self.est._pose_from_record16(r, self.n_dirs)
+        return self.est._pose_from_record16(r, self.n_dirs)
 
 
 class PoseEstimator:
@@ -90,7 +100,7 @@ class PoseEstimator:
         self.lut = fast.decode_lut(cfg.vote_range, cfg.tr_num_bins, cfg.rot_num_bins).to(self.device)
         self.encoder_impl = "tc"      # "tc": tcgen05 3xTF32 encoder (csrc/encode_tc.cu); "simt": fp32 FFMA (csrc/fused.cu)
         self.timing = None            # optional cppf_timing_create() handle passed to cppf_pose_fused
-        self._ws, self._ws_key = None, None
+        self._routed_scratch, self._routed_key = None, None
 
     def _timed(self, name):
         est = self
@@ -275,39 +285,55 @@ class PoseEstimator:
                     record=np.concatenate([[0.0, st[3]], pred_scale, R.reshape(-1), T]).astype(np.float32))
 
     # ------------------------------------------------------------------ one call per object
-    def _onecall_ok(self, cells=None):
-        lim = _lib.lib().cppf_vote_private_max_cells()
-        return (self.encoder_impl == "tc" and self.pe._fused_ok() and self.cfg.num_rots <= 72 and
-                self.ppf.out_dim == 141 and (cells is None or cells <= lim))
+    def _onecall_ok(self):
+        return (self.encoder_impl == "tc" and self.pe._fused_ok() and self.cfg.num_rots <= 72 and self.ppf.out_dim == 141)
 
-    def _workspace(self, n, n_pairs, max_cells):
-        key = (n, n_pairs, max_cells)
-        if self._ws_key != key:
-            nb = _lib.lib().cppf_pose_workspace_bytes(n, n_pairs, self.cfg.knn, max_cells, self.sphere.shape[0])
-            self._ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
-            self._ws_key = key
-        return self._ws
+    def _workspace(self, n, n_pairs, max_cells, routed_max_cells):
+        """One workspace per (device, stream), shared by every estimator (categories differ only in weights) and
+        grown on demand: work on one stream is ordered, so successive objects can reuse it."""
+        nb = _lib.lib().cppf_pose_workspace_bytes(n, n_pairs, self.cfg.knn, max_cells, routed_max_cells, self.cfg.num_rots,
+                                                  self.sphere.shape[0])
+        slot = (self.device.index or 0, torch.cuda.current_stream(self.device).cuda_stream)
+        ws = _WORKSPACES.get(slot)
+        if ws is None or ws.numel() < nb:
+            _WORKSPACES[slot] = None
+            ws = _WORKSPACES[slot] = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def grid_capacity(self, pc_in):
+        """(max_cells, routed_max_cells) for cppf_pose_fused from the cloud's bounding box (nocs/inference.py:194-195):
+        the exact cell count in the slot of the vote kernel that will run, or None when the grid needs the
+        global-reduction kernel of the staged path.  Costs one small device->host copy for a CUDA tensor."""
+        if isinstance(pc_in, torch.Tensor) and pc_in.is_cuda:
+            lo = pc_in.min(0)[0]
+            dims = tuple(int(v) for v in (((pc_in.max(0)[0] - lo) / self.cfg.res).int() + 1).cpu())
+        else:
+            _, dims = vote_grid_geometry(np.asarray(pc_in), self.cfg.res)
+        cells = dims[0] * dims[1] * dims[2]
+        if fast.vote_fits_private(dims):
+            return cells, 0
+        if fast.vote_routed_supported(dims):
+            return 1, cells
+        return None
 
     @torch.no_grad()
     def enqueue_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, inject_bins=None, max_cells=None,
-                      record_host=None):
+                      routed_max_cells=0, record_host=None):
         """Enqueue the whole per-object path (cppf_pose_fused) on the current stream and return a PendingPose;
-        nothing here waits for the GPU.  pc_in / nrm_in: float32 [N,3], host (numpy or pinned torch) or CUDA.
-        max_cells: capacity of the vote grid (default: the actual cell count when the cloud is on the host, else
-        the largest grid the shared-memory vote supports)."""
+        nothing here waits for the GPU when max_cells is given.  pc_in / nrm_in: float32 [N,3], host (numpy or
+        pinned torch) or CUDA.  max_cells / routed_max_cells: capacity of the vote grid in the shared-memory kernel /
+        in the routed-slab kernel (see grid_capacity; default: derived from the cloud's bounding box)."""
         cfg, dev = self.cfg, self.device
         L = _lib.lib()
         n = pc_in.shape[0]
-        on_dev = isinstance(pc_in, torch.Tensor) and pc_in.is_cuda
         if max_cells is None:
-            if on_dev:
-                max_cells = L.cppf_vote_private_max_cells()
-            else:
-                _, dims = vote_grid_geometry(np.asarray(pc_in), cfg.res)
-                max_cells = dims[0] * dims[1] * dims[2]
-        if not self._onecall_ok(max_cells):
-            raise RuntimeError("cppf_pose_fused needs the tcgen05 encoder, the reference PointEncoder configuration and a "
-                               "vote grid that fits one SM's shared memory; use estimate_fused(staged=True)")
+            cap = self.grid_capacity(pc_in)
+            if cap is None:
+                raise RuntimeError("vote grid too large for cppf_pose_fused; use estimate_fused(staged=True)")
+            max_cells, routed_max_cells = cap
+        if not self._onecall_ok():
+            raise RuntimeError("cppf_pose_fused needs the tcgen05 encoder and the reference PointEncoder / head "
+                               "configuration; use estimate_fused(staged=True)")
         pc = torch.as_tensor(pc_in).to(dev, torch.float32, non_blocking=True).contiguous()
         nrm = torch.as_tensor(nrm_in).to(dev, torch.float32, non_blocking=True).contiguous()
         if idxs is None and cfg.n_pairs > 0:                                        # nocs/inference.py:177
@@ -321,7 +347,7 @@ class PoseEstimator:
             assert uniforms.shape == (n_pairs, 4) and uniforms.is_contiguous() and uniforms.dtype == torch.float32
         if inject_bins is not None:
             assert inject_bins.dtype == torch.uint8 and inject_bins.is_contiguous() and inject_bins.shape[0] == n_pairs
-        ws = self._workspace(n, n_pairs, int(max_cells))
+        ws = self._workspace(n, n_pairs, int(max_cells), int(routed_max_cells))
         rec = torch.empty(16, dtype=torch.float64, device=dev)
         a = _lib.PoseArgs()
         a.struct_bytes = C.sizeof(_lib.PoseArgs)
@@ -336,8 +362,8 @@ class PoseEstimator:
         a.rot_subsample, a.seed = int(cfg.rot_subsample or 0), int(seed)
         a.n_points, a.idx_is_64 = n, int(idxs is not None and idxs.dtype == torch.int64)
         a.knn, a.n_rots, a.adaptive, a.regress_right = cfg.knn, cfg.num_rots, int(cfg.adaptive_voting), int(cfg.regress_right)
-        a.n_sphere, a.inject_cols, a.max_cells = self.sphere.shape[0], (inject_bins.shape[1] if inject_bins is not None else 0), \
-            int(max_cells)
+        a.n_sphere, a.inject_cols = self.sphere.shape[0], (inject_bins.shape[1] if inject_bins is not None else 0)
+        a.max_cells, a.routed_max_cells = int(max_cells), int(routed_max_cells)
         a.res, a.tol, a.cos_thr = float(cfg.res), float(3 * cfg.res), self.cos_thr
         with torch.cuda.device(dev):
             _lib.check(L.cppf_pose_fused(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "cppf_pose_fused")
@@ -357,19 +383,17 @@ class PoseEstimator:
 
     @torch.no_grad()
     def estimate_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, return_debug: bool = False,
-                       sync: bool = True, inject_bins=None, staged: bool = False, max_cells=None):
+                       sync: bool = True, inject_bins=None, staged: bool = False, max_cells=None, routed_max_cells=0):
         """Same pose as `estimate`, through the fused kernels: logits, (mu,nu) floats and rotation
         candidates never reach HBM; a single 128-byte record comes back to the host.  By default the whole
         object is ONE library call (cppf_pose_fused); staged=True / return_debug=True run it kernel by kernel
         (same kernels) and expose the intermediates.  sync=False returns a PendingPose (.result())."""
-        cells = None
-        if not (isinstance(pc_in, torch.Tensor) and pc_in.is_cuda):
-            _, d = vote_grid_geometry(np.asarray(pc_in), self.cfg.res)
-            cells = d[0] * d[1] * d[2]
-        if not (staged or return_debug) and self._onecall_ok(cells if max_cells is None else max_cells):
-            pend = self.enqueue_fused(pc_in, nrm_in, seed=seed, idxs=idxs, uniforms=uniforms, inject_bins=inject_bins,
-                                      max_cells=max_cells if max_cells is not None else cells)
-            return pend.result() if sync else pend
+        if not (staged or return_debug) and self._onecall_ok():
+            cap = (max_cells, routed_max_cells) if max_cells is not None else self.grid_capacity(pc_in)
+            if cap is not None:
+                pend = self.enqueue_fused(pc_in, nrm_in, seed=seed, idxs=idxs, uniforms=uniforms, inject_bins=inject_bins,
+                                          max_cells=cap[0], routed_max_cells=cap[1])
+                return pend.result() if sync else pend
         return self._estimate_fused_staged(pc_in, nrm_in, seed=seed, idxs=idxs, uniforms=uniforms, return_debug=return_debug,
                                            sync=sync, inject_bins=inject_bins)
 
@@ -406,7 +430,15 @@ class PoseEstimator:
             if fast.vote_fits_private(dims) and cfg.num_rots <= 72:
                 fast.vote_fast(pc, idxs, grid, corner, cfg.res, bins=bins, lut=self.lut, n_rots=cfg.num_rots,
                                adaptive=cfg.adaptive_voting)
-            else:                                   # grid too large for one SM's shared memory: global fp32 reductions
+            elif fast.vote_routed_supported(dims) and cfg.num_rots <= 72:     # up to 8 shared-memory slabs (64^3)
+                if self._routed_scratch is None or self._routed_key != (n, idxs is None, dims):
+                    n_pairs = n * n if idxs is None else idxs.shape[0]
+                    nb = _lib.lib().cppf_vote_routed_scratch_bytes(n_pairs, cfg.num_rots, *dims)
+                    self._routed_scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+                    self._routed_key = (n, idxs is None, dims)
+                fast.vote_routed(pc, idxs, grid, corner, cfg.res, bins=bins, lut=self.lut, n_rots=cfg.num_rots,
+                                 adaptive=cfg.adaptive_voting, scratch=self._routed_scratch)
+            else:                                   # larger still (scene-scale grids): global fp32 reductions
                 b = bins.long()
                 mu_nu = torch.stack([self.lut[b[:, 0]], self.lut[32 + b[:, 1]]], -1).contiguous()
                 voting.ppf_vote(pc, mu_nu, idxs, grid, corner, cfg.res, cfg.num_rots, cfg.adaptive_voting)
@@ -435,3 +467,12 @@ class PoseEstimator:
         if return_debug:
             out.update(grid=grid, bins=bins, tail=tail, mask=mask, pos=pos, count=cnt, feat=feat, idxs=idxs, table=table)
         return out
+
+
+def estimate_many(items, sync: bool = True):
+    """Batch of objects, possibly of different categories: items = [(estimator, pc, normals, seed), ...]
+    (the reference loops over them one at a time and picks the category's weights, nocs/inference.py:120-129).
+    Every object is enqueued before the first record is read, so the GPU works through the batch without
+    waiting for the host.  Returns the list of pose dicts (or PendingPose objects with sync=False)."""
+    pend = [est.estimate_fused(pc, nrm, seed=seed, sync=False) for est, pc, nrm, seed in items]
+    return [p.result() for p in pend] if sync else pend

@@ -182,6 +182,18 @@ int cppf_vote_fast(const float* points, const float* mu_nu, const uint8_t* bins,
                    const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
                    int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, void* stream);
 
+/* The same contract for grids of up to eight shared-memory slabs (e.g. the 64^3 grid of BASELINE config 3, 1 MB):
+ * candidates are routed through HBM to the x-slab that owns them (32 B per in-bounds candidate) and accumulated
+ * in that slab's shared-memory copy (csrc/vote_routed.cu).  Same fixed-point sums, hence the same grid as
+ * cppf_vote_fast would produce.  scratch: >= cppf_vote_routed_scratch_bytes(...) is recommended (room for every
+ * candidate of 4M pairs per pass); smaller scratch means more passes, too small returns cudaErrorInvalidValue. */
+int cppf_vote_routed_supported(int gx, int gy, int gz);
+int64_t cppf_vote_routed_scratch_bytes(int64_t n_pairs, int n_rots, int gx, int gy, int gz);
+int cppf_vote_routed(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut,
+                     const void* idx, int idx_is_64, float* grid, void* scratch, int64_t scratch_bytes,
+                     const float* corner, float res, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz,
+                     int adaptive, void* stream);
+
 /* models/voting.py:74-112 + nocs/inference.py:207-211,229-230 from bins: the winning cell is
  * read from device memory (*argmax_flat), centre = corner + cell*res as at :209; out_mask[p] =
  * any(out_offsets[p] != 0). */
@@ -213,7 +225,7 @@ int cppf_survivor_stats(const float* points, const float* nrm, const float* tail
  * doubles) receives
  *   [0] argmax flat index | [1] best up bin | [2] best right bin (-1) | [3..5] sum of log-scales |
  *   [6] survivor count | [7] S_up | [8] S_right | [9..11] grid corner | [12..14] grid dims | [15] status
- * status 1 = the vote grid has more than max_cells cells (nothing was voted; use the staged entry points).
+ * status 1 = the vote grid exceeds max_cells and routed_max_cells (nothing was voted; use the staged entry points).
  * The host tail (Gram-Schmidt, scale, RT: nocs/inference.py:305-339) is cppf_b200/pipeline.py.
  * struct_bytes must be sizeof(cppf_pose_args).  All pointers are device pointers. */
 typedef struct cppf_pose_args {
@@ -242,13 +254,16 @@ typedef struct cppf_pose_args {
     int regress_right;
     int n_sphere;
     int inject_cols;
-    int max_cells;               /* capacity of the vote grid: <= cppf_vote_private_max_cells() */
+    int max_cells;               /* capacity of the shared-memory vote grid: <= cppf_vote_private_max_cells() */
+    int routed_max_cells;        /* 0, or the capacity for larger grids voted through routed x-slabs
+                                    (cppf_vote_routed): <= 8 * 56320 */
     float res;
     float tol;                   /* back-vote tolerance, float32(3 * res) at nocs/inference.py:226 */
     float cos_thr;               /* float32(cos(angle_prec)) at :283 */
 } cppf_pose_args;
 int cppf_pose_record_doubles(void);
-int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int n_sphere);
+int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells, int n_rots,
+                                  int n_sphere);
 int cppf_pose_fused(const cppf_pose_args* args, void* stream);
 
 /* Stage timing for cppf_pose_fused: CUDA events recorded on the launching stream around every stage.

@@ -288,3 +288,49 @@ def test_one_call_pipeline_reports_oversized_grid():
     pc, nrm = synth.synth_bottle(256, 1)
     with pytest.raises(RuntimeError, match="capacity"):
         est.estimate_fused(torch.from_numpy(pc).to(DEV), torch.from_numpy(nrm).to(DEV), max_cells=1000)
+
+
+def test_vote_routed_64_cube_matches_oracle_and_global_kernel():
+    """64^3 grid (BASELINE config 3): too large for one SM's shared memory -> candidates are routed through
+    HBM to 7 x-slabs (cppf_vote_routed).  Same fixed-point sums as the privatised kernel: exact vs the oracle
+    up to the 2^-14 weight rounding, deterministic, same argmax as the global-reduction kernel."""
+    res = 4e-3
+    n, p = 1024, 120000
+    pc, _ = synth.synth_cylinder_grid64(n, 2, res=res)
+    corner, dims = synth.vote_grid_geometry(pc, res)
+    assert dims == (64, 64, 64) and not fast.vote_fits_private(dims) and fast.vote_routed_supported(dims)
+    idxs = synth.sample_pairs(n, p, 2)
+    tr = synth.trained_like_tr(pc, idxs)
+    ref = clib.ppf_voting(pc, tr, np.ones(n, np.float32), idxs.astype(np.int32), dims, corner, res, 72, True, f64=True)
+    grids = []
+    for _ in range(2):
+        g = torch.zeros(dims, device=DEV)
+        fast.vote_routed(_t(pc), _t(idxs, torch.int32), g, _t(corner), res, mu_nu=_t(tr))
+        grids.append(g)
+    assert torch.equal(grids[0], grids[1])
+    got = grids[0].cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=5e-3)
+    assert int(voting.grid_argmax(grids[0]).item()) == int(np.argmax(ref))
+    assert abs(float(got.sum()) - float(ref.sum())) / float(ref.sum()) < 1e-5
+    # dense pairs from bins, two passes over a deliberately small pool (scratch sized for 60 % of the pairs)
+    n2 = 640
+    pc2, _ = synth.synth_cylinder_grid64(n2, 3, res=res)
+    corner2, dims2 = synth.vote_grid_geometry(pc2, res)
+    inj = synth.trained_like_bins_dense_torch(torch.from_numpy(pc2).to(DEV), dict(synth.BOTTLE))
+    bins = torch.zeros(n2 * n2, 4, dtype=torch.uint8, device=DEV)
+    bins[:, :3] = inj
+    lut = fast.decode_lut(synth.BOTTLE["vote_range"]).to(DEV)
+    full = torch.zeros(dims2, device=DEV)
+    fast.vote_routed(_t(pc2), None, full, _t(corner2), res, bins=bins, lut=lut)
+    from cppf_b200 import _lib
+    nb = _lib.lib().cppf_vote_routed_scratch_bytes(n2 * n2 * 6 // 10, 72, *dims2)
+    small = torch.zeros(dims2, device=DEV)
+    fast.vote_routed(_t(pc2), None, small, _t(corner2), res, bins=bins, lut=lut,
+                     scratch=torch.empty(nb, dtype=torch.uint8, device=DEV))
+    assert torch.equal(full, small)
+    b = bins.long()
+    mu_nu = torch.stack([lut[b[:, 0]], lut[32 + b[:, 1]]], -1).contiguous()
+    slow = torch.zeros(dims2, device=DEV)
+    voting.ppf_vote(_t(pc2), mu_nu, None, slow, _t(corner2), res, 72, True)
+    np.testing.assert_allclose(full.cpu().numpy(), slow.cpu().numpy(), rtol=2e-4, atol=2e-2)
+    assert int(voting.grid_argmax(full).item()) == int(voting.grid_argmax(slow).item())

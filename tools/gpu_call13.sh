@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -k 10 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+timeout -k 10 600 python tools/config_sweep.py 3 > gpurun_out/config_sweep3.json 2> gpurun_out/config_sweep3.err; echo "rc=$?" >> gpurun_out/config_sweep3.err
+ls -la gpurun_out
