@@ -53,6 +53,11 @@ SIGNATURES = {
     "cppf_backvote_bins": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _f, _f, _i, _i64, _i, _i, _i, _i, _p]),
     "cppf_rot_hist": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i64, C.c_uint64, _f, _p]),
     "cppf_survivor_stats": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i64, _p]),
+    "cppf_backproject_scratch_bytes": (_i64, [_i, _i]),
+    "cppf_backproject": (_i, [_p, _i, _p, _i, _i, _p, C.c_double, _p, _p, _p, _p, _p]),
+    "cppf_voxel_scratch_bytes": (_i64, [_i64]),
+    "cppf_voxel_first": (_i, [_p, _p, _i64, C.c_double, _p, _p, _p, _p, _p]),
+    "cppf_normals_pca": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "cppf_pose_record_doubles": (_i, []),
     "cppf_pose_workspace_bytes": (_i64, [_i, _i64, _i, _i, _i, _i, _i]),
     "cppf_pose_fused": (_i, [_p, _p]),

@@ -275,6 +275,35 @@ int cppf_timing_stages(void);
 const char* cppf_timing_stage_name(int stage);
 int cppf_timing_collect(void* timing, float* h_ms_sum);
 
+/* ==== per-object pre-processing =====================
+ * What nocs/inference.py:131-142 does on the host with numpy / MinkowskiEngine / open3d before the hot path,
+ * on the device.  Coordinates stay float64 until after the voxel quantisation, where the reference casts (:141).
+ *
+ * cppf_backproject replaces utils/util.py:598-631 `backproject` + nocs/inference.py:132,136-137: for every pixel
+ * with mask != 0 and depth > 0, in row-major (np.where) order, out_pts[k] = ((Kinv @ (u, v, 1)) * z / w) / depth_scale
+ * (float64 [<= H*W, 3]; the two axis flips of the reference cancel), out_pix[k] = v * width + u, *out_count = number
+ * of points.  depth: uint16 (depth_is_u16, the NOCS png format) or float32 [H, W]; h_intrinsics_inv: 9 doubles on the
+ * HOST (np.linalg.inv(intrinsics), utils/util.py:599).  scratch: cppf_backproject_scratch_bytes(H, W).
+ *
+ * cppf_voxel_first stands in for ME.utils.sparse_quantize(pc, return_index=True, quantization_size=res)[1]
+ * (nocs/inference.py:140): voxel = floor(p / voxel) per axis; the FIRST point of every occupied voxel is kept, indices
+ * increasing (MinkowskiEngine's own pick/order inside a voxel is an implementation detail of its hash map).
+ * pts float64 [n_max, 3], *count (optional device int64) limits the valid prefix; out_index int64 [<= n_max],
+ * out_pc (optional) float32 [<= n_max, 3] = float32(pts[out_index]) (:141).
+ *
+ * cppf_normals_pca stands in for open3d estimate_normals(KDTreeSearchParamKNN(knn)) (utils/util.py:61-65): covariance
+ * of the k nearest neighbours (self included, cppf_knn) in float64, unit eigenvector of the smallest eigenvalue.
+ * orient 0: raw sign (open3d leaves it unspecified); 1: towards the camera at the origin.  nbrs_scratch: int64
+ * [n_points, k]. */
+int64_t cppf_backproject_scratch_bytes(int height, int width);
+int cppf_backproject(const void* depth, int depth_is_u16, const uint8_t* mask, int height, int width,
+                     const double* h_intrinsics_inv, double depth_scale, double* out_pts, int64_t* out_pix,
+                     int64_t* out_count, void* scratch, void* stream);
+int64_t cppf_voxel_scratch_bytes(int64_t n_max);
+int cppf_voxel_first(const double* pts, const int64_t* count, int64_t n_max, double voxel, float* out_pc,
+                     int64_t* out_index, int64_t* out_count, void* scratch, void* stream);
+int cppf_normals_pca(const float* pc, int n_points, int k, int orient, int64_t* nbrs_scratch, float* normals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,9 @@ pairs.  This script (run in the build container, where /root/reference exists):
 * ``ast``-extracts ``fibonacci_sphere`` (utils/util.py:102-118) and ``generate_target``
   (utils/dataset.py:20-60) -- their modules cannot be imported (open3d, pyrender) --
   and executes them -> ``tests/golden/host_glue.npz``;
-* records ``torch.multinomial`` draws next to the Exp(1) noise that reproduces them.
+* records ``torch.multinomial`` draws next to the Exp(1) noise that reproduces them;
+* ``ast``-extracts ``backproject`` (utils/util.py:598-631) and runs it on a window of the reference's demo depth
+  frame -> ``tests/golden/preprocess_demo.npz``.
 
 Nothing here is needed at test time on the GPU box; the .npz files travel.
 """
@@ -134,9 +136,32 @@ def host_glue_fixture():
           bool((torch.argmax(probs / q, -1) == draws).all()))
 
 
+def preprocess_fixture():
+    """utils/util.py:598-631 `backproject` (ast-extracted: the module imports open3d) executed on a window of the
+    reference's demo frame data/demo/0000_depth.png with the NOCS intrinsics of nocs/inference.py:98."""
+    import cv2
+    ns = {"np": np}
+    exec(_extract_function(os.path.join(REF, "utils", "util.py"), "backproject"), ns)
+    depth_full = cv2.imread(os.path.join(REF, "data", "demo", "0000_depth.png"), -1)
+    r0, c0, h, w = 200, 260, 96, 128
+    depth = np.ascontiguousarray(depth_full[r0:r0 + h, c0:c0 + w])
+    yy, xx = np.mgrid[0:h, 0:w]
+    mask = ((yy - 48) ** 2 / 40.0 ** 2 + (xx - 64) ** 2 / 56.0 ** 2) <= 1.0           # an elliptical "instance"
+    intr = np.array([[591.0125, 0, 322.525], [0, 590.16775, 244.11084], [0, 0, 1]])    # nocs/inference.py:98
+    intr_win = intr.copy()
+    intr_win[0, 2] -= c0
+    intr_win[1, 2] -= r0
+    pts, idxs = ns["backproject"](depth, intr_win, mask)
+    np.savez_compressed(os.path.join(OUT, "preprocess_demo.npz"), depth=depth, mask=mask, intrinsics=intr_win, pts=pts,
+                        rows=idxs[0].astype(np.int64), cols=idxs[1].astype(np.int64))
+    print("preprocess_demo.npz", depth.shape, depth.dtype, "valid", len(pts))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)            # deterministic reduction order for the fixtures
-    encoder_fixture()
-    voting_fixture()
-    host_glue_fixture()
+    only = sys.argv[1:]
+    for name, fn in (("encoder", encoder_fixture), ("voting", voting_fixture), ("host_glue", host_glue_fixture),
+                     ("preprocess", preprocess_fixture)):
+        if not only or name in only:
+            fn()
