@@ -58,6 +58,9 @@ SIGNATURES = {
     "cppf_voxel_scratch_bytes": (_i64, [_i64]),
     "cppf_voxel_first": (_i, [_p, _p, _i64, C.c_double, _p, _p, _p, _p, _p]),
     "cppf_normals_pca": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "cppf_pair_filter": (_i, [_p, _p, _p, _i, _i, _i64, _p, _p]),
+    "cppf_gaussian3d": (_i, [_p, _p, _p, _i, _i, _i, C.c_double, C.c_double, _p]),
+    "cppf_scene_proposals": (_i, [_p, _i, _i, _i, _f, _i, _f, _i, _p, _p, _p]),
     "cppf_pose_record_doubles": (_i, []),
     "cppf_pose_workspace_bytes": (_i64, [_i, _i64, _i, _i, _i, _i, _i]),
     "cppf_pose_fused": (_i, [_p, _p]),

@@ -304,6 +304,28 @@ int cppf_voxel_first(const double* pts, const int64_t* count, int64_t n_max, dou
                      int64_t* out_index, int64_t* out_count, void* scratch, void* stream);
 int cppf_normals_pca(const float* pc, int n_points, int k, int orient, int64_t* nbrs_scratch, float* normals, void* stream);
 
+/* ==== scene-scale ("zero-shot") mode: nocs/zero_shot.ipynb ============
+ * The notebook votes ~5 M random pairs of a whole depth frame into one scene-sized grid (cppf_ppf_vote), smooths it,
+ * extracts several peaks greedily and refines each with the per-object entry points above.  Cell = code cell of the
+ * notebook.
+ *
+ * cppf_pair_filter (cell 6): out_keep[p] = 0 for indistinguishable pairs (|n_a.n_b| > 0.9 and |ab.n_a| < 0.1 and
+ * |ab.n_b| < 0.1, ab the unit vector a - b), else 1.
+ * cppf_gaussian3d (cell 9): scipy.ndimage.gaussian_filter(grid, sigma, truncate=truncate) for a float32 [gx,gy,gz] grid:
+ * separable, radius int(truncate*sigma + 0.5), mode 'reflect', axis 0 then 1 then 2, each pass accumulated in float64 and
+ * rounded to float32 like scipy.  tmp: a second [gx,gy,gz] float32 buffer; out may not alias grid.
+ * cppf_scene_proposals (cell 9): greedy peaks of `grid` (modified in place: accepted boxes are zeroed): argmax, contrast =
+ * value - mean of the means over the 12 edges of the box loc +- margin; a proposal is kept while contrast > thresh; the
+ * loop stops at contrast < thresh or contrast < rel_stop * first contrast (0.7 in the notebook), or at max_props.
+ * h_out: HOST float [max_props][5] = loc x, y, z, value, contrast.  Returns the proposal count, or -(CUDA error).
+ * scratch: 64 device bytes.  Synchronises the stream once per proposal. */
+int cppf_pair_filter(const float* pc, const float* nrm, const void* idx, int idx_is_64, int n_points, int64_t n_pairs,
+                     uint8_t* out_keep, void* stream);
+int cppf_gaussian3d(const float* grid, float* out, float* tmp, int gx, int gy, int gz, double sigma, double truncate,
+                    void* stream);
+int cppf_scene_proposals(float* grid, int gx, int gy, int gz, float thresh, int margin, float rel_stop, int max_props,
+                         float* h_out, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
