@@ -169,28 +169,68 @@ __device__ __forceinline__ void st_chunk(unsigned char* a_hi, int c, int row, fl
     *reinterpret_cast<float4*>(a_hi + kABytes + c * kAPlane + row * 16) = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
 }
 
-// One categorical draw from NB logits in registers: e_k = 2^((l_k - max) log2 e);
-// bin = #{k : cumsum(e)_k <= u * sum(e)}, clamped (same operation order as fused.cu / the oracle).
+// One categorical draw from NB logits in registers.  The logits arrive in log2 units (the host folds log2 e into
+// the head weights), so e_k = 2^(l_k - max l) is one FADD + one MUFU.EX2; bin = #{k : cumsum(e)_k <= u * sum(e)}
+// (same draw as the sequential scan of fused.cu / the oracle, with the partial sums associated as a binary tree:
+// 31 adds build the tree, 5 compare-and-descend levels walk it).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sel4(float a, float b, float c, float d, bool lo, bool hi) {   // index = hi*2 + lo
+    const float x = lo ? b : a, y = lo ? d : c;
+    return hi ? y : x;
+}
+
+// e[0:32] -> (bin, total); t_in = u * total is applied by the caller through `t`
+__device__ __forceinline__ int tree32(const float (&e)[32], const float (&s2)[16], const float (&s4)[8], const float (&s8)[4],
+                                      float s16_0, float t) {
+    const bool b4 = t >= s16_0;                                   // bin bit 4
+    t -= b4 ? s16_0 : 0.f;
+    const float l8 = b4 ? s8[2] : s8[0];
+    const bool b3 = t >= l8;
+    t -= b3 ? l8 : 0.f;
+    const float l4 = sel4(s4[0], s4[2], s4[4], s4[6], b3, b4);
+    const bool b2 = t >= l4;
+    t -= b2 ? l4 : 0.f;
+    const float l2 = b4 ? sel4(s2[8], s2[10], s2[12], s2[14], b2, b3) : sel4(s2[0], s2[2], s2[4], s2[6], b2, b3);
+    const bool b1 = t >= l2;
+    t -= b1 ? l2 : 0.f;
+    const float q0 = sel4(e[0], e[2], e[4], e[6], b1, b2), q1 = sel4(e[8], e[10], e[12], e[14], b1, b2);
+    const float q2 = sel4(e[16], e[18], e[20], e[22], b1, b2), q3 = sel4(e[24], e[26], e[28], e[30], b1, b2);
+    const float l1 = sel4(q0, q1, q2, q3, b3, b4);
+    const bool b0 = t >= l1;
+    return (b4 ? 16 : 0) + (b3 ? 8 : 0) + (b2 ? 4 : 0) + (b1 ? 2 : 0) + (b0 ? 1 : 0);
+}
+
 template <int NB>
 __device__ __forceinline__ int sample_regs(float (&l)[NB], float u) {
+    static_assert(NB == 32 || NB == 36, "heads have 32 (translation) or 36 (rotation) bins");
     float m = l[0];
 #pragma unroll
     for (int k = 1; k < NB; ++k) m = fmaxf(m, l[k]);
-    float tot = 0.f;
+    float e[32], s2[16], s4[8], s8[4];
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-        l[k] = exp2f((l[k] - m) * 1.4426950408889634f);
-        tot += l[k];
-    }
+    for (int k = 0; k < 32; ++k) e[k] = ex2_approx(l[k] - m);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s2[k] = e[2 * k] + e[2 * k + 1];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s4[k] = s2[2 * k] + s2[2 * k + 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s8[k] = s4[2 * k] + s4[2 * k + 1];
+    const float s16_0 = s8[0] + s8[1], s16_1 = s8[2] + s8[3];
+    const float tot32 = s16_0 + s16_1;
+    if (NB == 32) return tree32(e, s2, s4, s8, s16_0, u * tot32);
+    // 36 bins: the four extra bins sit behind the tree
+    const float x0 = ex2_approx(l[NB - 4] - m), x1 = ex2_approx(l[NB - 3] - m), x2 = ex2_approx(l[NB - 2] - m),
+                x3 = ex2_approx(l[NB - 1] - m);
+    const float x01 = x0 + x1, tot = tot32 + (x01 + (x2 + x3));
     const float t = u * tot;
-    float acc = 0.f;
-    int bin = 0;
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-        acc += l[k];
-        bin += acc <= t ? 1 : 0;
-    }
-    return bin < NB - 1 ? bin : NB - 1;
+    const int in_tree = tree32(e, s2, s4, s8, s16_0, t);
+    const float r = t - tot32;
+    const int extra = 32 + (r >= x0 ? 1 : 0) + (r >= x01 ? 1 : 0) + (r >= x01 + x2 ? 1 : 0);
+    return t >= tot32 ? extra : in_tree;
 }
 
 __device__ __forceinline__ void ppf_of(f3 pa, f3 pb, f3 na, f3 nb, float (&ppf)[4]) {   // models/model.py:120-129

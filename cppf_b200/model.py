@@ -114,6 +114,9 @@ def _canon_hi_lo(w: np.ndarray, n_pad: int, k_pad: int) -> list:
     return [canon(hi), canon(lo)]
 
 
+LOG2E = 1.4426950408889634
+
+
 def pack_tc_weights(sd) -> np.ndarray:
     """Pack a PPFEncoder ``state_dict`` for the tcgen05 encoder (csrc/encode_tc.cu, "chain algebra"):
     adjacent linear maps of models/model.py:26-31,134-137 are composed here in float64 and rounded once
@@ -141,9 +144,12 @@ def pack_tc_weights(sd) -> np.ndarray:
     pre_w = np.concatenate([front[:, :_F].T, front[:, _F:2 * _F].T], 1)          # [40,192]: A side | B side
     pre_b = np.concatenate([bV1, bQ1, bQ2, np.zeros(96)])
     r_up, r_rt, r_tail = 2 * TR_BINS, 2 * TR_BINS + ROT_BINS, 2 * TR_BINS + 2 * ROT_BINS
-    head_rows = np.concatenate([Wf[:r_rt], Wf[r_tail:]], 0)           # mu | nu | up | tail  (105 rows)
+    # the categorical heads are only ever consumed as softmax probabilities (nocs/inference.py:185-186,245-256), which the
+    # kernel evaluates as 2^(l' - max l') with l' = l * log2(e): the factor is folded into their rows here (the tail rows --
+    # aux logits and log-scales -- are outputs and stay unscaled)
+    head_rows = np.concatenate([Wf[:r_rt] * LOG2E, Wf[r_tail:]], 0)   # mu | nu | up | tail  (105 rows)
     WH = np.concatenate([head_rows @ W2_2, head_rows], 1)             # acts on [u2 ; r2]  [105,32]
-    WR = np.concatenate([Wf[r_rt:r_tail] @ W2_2, Wf[r_rt:r_tail]], 1)            # right head [36,32]
+    WR = np.concatenate([Wf[r_rt:r_tail] @ W2_2, Wf[r_rt:r_tail]], 1) * LOG2E    # right head [36,32]
     f32 = lambda a: np.asarray(a, np.float64).astype(np.float32)
     parts = [f32(pre_w).reshape(-1), f32(pre_b)]
     parts += _canon_hi_lo(f32(front[:, 2 * _F:]), 96, 8)              # Wp : ppf columns
@@ -152,9 +158,9 @@ def pack_tc_weights(sd) -> np.ndarray:
     parts += _canon_hi_lo(f32(WH), 112, 32)
     parts += _canon_hi_lo(f32(WR), 48, 32)
     bias = np.zeros(256, np.float32)
-    bias[0:r_rt] = f32(bf[:r_rt])
+    bias[0:r_rt] = f32(bf[:r_rt] * LOG2E)
     bias[r_rt:r_rt + 5] = f32(bf[r_tail:])
-    bias[112:112 + ROT_BINS] = f32(bf[r_rt:r_tail])
+    bias[112:112 + ROT_BINS] = f32(bf[r_rt:r_tail] * LOG2E)
     parts.append(bias)
     blob = np.concatenate([np.ascontiguousarray(q, dtype=np.float32).reshape(-1) for q in parts])
     assert blob.size == _lib.lib().cppf_tc_blob_floats(), blob.size

@@ -141,7 +141,8 @@ def test_tc_blob_chain_algebra_matches_oracle():
     a3 = np.concatenate([np.maximum(t[:, :16], 0), t[:, 16:]], 1)
     heads = a3 @ wh.T + bias[:112]                                                                # step 3
     right = a3 @ wr.T + bias[112:160]
-    got = np.concatenate([heads[:, :100], right[:, :36], heads[:, 100:105]], 1)                   # reference column order
+    # the categorical heads are packed in log2 units (x log2 e); the tail columns are not
+    got = np.concatenate([heads[:, :100] / model.LOG2E, right[:, :36] / model.LOG2E, heads[:, 100:105]], 1)   # reference column order
     x = torch.from_numpy(np.concatenate([feat[ia], feat[ib], ppf], 1))
     want = ref_model.pair_mlp(x, {k: v for k, v in sd.items()}).numpy()
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
