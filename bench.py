@@ -36,10 +36,14 @@ if ROOT not in sys.path:
 
 METRIC = "point_pairs_per_sec"
 UNIT = "pairs/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1b_fused_kernels_ncu.md, profiles/r1c_vote_sorted_ncu.md), N=4096 dense
-TRAFFIC_NCU = {"encode_sample": 3.485184e6 + 346.669056e6, "vote": 67.346432e6 + 0.404992e6,
-               "backvote": 67.203328e6 + 3.382784e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch and the utilisation of the resource that binds each kernel,
+# from the committed `ncu --set full` capture of this pipeline (profiles/r1d_kernels_ncu.md), N=4096 dense
+TRAFFIC_NCU = {"encode_sample": 3.378432e6 + 348.861184e6, "vote": 67.368704e6 + 0.92416e6,
+               "backvote": 67.202816e6 + 3.360256e6, "stats": 402.321152e6 + 3.837952e6}
+BINDING_NCU = {"encode_sample": {"issue_slots_busy": 0.473, "tensor_pipe_active": 0.326, "warps_per_sm": 16},
+               "vote": {"shared_memory_wavefronts_of_peak": 0.729, "issue_slots_busy": 0.749,
+                        "wavefronts_per_ATOMS": 4.02},
+               "backvote": {"issue_slots_busy": 0.799}, "stats": {"dram_read_tbs": 2.89}}
 
 
 def parse():
@@ -335,16 +339,22 @@ def main():
         #   vote          : 4 B/pair read (bins); ~180 shared-memory atomics/pair under the trained-like load
         #   twopass       : first-pass encode writes 64 fp32 logits/pair, vote reads 8 B (mu,nu)/pair
         algo_bytes = {"encode_sample": pairs_per_obj * 24, "vote": pairs_per_obj * 4, "backvote": pairs_per_obj * 5,
+                      "stats": pairs_per_obj * 24,
                       "ppf_encode_pass1": pairs_per_obj * 64 * 4, "ppf_vote": pairs_per_obj * 8}
         algo_flops = {"encode_sample": pairs_per_obj * 23968.0, "ppf_encode_pass1": pairs_per_obj * (23968.0 - 2 * 16 * 77)}
         binding = {"encode_sample": "tensor pipe issue + MMA round-trip latency (tcgen05 3xTF32 chain)" if args.encoder == "tc"
                                     else "fp32 FMA pipe",
-                   "vote": "shared-memory atomic throughput", "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput",
+                   "vote": "shared-memory pipe (73 % of peak wavefronts; 4.0 bank/same-cell replays per ATOMS)",
+                   "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput", "stats": "HBM gather (2.9 TB/s)",
                    "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "torch ops (cdist/topk/LayerNorm), launch-bound"}
         detail = {}
         for k, v in kern.items():
             t = v["avg_ms"] * 1e-3
             d = {"avg_ms": v["avg_ms"], "binding_resource": binding.get(k)}
+            if k in BINDING_NCU:
+                d["binding_utilisation_ncu"] = BINDING_NCU[k]
+            if k in TRAFFIC_NCU:
+                d["dram_bytes_per_launch_ncu"] = TRAFFIC_NCU[k]
             if k in algo_bytes:
                 d["hbm"] = {"achieved": algo_bytes[k] / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": algo_bytes[k] / t / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": algo_bytes[k]}

@@ -30,7 +30,10 @@ def main():
         rows.append((r[ki], ms))
     if marker:
         cuts = [i for i, (k, _) in enumerate(rows) if marker in k]
-        if len(cuts) >= 2:
+        if "--step-index" in sys.argv:                      # the step that starts at the given occurrence of the marker
+            j = int(sys.argv[sys.argv.index("--step-index") + 1])
+            rows = rows[cuts[j]:cuts[j + 1]]
+        elif len(cuts) >= 2:
             rows = rows[cuts[-2]:cuts[-1]]
     agg = OrderedDict()
     for k, ms in rows:
