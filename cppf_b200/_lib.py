@@ -50,6 +50,8 @@ SIGNATURES = {
     "cppf_vote_routed_supported": (_i, [_i, _i, _i]),
     "cppf_vote_routed_scratch_bytes": (_i64, [_i64, _i, _i, _i, _i]),
     "cppf_vote_routed": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _i64, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),
+    "cppf_vote_slabs_supported": (_i, [_i, _i, _i]),
+    "cppf_vote_slabs": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),
     "cppf_backvote_bins": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _f, _f, _i, _i64, _i, _i, _i, _i, _p]),
     "cppf_rot_hist": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i64, C.c_uint64, _f, _p]),
     "cppf_survivor_stats": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i64, _p]),

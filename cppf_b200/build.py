@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-Xlinker", "--no-undefined"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     with open(os.path.join(OBJ, "ptxas.log"), "w") as f:

@@ -34,6 +34,11 @@ struct VotePParams {
     const Geom* geom;          // optional: device-side geometry overrides corner / dims / upper bounds
     int max_cells;             // capacity of the shared-memory grid of this launch
     int rep_stride;            // 0, or the offset (in cells) of a second replica of the grid used by the odd lanes
+    int slab_planes;           // 0: every CTA holds the whole grid.  > 0 ("slab passes", grids of up to gridDim slabs): CTA b
+                               // holds the x-slab (b % n_slabs) of slab_planes base planes (+ 1 overlap plane), walks the
+                               // pairs of part (b / n_slabs) and keeps only the candidates whose floor(g.x) it owns --
+                               // phase 1 is repeated per slab, but nothing is routed through memory
+    int n_slabs;
 };
 
 constexpr int kVoteThreads = 1024;
@@ -72,14 +77,36 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     int gx = prm.gx, gy = prm.gy, gzd = prm.gz;
     float hx = prm.hx, hy = prm.hy, hz = prm.hz, dhx = prm.dhx, dhy = prm.dhy, dhz = prm.dhz;
     const float* corner = prm.corner;
+    int pps = prm.slab_planes, n_slabs = prm.n_slabs;
     if (prm.geom != nullptr) {
         const Geom g = *prm.geom;
-        if (g.status != 0 || g.mode != 0 || g.cells > prm.max_cells) return;
+        if (g.status != 0) return;
+        if (pps == 0 ? (g.mode != 0 || g.cells > prm.max_cells) : g.mode != 1) return;
         gx = g.gx; gy = g.gy; gzd = g.gz;
         hx = g.hx; hy = g.hy; hz = g.hz; dhx = g.dhx; dhy = g.dhy; dhz = g.dhz;
         corner = prm.geom->corner;
+        if (pps != 0) {                              // slab plan from the capacity of this launch
+            pps = prm.max_cells / (gy * gzd) - 1;
+            if (pps < 1) return;
+            if (pps > gx) pps = gx;
+            n_slabs = (gx + pps - 1) / pps;
+        }
     }
-    const int cells = gx * gy * gzd;
+    int x0 = 0, part = blockIdx.x, parts = gridDim.x;
+    float dlx = prm.dlo;
+    if (pps != 0) {
+        parts = gridDim.x / n_slabs;
+        if (parts < 1 || (int)blockIdx.x >= parts * n_slabs) return;
+        x0 = (blockIdx.x % n_slabs) * pps;
+        part = blockIdx.x / n_slabs;
+        // conservative bounds on d.x for floor(g.x) in [x0, x0 + pps): the division rounds within 2^-24
+        if (x0 > 0) dlx = fmaxf(dlx, (float)x0 * prm.res * 0.999998f);
+        dhx = fminf(dhx, (float)(x0 + pps) * prm.res * 1.000002f);
+    }
+    const int x_hi = pps != 0 ? x0 + pps : 0x7fffffff;           // owned base planes: [x0, x_hi)
+    const int cells = (pps != 0 ? min(gx, x0 + pps + 1) - x0 : gx) * gy * gzd;
+    const long long acc_off = (long long)x0 * gy * gzd;
+    const float fx0 = (float)x0;
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
     if (BINS && threadIdx.x < 64) s_lut[threadIdx.x] = __ldg(prm.lut + threadIdx.x);
     if (BINS && threadIdx.x < 32) {
@@ -105,7 +132,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     const float cx = __ldg(corner), cy = __ldg(corner + 1), cz = __ldg(corner + 2);
     const long long n_batches = (prm.n_pairs + kVoteBatch - 1) / kVoteBatch;
 
-    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    for (long long batch = part; batch < n_batches; batch += parts) {
         const long long base = batch * kVoteBatch;
         // ---- (1a) keys + ranks: n of each of this thread's two pairs
         int key[2], rank[2];
@@ -130,13 +157,13 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
         for (int i = threadIdx.x; i < cells; i += blockDim.x) {
             const unsigned v = s_grid[i];
             if (v >= kFlushAt) {
-                atomicAdd(prm.acc + i, (unsigned long long)v);
+                atomicAdd(prm.acc + acc_off + i, (unsigned long long)v);
                 s_grid[i] = 0u;
             }
             if (rep) {
                 const unsigned w = s_grid[rep + i];
                 if (w >= kFlushAt) {
-                    atomicAdd(prm.acc + i, (unsigned long long)w);
+                    atomicAdd(prm.acc + acc_off + i, (unsigned long long)w);
                     s_grid[rep + i] = 0u;
                 }
             }
@@ -228,7 +255,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
                 const f3 off = x * cs.x + y * cs.y;                            // :34
                 const float dx = c.x + off.x - cx, dy = c.y + off.y - cy, dz = c.z + off.z - cz;   // :35 before `/ res`
                 // conservative: every candidate the exact test of phase 2 accepts passes here
-                const bool inb = i < n && dx >= prm.dlo && dy >= prm.dlo && dz >= prm.dlo && dx < dhx && dy < dhy && dz < dhz;
+                const bool inb = i < n && dx >= dlx && dy >= prm.dlo && dz >= prm.dlo && dx < dhx && dy < dhy && dz < dhz;
                 const unsigned m = __ballot_sync(0xffffffffu, inb);
                 if (inb) st_shared_f4(q_addr + (((q_tail + __popc(m & lt_mask)) & (kVoteQueue - 1)) << 4), dx, dy, dz);
                 q_tail += __popc(m);
@@ -238,8 +265,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
                     const float gxf = div_by(d.x, prm.res, prm.inv_res);       // :35
                     const float gyf = div_by(d.y, prm.res, prm.inv_res);
                     const float gzf = div_by(d.z, prm.res, prm.inv_res);
-                    if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz))
-                        splat_fixed(s_lane, gxf, gyf, gzf, gyz, gz);           // :36-63
+                    if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz) &&
+                        (int)gxf >= x0 && (int)gxf < x_hi)
+                        splat_fixed(s_lane, gxf - fx0, gyf, gzf, gyz, gz);     // :36-63
                     q_head += 32u;
                     __syncwarp();
                 }
@@ -251,14 +279,15 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
             const float gxf = div_by(d.x, prm.res, prm.inv_res);
             const float gyf = div_by(d.y, prm.res, prm.inv_res);
             const float gzf = div_by(d.z, prm.res, prm.inv_res);
-            if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz))
-                splat_fixed(s_lane, gxf, gyf, gzf, gyz, gz);
+            if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz) && (int)gxf >= x0 &&
+                (int)gxf < x_hi)
+                splat_fixed(s_lane, gxf - fx0, gyf, gzf, gyz, gz);
         }
         __syncthreads();
     }
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
         const unsigned long long v = (unsigned long long)s_grid[i] + (rep ? (unsigned long long)s_grid[rep + i] : 0ull);
-        if (v) atomicAdd(prm.acc + i, v);
+        if (v) atomicAdd(prm.acc + acc_off + i, v);
     }
 }
 
@@ -598,12 +627,31 @@ static float vote_bound_below(float g, float res) { return nextafterf((float)((d
 namespace cppf {
 // Launch of the privatised vote with the geometry either in the arguments (geom == nullptr) or in device
 // memory (geom != nullptr: gx/gy/gz are ignored and max_cells sizes the shared-memory grid).
+// slab_cells == 0: every CTA holds the whole grid (<= max_cells).  slab_cells > 0: "slab passes" for grids of up to
+// sm_count() x-slabs -- every CTA holds one slab of <= slab_cells cells; scratch / grid then hold total_cells cells
+// (host geometry: gx*gy*gz; device geometry: the caller's capacity) and the final conversion covers all of them.
 int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, const void* idx,
                      int idx_is_64, float* grid, void* scratch, const float* corner, float res, int n_points,
                      int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, const Geom* geom, int max_cells,
-                     cudaStream_t stream) {
-    const long long cells = geom ? (long long)max_cells : (long long)gx * gy * gz;
-    if (cells <= 0 || cells > cppf_vote_private_max_cells() || n_rots > kMaxRotsP || n_rots <= 0)
+                     cudaStream_t stream, int slab_cells, long long total_cells) {
+    const bool slabs = slab_cells > 0;
+    long long cells = geom ? (long long)(slabs ? slab_cells : max_cells) : (long long)gx * gy * gz;
+    int pps = 0, n_slabs = 1;
+    if (slabs && !geom) {
+        const long long gyz = (long long)gy * gz;
+        pps = (int)(slab_cells / gyz) - 1;
+        if (pps < 1) return (int)cudaErrorInvalidValue;
+        if (pps > gx) pps = gx;
+        n_slabs = (gx + pps - 1) / pps;
+        if (n_slabs > sm_count()) return (int)cudaErrorInvalidValue;
+        total_cells = cells;
+        cells = (long long)(pps + 1 < gx ? pps + 1 : gx) * gyz;
+    } else if (slabs) {
+        pps = 1;                                     // recomputed in the kernel from the device geometry
+    } else {
+        total_cells = cells;
+    }
+    if (cells <= 0 || cells > cppf_vote_private_max_cells() || n_rots > kMaxRotsP || n_rots <= 0 || total_cells <= 0)
         return (int)cudaErrorInvalidValue;
     if ((mu_nu == nullptr) == (bins == nullptr)) return (int)cudaErrorInvalidValue;
     if (bins != nullptr && lut == nullptr) return (int)cudaErrorInvalidValue;
@@ -612,7 +660,7 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
     int terr = 0;
     const float2* rot_tab = rot_table_device(stream, &terr);
     if (terr) return terr;
-    CPPF_RETURN_IF(cudaMemsetAsync(scratch, 0, (size_t)cells * 8, stream));
+    CPPF_RETURN_IF(cudaMemsetAsync(scratch, 0, (size_t)total_cells * 8, stream));
     const float lo = float_ceil_p(0.01);
     float hx = 0.f, hy = 0.f, hz = 0.f, dhx = 0.f, dhy = 0.f, dhz = 0.f;
     if (!geom) {
@@ -622,7 +670,7 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
     }
     VotePParams prm{rot_tab, points, mu_nu, bins, lut, idx, reinterpret_cast<unsigned long long*>(scratch), corner, res,
                     (float)(1.0 / (double)res), lo, hx, hy, hz, vote_bound_below(lo, res), dhx, dhy, dhz, n_points,
-                    (long long)n_pairs, n_rots, gx, gy, gz, adaptive, geom, (int)cells, 0};
+                    (long long)n_pairs, n_rots, gx, gy, gz, adaptive, geom, (int)cells, 0, pps, n_slabs};
     // second replica 8 banks away from the first, when both fit
     long long rep_stride = ((cells + 31) & ~31ll) + 8;
     if ((size_t)(rep_stride + cells) * 4 + vote_private_fixed_smem() + 1024 > (size_t)225 * 1024) rep_stride = 0;
@@ -631,14 +679,15 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
     const int threads = kVoteThreads;
     long long blocks = (n_pairs + kVoteBatch - 1) / kVoteBatch;
     if (blocks > sm_count()) blocks = sm_count();
+    if (slabs) blocks = geom ? sm_count() : (long long)n_slabs * (sm_count() / n_slabs);
     void (*kern)(const VotePParams);
     if (bins) kern = idx_is_64 ? vote_private_kernel<true, true> : vote_private_kernel<false, true>;
     else kern = idx_is_64 ? vote_private_kernel<true, false> : vote_private_kernel<false, false>;
     CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(int)blocks, threads, smem, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
-    vote_finalize_kernel<<<(int)((cells + 255) / 256), 256, 0, stream>>>(reinterpret_cast<unsigned long long*>(scratch),
-                                                                        grid, (int)cells, geom, geom ? 0 : -1);
+    vote_finalize_kernel<<<(int)((total_cells + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<unsigned long long*>(scratch), grid, (int)total_cells, geom, geom ? (slabs ? 1 : 0) : -1);
     CPPF_LAUNCH_CHECK();
     return 0;
 }
@@ -678,7 +727,22 @@ extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uin
                               int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
                               void* stream_) {
     return vote_fast_launch(points, mu_nu, bins, lut, idx, idx_is_64, grid, scratch, corner, res, n_points, n_pairs, n_rots,
-                            gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_);
+                            gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, 0, 0);
+}
+
+extern "C" int cppf_vote_slabs_supported(int gx, int gy, int gz) {
+    const long long gyz = (long long)gy * gz;
+    const long long pps = cppf_vote_private_max_cells() / gyz - 1;
+    if (pps < 1) return 0;
+    return (gx + pps - 1) / pps <= sm_count() ? 1 : 0;
+}
+
+extern "C" int cppf_vote_slabs(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut,
+                               const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
+                               int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
+                               void* stream_) {
+    return vote_fast_launch(points, mu_nu, bins, lut, idx, idx_is_64, grid, scratch, corner, res, n_points, n_pairs, n_rots,
+                            gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, cppf_vote_private_max_cells(), 0);
 }
 
 extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, const float* lut, const void* idx,

@@ -90,6 +90,24 @@ def vote_fast(points, idxs, grid, corner, res, *, mu_nu=None, bins=None, lut=Non
     return grid
 
 
+def vote_slabs(points, idxs, grid, corner, res, *, mu_nu=None, bins=None, lut=None, n_rots=72, adaptive=True, scratch=None):
+    """Centre vote for large grids by slab passes (cppf_vote_slabs): same kernel as vote_fast, one x-slab per CTA."""
+    dev = points.device
+    n = points.shape[0]
+    ip, is64 = _idx_args(idxs)
+    n_pairs = n * n if idxs is None else idxs.shape[0]
+    gx, gy, gz = grid.shape
+    if scratch is None:
+        scratch = torch.empty(gx * gy * gz, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cppf_vote_slabs(
+            points.data_ptr(), mu_nu.data_ptr() if mu_nu is not None else None,
+            bins.data_ptr() if bins is not None else None, lut.data_ptr() if lut is not None else None, ip, is64,
+            grid.data_ptr(), scratch.data_ptr(), corner.data_ptr(), float(res), n, n_pairs, int(n_rots), gx, gy, gz,
+            int(bool(adaptive)), _sp(dev)), "cppf_vote_slabs")
+    return grid
+
+
 def vote_routed_supported(dims) -> bool:
     return bool(_lib.lib().cppf_vote_routed_supported(int(dims[0]), int(dims[1]), int(dims[2])))
 

@@ -194,6 +194,14 @@ int cppf_vote_routed(const float* points, const float* mu_nu, const uint8_t* bin
                      const float* corner, float res, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz,
                      int adaptive, void* stream);
 
+/* A third way for large grids, "slab passes": the same shared-memory kernel as cppf_vote_fast, every CTA holding one
+ * x-slab of the grid and keeping only the candidates whose floor(g.x) it owns.  Phase 1 (candidate generation) is
+ * repeated once per slab but nothing is routed through memory; same exact sums.  scratch: gx*gy*gz*8 bytes. */
+int cppf_vote_slabs_supported(int gx, int gy, int gz);
+int cppf_vote_slabs(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut,
+                    const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
+                    int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, void* stream);
+
 /* models/voting.py:74-112 + nocs/inference.py:207-211,229-230 from bins: the winning cell is
  * read from device memory (*argmax_flat), centre = corner + cell*res as at :209; out_mask[p] =
  * any(out_offsets[p] != 0). */

@@ -328,6 +328,10 @@ def test_vote_routed_64_cube_matches_oracle_and_global_kernel():
     fast.vote_routed(_t(pc2), None, small, _t(corner2), res, bins=bins, lut=lut,
                      scratch=torch.empty(nb, dtype=torch.uint8, device=DEV))
     assert torch.equal(full, small)
+    # slab passes (the privatised kernel with one x-slab per CTA): bit-identical to the routed variant
+    slabs = torch.zeros(dims2, device=DEV)
+    fast.vote_slabs(_t(pc2), None, slabs, _t(corner2), res, bins=bins, lut=lut)
+    assert torch.equal(full, slabs)
     b = bins.long()
     mu_nu = torch.stack([lut[b[:, 0]], lut[32 + b[:, 1]]], -1).contiguous()
     slow = torch.zeros(dims2, device=DEV)
