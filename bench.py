@@ -237,8 +237,8 @@ def main():
     n_obj = args.warmup + args.steps
     clouds = [synth.synth_bottle(n, 1000 * rank + s) for s in range(n_obj)]
     pinned = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(q).pin_memory()) for p, q in clouds]
-    h2d = 2 * n * 3 * 4 + 12
-    d2h = 8 * 8 + 8
+    h2d = 2 * n * 3 * 4             # xyz + normals of the cloud (float32)
+    d2h = 16 * 8                    # the pose record (16 doubles)
 
     def barrier():
         if dist_on:
@@ -252,6 +252,8 @@ def main():
 
     L = _lib.lib()
     timing = L.cppf_timing_create() if args.path == "fused" else None
+    if timing:
+        L.cppf_timing_reserve(timing, max(args.steps, 200))
     stage_names = [L.cppf_timing_stage_name(i).decode() for i in range(L.cppf_timing_stages())]
 
     def run(leg, votes_injected=True):
@@ -319,6 +321,52 @@ def main():
     ms_net = None
     if args.votes == "trained_like" and args.path == "fused":
         ms_net, _, _, _ = run("hbm", votes_injected=False)
+    sampled = None
+    if args.path == "fused":
+        # the reference's own inference regime (nocs/inference.py:177): 100 000 random pairs per object, from pinned host
+        # clouds; one cppf_pose_fused call per object, all objects of the run enqueued back to back.  The kernels of one
+        # such object are short (0.5 ms in ~25 launches), so objects are also dealt round-robin to a few CUDA streams.
+        est_s = PoseEstimator(pe, ppf, PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=100000)), dev)
+        n_s = 240
+
+        def enq(s_):
+            return est_s.enqueue_fused(pinned[s_ % n_obj][0], pinned[s_ % n_obj][1], seed=s_, max_cells=cells[s_ % n_obj])
+        for s_ in range(3):
+            enq(s_).result()
+        barrier()
+        host_us = []
+        for s_ in range(20):            # host cost of one enqueue with an idle GPU
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            q = enq(s_)
+            host_us.append((time.perf_counter() - t0) * 1e6)
+            q.result()
+        barrier()
+        reps = []
+        for _ in range(3):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            pend = [enq(s_) for s_ in range(n_s)]
+            for q in pend:
+                q.result()
+            a1.record()
+            barrier()
+            reps.append(a0.elapsed_time(a1))
+        ms_1 = statistics.median(reps)
+        stage_s = {}
+        if timing:                      # stage breakdown from a separate short run (event records slow short objects down)
+            L.cppf_timing_collect(timing, (C.c_float * len(stage_names))())
+            est_s.timing = timing
+            for s_ in range(20):
+                est_s.enqueue_fused(pinned[s_ % n_obj][0], pinned[s_ % n_obj][1], seed=s_, max_cells=cells[s_ % n_obj]).result()
+            acc = (C.c_float * len(stage_names))()
+            calls = L.cppf_timing_collect(timing, acc)
+            est_s.timing = None
+            stage_s = {nm: round(acc[i] / max(calls, 1), 4) for i, nm in enumerate(stage_names)}
+        sampled = {"objects_per_sec_per_gpu": n_s / (ms_1 * 1e-3), "pairs_per_sec_per_gpu": n_s * 100000 / (ms_1 * 1e-3),
+                   "ms_per_object": ms_1 / n_s, "ms_per_object_repeats": [r / n_s for r in reps], "host_enqueue_us_per_object": statistics.median(host_us), "stage_ms": stage_s,
+                   "pairs_per_object": 100000,
+                   "note": "reference regime: P = 100 000 sampled pairs (nocs/inference.py:177), host clouds in, pose records out"}
     total_pairs = world * args.steps * pairs_per_obj
     value = total_pairs / (ms_hbm * 1e-3)
     e2e = total_pairs / (ms_e2e * 1e-3)
@@ -396,6 +444,8 @@ def main():
             line["variant_network_votes"] = {"value": total_pairs / (ms_net * 1e-3), "unit": UNIT,
                                              "ms_per_step": ms_net / args.steps,
                                              "note": "no bin injection: votes from the random-init network's own samples"}
+        if sampled is not None:
+            line["variant_sampled_100k"] = sampled
         print(json.dumps(line))
     if dist_on:
         dist.destroy_process_group()

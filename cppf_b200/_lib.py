@@ -64,10 +64,12 @@ SIGNATURES = {
     "cppf_gaussian3d": (_i, [_p, _p, _p, _i, _i, _i, C.c_double, C.c_double, _p]),
     "cppf_scene_proposals": (_i, [_p, _i, _i, _i, _f, _i, _f, _i, _p, _p, _p]),
     "cppf_pose_record_doubles": (_i, []),
+    "cppf_pose_args_bytes": (_i, []),
     "cppf_pose_workspace_bytes": (_i64, [_i, _i64, _i, _i, _i, _i, _i]),
     "cppf_pose_fused": (_i, [_p, _p]),
     "cppf_timing_create": (_p, []),
     "cppf_timing_destroy": (None, [_p]),
+    "cppf_timing_reserve": (_i, [_p, _i]),
     "cppf_timing_stages": (_i, []),
     "cppf_timing_stage_name": (C.c_char_p, [_i]),
     "cppf_timing_collect": (_i, [_p, _p]),

@@ -212,6 +212,7 @@ struct Timing {
 using namespace cppf;
 
 extern "C" int cppf_pose_record_doubles(void) { return 16; }
+extern "C" int cppf_pose_args_bytes(void) { return (int)sizeof(cppf_pose_args); }
 
 extern "C" int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells,
                                              int n_rots, int n_sphere) {
@@ -225,6 +226,18 @@ extern "C" void cppf_timing_destroy(void* t) {
     Timing* tm = reinterpret_cast<Timing*>(t);
     for (cudaEvent_t e : tm->pool) cudaEventDestroy(e);
     delete tm;
+}
+// pre-create the events of `n_calls` calls (cudaEventCreate is slow enough to show up when timing short objects)
+extern "C" int cppf_timing_reserve(void* t, int n_calls) {
+    Timing* tm = reinterpret_cast<Timing*>(t);
+    const size_t want = (size_t)n_calls * (kStages + 1);
+    while (tm->pool.size() < want) {
+        cudaEvent_t e;
+        const cudaError_t r = cudaEventCreate(&e);
+        if (r != cudaSuccess) return (int)r;
+        tm->pool.push_back(e);
+    }
+    return 0;
 }
 extern "C" int cppf_timing_stages(void) { return kStages; }
 extern "C" const char* cppf_timing_stage_name(int i) { return (i >= 0 && i < kStages) ? kStageNames[i] : ""; }

@@ -64,7 +64,7 @@ static_assert((unsigned long long)kVoteBatch * kMaxRotsP * (1ull << kFixShift) <
 // Without the ring the splat runs under the divergence of the in-bounds test (about a third of the lanes
 // active); with it the atomics always issue from full warps.  Integer sums are order-independent, so neither
 // the sort nor the dynamic chunk assignment changes the result.
-template <bool IDX64, bool BINS>
+template <bool IDX64, bool BINS, bool SLABS>
 __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const VotePParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tab = reinterpret_cast<float2*>(smem_raw);
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     int gx = prm.gx, gy = prm.gy, gzd = prm.gz;
     float hx = prm.hx, hy = prm.hy, hz = prm.hz, dhx = prm.dhx, dhy = prm.dhy, dhz = prm.dhz;
     const float* corner = prm.corner;
-    int pps = prm.slab_planes, n_slabs = prm.n_slabs;
+    int pps = SLABS ? prm.slab_planes : 0, n_slabs = prm.n_slabs;
     if (prm.geom != nullptr) {
         const Geom g = *prm.geom;
         if (g.status != 0) return;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     }
     int x0 = 0, part = blockIdx.x, parts = gridDim.x;
     float dlx = prm.dlo;
-    if (pps != 0) {
+    if (SLABS) {
         parts = gridDim.x / n_slabs;
         if (parts < 1 || (int)blockIdx.x >= parts * n_slabs) return;
         x0 = (blockIdx.x % n_slabs) * pps;
@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
         if (x0 > 0) dlx = fmaxf(dlx, (float)x0 * prm.res * 0.999998f);
         dhx = fminf(dhx, (float)(x0 + pps) * prm.res * 1.000002f);
     }
-    const int x_hi = pps != 0 ? x0 + pps : 0x7fffffff;           // owned base planes: [x0, x_hi)
-    const int cells = (pps != 0 ? min(gx, x0 + pps + 1) - x0 : gx) * gy * gzd;
-    const long long acc_off = (long long)x0 * gy * gzd;
+    const int x_hi = SLABS ? x0 + pps : 0x7fffffff;              // owned base planes: [x0, x_hi)
+    const int cells = (SLABS ? min(gx, x0 + pps + 1) - x0 : gx) * gy * gzd;
+    const long long acc_off = SLABS ? (long long)x0 * gy * gzd : 0ll;
     const float fx0 = (float)x0;
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
     if (BINS && threadIdx.x < 64) s_lut[threadIdx.x] = __ldg(prm.lut + threadIdx.x);
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
                     const float gyf = div_by(d.y, prm.res, prm.inv_res);
                     const float gzf = div_by(d.z, prm.res, prm.inv_res);
                     if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz) &&
-                        (int)gxf >= x0 && (int)gxf < x_hi)
-                        splat_fixed(s_lane, gxf - fx0, gyf, gzf, gyz, gz);     // :36-63
+                        (!SLABS || ((int)gxf >= x0 && (int)gxf < x_hi)))
+                        splat_fixed(s_lane, SLABS ? gxf - fx0 : gxf, gyf, gzf, gyz, gz);     // :36-63
                     q_head += 32u;
                     __syncwarp();
                 }
@@ -279,9 +279,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
             const float gxf = div_by(d.x, prm.res, prm.inv_res);
             const float gyf = div_by(d.y, prm.res, prm.inv_res);
             const float gzf = div_by(d.z, prm.res, prm.inv_res);
-            if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz) && (int)gxf >= x0 &&
-                (int)gxf < x_hi)
-                splat_fixed(s_lane, gxf - fx0, gyf, gzf, gyz, gz);
+            if (!(gxf < prm.lo || gyf < prm.lo || gzf < prm.lo || gxf >= hx || gyf >= hy || gzf >= hz) &&
+                (!SLABS || ((int)gxf >= x0 && (int)gxf < x_hi)))
+                splat_fixed(s_lane, SLABS ? gxf - fx0 : gxf, gyf, gzf, gyz, gz);
         }
         __syncthreads();
     }
@@ -328,6 +328,8 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
     __shared__ float s_lut[64];
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
     if (threadIdx.x < 64) s_lut[threadIdx.x] = __ldg(prm.lut + threadIdx.x);
+    __shared__ int s_nlut[32];                                             // rotation count of every nu bin (:97)
+    if (threadIdx.x < 32) s_nlut[threadIdx.x] = adaptive_rots(__ldg(prm.lut + 32 + threadIdx.x), prm.res, prm.n_rots);
     __syncthreads();
     int gy = prm.gy, gz = prm.gz;
     float hx = prm.hx, hy = prm.hy, hz = prm.hz;
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
             const f3 c = a - ab * mu;
             const f3 x = ex * nu;
             const f3 y = cross3(x, ab);
-            const int n = adaptive_rots(nu, prm.res, prm.n_rots);              // :97
+            const int n = s_nlut[bn.y & 31];                                   // :97
             const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
             // The reference walks i = 0..n-1 and stops at the first candidate within `tol` of the centre; only
             // whether such a candidate EXISTS is consumed (nocs/inference.py:229-230).  The candidates lie on a
@@ -367,23 +369,37 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
             // angle of T's in-plane projection: bound that arc analytically (with generous slack), then test only
             // its candidates -- each with the reference's own arithmetic, so the mask is unchanged.
             int i_lo = 0, i_cnt = n;
+            // in the pair's own frame (ab, ex, ey orthonormal) the squared distance of candidate i from the centre T is
+            //   nu^2 + |v|^2 - 2 nu (px cos_i + py sin_i),   v = T - c, px = v.ex, py = v.ey
+            // so a candidate can only be within tol if  nu (px cos_i + py sin_i) >= K = (nu^2 + |v|^2 - tol^2) / 2.
+            const f3 v = {tx - c.x, ty - c.y, tz - c.z};
+            const f3 ey = cross3(ex, ab);
+            const float dpl = dot3(v, ab), px = dot3(v, ex), py = dot3(v, ey);
+            const float vv = dpl * dpl + px * px + py * py;
+            const float tol2 = prm.tol * prm.tol;
+            const float kq = 0.5f * (nu * nu + vv - tol2) - (0.02f * tol2 + 1e-6f * (nu * nu + vv));   // K minus rounding slack
             if (n > 12) {
-                const f3 v = {tx - c.x, ty - c.y, tz - c.z};
-                const f3 ey = cross3(ex, ab);
-                const float dpl = dot3(v, ab), px = dot3(v, ex), py = dot3(v, ey);
                 const float rho = sqrtf(px * px + py * py);
-                const float tol2 = prm.tol * prm.tol * 1.01f + 1e-12f;
-                const float room = tol2 - dpl * dpl - (nu - rho) * (nu - rho);   // >= 2 nu rho (1 - cos d) for a hit
+                const float room = tol2 * 1.01f + 1e-12f - dpl * dpl - (nu - rho) * (nu - rho);   // >= 2 nu rho (1 - cos d) for a hit
                 const float two_nr = 2.f * fabsf(nu) * rho;
                 if (room < 0.f) {
                     i_cnt = 0;
                 } else if (room < 1.9f * two_nr) {
-                    const float dmax = acosf(1.f - room / two_nr);               // half-width of the arc (rad)
+                    // half-width of the arc: acos(1 - q) <= sqrt(2q) (1 + 0.22 q) on [0, 1.9] (no acosf, no atan2f: a
+                    // polynomial atan2 good to 2e-4 rad only has to place the centre of the window)
+                    const float q = room / two_nr;
+                    const float dmax = sqrtf(2.f * q) * fmaf(0.22f, q, 1.f) + 1e-5f;
                     const float step = 6.2831853f / (float)n;
-                    float th = atan2f(py, px);
+                    const float apx = fabsf(px), apy = fabsf(py);
+                    const float mx = fmaxf(apx, apy), mn = fminf(apx, apy);
+                    const float t = mn / fmaxf(mx, 1e-30f), t2 = t * t;
+                    float th = fmaf(fmaf(fmaf(-0.0464964749f, t2, 0.15931422f), t2, -0.327622764f) * t2, t, t);
+                    if (apy > apx) th = 1.57079633f - th;
+                    if (px < 0.f) th = 3.14159265f - th;
+                    if (py < 0.f) th = -th;
                     if (nu < 0.f) th += 3.14159265f;                             // x, y carry the sign of nu
                     if (th < 0.f) th += 6.2831853f;
-                    const int w = (int)(dmax / step) + 2;
+                    const int w = (int)(dmax / step + 0.52f) + 1;
                     if (2 * w + 1 < n) {
                         i_lo = (int)(th / step + 0.5f) - w;
                         i_cnt = 2 * w + 1;
@@ -395,6 +411,7 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
                 i = i < 0 ? i + n : (i >= n ? i - n : i);
                 i = i < 0 ? i + n : (i >= n ? i - n : i);
                 const float2 cs = tab[i];
+                if (nu * fmaf(px, cs.x, py * cs.y) < kq) continue;              // cannot be within tol (see above)
                 const f3 off = x * cs.x + y * cs.y;
                 const f3 pc = c + off;
                 const f3 dlt = {pc.x - tx, pc.y - ty, pc.z - tz};
@@ -681,8 +698,13 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
     if (blocks > sm_count()) blocks = sm_count();
     if (slabs) blocks = geom ? sm_count() : (long long)n_slabs * (sm_count() / n_slabs);
     void (*kern)(const VotePParams);
-    if (bins) kern = idx_is_64 ? vote_private_kernel<true, true> : vote_private_kernel<false, true>;
-    else kern = idx_is_64 ? vote_private_kernel<true, false> : vote_private_kernel<false, false>;
+    if (slabs) {
+        if (bins) kern = idx_is_64 ? vote_private_kernel<true, true, true> : vote_private_kernel<false, true, true>;
+        else kern = idx_is_64 ? vote_private_kernel<true, false, true> : vote_private_kernel<false, false, true>;
+    } else {
+        if (bins) kern = idx_is_64 ? vote_private_kernel<true, true, false> : vote_private_kernel<false, true, false>;
+        else kern = idx_is_64 ? vote_private_kernel<true, false, false> : vote_private_kernel<false, false, false>;
+    }
     CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(int)blocks, threads, smem, stream>>>(prm);
     CPPF_LAUNCH_CHECK();

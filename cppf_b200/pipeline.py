@@ -101,6 +101,9 @@ class PoseEstimator:
         self.encoder_impl = "tc"      # "tc": tcgen05 3xTF32 encoder (csrc/encode_tc.cu); "simt": fp32 FFMA (csrc/fused.cu)
         self.timing = None            # optional cppf_timing_create() handle passed to cppf_pose_fused
         self._routed_scratch, self._routed_key = None, None
+        self._pe_fused_ok = None
+        self._rec_ring, self._rec_next = None, 0      # pinned pose records handed out round-robin (<= 1024 objects in flight)
+        self._gen = None              # CUDA generator for the pair sampling of nocs/inference.py:177 (re-seeded per object)
 
     def _timed(self, name):
         est = self
@@ -286,7 +289,9 @@ class PoseEstimator:
 
     # ------------------------------------------------------------------ one call per object
     def _onecall_ok(self):
-        return (self.encoder_impl == "tc" and self.pe._fused_ok() and self.cfg.num_rots <= 72 and self.ppf.out_dim == 141)
+        if self._pe_fused_ok is None:
+            self._pe_fused_ok = bool(self.pe._fused_ok())
+        return (self.encoder_impl == "tc" and self._pe_fused_ok and self.cfg.num_rots <= 72 and self.ppf.out_dim == 141)
 
     def _workspace(self, n, n_pairs, max_cells, routed_max_cells):
         """One workspace per (device, stream), shared by every estimator (categories differ only in weights) and
@@ -337,8 +342,9 @@ class PoseEstimator:
         pc = torch.as_tensor(pc_in).to(dev, torch.float32, non_blocking=True).contiguous()
         nrm = torch.as_tensor(nrm_in).to(dev, torch.float32, non_blocking=True).contiguous()
         if idxs is None and cfg.n_pairs > 0:                                        # nocs/inference.py:177
-            g = torch.Generator(device=dev).manual_seed(seed)
-            idxs = torch.randint(0, n, (cfg.n_pairs, 2), generator=g, device=dev, dtype=torch.int32)
+            if self._gen is None:
+                self._gen = torch.Generator(device=dev)
+            idxs = torch.randint(0, n, (cfg.n_pairs, 2), generator=self._gen.manual_seed(seed), device=dev, dtype=torch.int32)
         elif idxs is not None:
             idxs = torch.as_tensor(idxs).to(dev).contiguous()
             assert idxs.dtype in (torch.int32, torch.int64)
@@ -367,8 +373,11 @@ class PoseEstimator:
         a.res, a.tol, a.cos_thr = float(cfg.res), float(3 * cfg.res), self.cos_thr
         with torch.cuda.device(dev):
             _lib.check(L.cppf_pose_fused(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "cppf_pose_fused")
-        if record_host is None:
-            record_host = torch.empty(16, dtype=torch.float64, pin_memory=True)
+        if record_host is None:         # a slot of a pinned ring (a fresh pinned allocation per object costs a cudaHostAlloc)
+            if self._rec_ring is None:
+                self._rec_ring = torch.empty((1024, 16), dtype=torch.float64, pin_memory=True)
+            record_host = self._rec_ring[self._rec_next % 1024]
+            self._rec_next += 1
         record_host.copy_(rec, non_blocking=True)
         done = torch.cuda.Event()
         done.record()

@@ -270,6 +270,7 @@ typedef struct cppf_pose_args {
     float cos_thr;               /* float32(cos(angle_prec)) at :283 */
 } cppf_pose_args;
 int cppf_pose_record_doubles(void);
+int cppf_pose_args_bytes(void);            /* sizeof(cppf_pose_args) as compiled: lets a binding check its mirror of the struct */
 int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells, int n_rots,
                                   int n_sphere);
 int cppf_pose_fused(const cppf_pose_args* args, void* stream);
@@ -279,6 +280,7 @@ int cppf_pose_fused(const cppf_pose_args* args, void* stream);
  * to h_ms_sum[cppf_timing_stages()] (HOST array), returns the number of calls and resets the handle. */
 void* cppf_timing_create(void);
 void cppf_timing_destroy(void* timing);
+int cppf_timing_reserve(void* timing, int n_calls);    /* pre-create the events of n_calls calls */
 int cppf_timing_stages(void);
 const char* cppf_timing_stage_name(int stage);
 int cppf_timing_collect(void* timing, float* h_ms_sum);
