@@ -285,76 +285,162 @@ __device__ __forceinline__ unsigned d2_bits(f3 q, const float* __restrict__ pc, 
 }
 
 constexpr int kKnnWarps = 8;
+constexpr int kKnnBins = 1024;           // coarse histogram: sign (0) + exponent + 2 mantissa bits of d^2 = bits >> 21
+constexpr int kKnnCand = 256;            // candidates of the boundary bin kept in shared memory
 
+// One query, generic path: radix select on all 32 bits (4 sweeps of 8 bits + the collection sweep).
+__device__ __noinline__ void knn_query_radix(const float* __restrict__ pc, int n_points, int k, int qi, unsigned* hist,
+                                                int lane, long long* __restrict__ out) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const f3 q = ld3(pc, qi);
+    unsigned prefix = 0;                  // the bits of the k-th smallest distance found so far
+    int need = k;                         // rank of the wanted element among those matching the prefix
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0u;
+        __syncwarp();
+        for (int j = lane; j < n_points; j += 32) {
+            const unsigned b = d2_bits(q, pc, j);
+            if (pass == 0 || (b >> (shift + 8)) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        unsigned cnt[8], mine = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            cnt[i] = hist[lane * 8 + i];
+            mine += cnt[i];
+        }
+        unsigned incl = mine;             // inclusive scan of the per-lane totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned excl = incl - mine;
+        const bool here = (unsigned)need > excl && (unsigned)need <= incl;   // exactly one lane
+        int digit = 0, below = 0;
+        if (here) {
+            unsigned run = excl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if ((unsigned)need > run && (unsigned)need <= run + cnt[i]) {
+                    digit = lane * 8 + i;
+                    below = (int)run;
+                }
+                run += cnt[i];
+            }
+        }
+        const unsigned src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+        digit = __shfl_sync(0xffffffffu, digit, src);
+        below = __shfl_sync(0xffffffffu, below, src);
+        prefix = (prefix << 8) | (unsigned)digit;
+        need -= below;
+        __syncwarp();
+    }
+    // collection sweep: everything strictly below the threshold, then the first `need` ties in index order
+    const unsigned thr = prefix;
+    int n_lt = 0, n_eq = 0;
+    const int base_eq = k - need;         // ties are written after the strictly-smaller ones
+    for (int j0 = 0; j0 < n_points; j0 += 32) {
+        const int j = j0 + lane;
+        const unsigned b = j < n_points ? d2_bits(q, pc, j) : 0xFFFFFFFFu;
+        const bool lt = b < thr, eq = b == thr;
+        const unsigned m_lt = __ballot_sync(0xffffffffu, lt), m_eq = __ballot_sync(0xffffffffu, eq);
+        if (lt) out[n_lt + __popc(m_lt & lt_mask)] = j;
+        const int e = n_eq + __popc(m_eq & lt_mask);
+        if (eq && e < need) out[base_eq + e] = j;
+        n_lt += __popc(m_lt);
+        n_eq += __popc(m_eq);
+    }
+}
+
+// One warp per query.  Fast path, two sweeps: (1) a 1024-bin histogram of the top bits of d^2 locates the bin that
+// holds the k-th neighbour (19 % wide in d^2, so it holds a handful of points); (2) the collection sweep writes
+// everything in lower bins and parks the boundary bin's points in shared memory, where the `need` smallest are
+// picked by (d^2 bits, index) rank -- the same set, ties to the lowest indices, as the full radix select, which
+// remains the fallback when the boundary bin overflows (e.g. many coincident points).
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __restrict__ pc, int n_points, int k,
                                                               long long* __restrict__ out_idx) {
-    __shared__ unsigned s_hist[kKnnWarps][256];
+    extern __shared__ unsigned knn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned* hist = s_hist[warp];
+    unsigned* hist = knn_smem + warp * (kKnnBins + 2 * kKnnCand);
+    unsigned* cand_key = hist + kKnnBins;
+    unsigned* cand_idx = cand_key + kKnnCand;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int qi = blockIdx.x * kKnnWarps + warp; qi < n_points; qi += gridDim.x * kKnnWarps) {
         const f3 q = ld3(pc, qi);
-        unsigned prefix = 0;                  // the bits of the k-th smallest distance found so far
-        int need = k;                         // rank of the wanted element among those matching the prefix
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0u;
-            __syncwarp();
-            for (int j = lane; j < n_points; j += 32) {
-                const unsigned b = d2_bits(q, pc, j);
-                if (pass == 0 || (b >> (shift + 8)) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
-            }
-            __syncwarp();
-            unsigned cnt[8], mine = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                cnt[i] = hist[lane * 8 + i];
-                mine += cnt[i];
-            }
-            unsigned incl = mine;             // inclusive scan of the per-lane totals
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const unsigned excl = incl - mine;
-            const bool here = (unsigned)need > excl && (unsigned)need <= incl;   // exactly one lane
-            int digit = 0, below = 0;
-            if (here) {
-                unsigned run = excl;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if ((unsigned)need > run && (unsigned)need <= run + cnt[i]) {
-                        digit = lane * 8 + i;
-                        below = (int)run;
-                    }
-                    run += cnt[i];
-                }
-            }
-            const unsigned src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
-            digit = __shfl_sync(0xffffffffu, digit, src);
-            below = __shfl_sync(0xffffffffu, below, src);
-            prefix = (prefix << 8) | (unsigned)digit;
-            need -= below;
-            __syncwarp();
-        }
-        // collection sweep: everything strictly below the threshold, then the first `need` ties in index order
-        const unsigned thr = prefix;
-        int n_lt = 0, n_eq = 0;
-        const int base_eq = k - need;         // ties are written after the strictly-smaller ones
         long long* out = out_idx + (long long)qi * k;
+        for (int i = lane; i < kKnnBins; i += 32) hist[i] = 0u;
+        __syncwarp();
+        for (int j = lane; j < n_points; j += 32) atomicAdd(&hist[d2_bits(q, pc, j) >> 21], 1u);
+        __syncwarp();
+        // bin of the k-th smallest: lane l owns bins [32 l, 32 l + 32)
+        unsigned mine = 0;
+        for (int i = 0; i < 32; ++i) mine += hist[lane * 32 + ((i + lane) & 31)];
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned excl = incl - mine;
+        const bool here = (unsigned)k > excl && (unsigned)k <= incl;
+        int bin = 0, below = 0, in_bin = 0;
+        if (here) {
+            unsigned run = excl;
+            for (int i = 0; i < 32; ++i) {
+                const unsigned c = hist[lane * 32 + i];
+                if ((unsigned)k > run && (unsigned)k <= run + c) {
+                    bin = lane * 32 + i;
+                    below = (int)run;
+                    in_bin = (int)c;
+                }
+                run += c;
+            }
+        }
+        const unsigned src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+        bin = __shfl_sync(0xffffffffu, bin, src);
+        below = __shfl_sync(0xffffffffu, below, src);
+        in_bin = __shfl_sync(0xffffffffu, in_bin, src);
+        __syncwarp();
+        if (in_bin > kKnnCand) {                      // boundary bin too full for the candidate list
+            knn_query_radix(pc, n_points, k, qi, hist, lane, out);
+            __syncwarp();
+            continue;
+        }
+        const int need = k - below;                   // how many of the boundary bin's points belong to the k nearest
+        int n_lt = 0, n_c = 0;
         for (int j0 = 0; j0 < n_points; j0 += 32) {
             const int j = j0 + lane;
             const unsigned b = j < n_points ? d2_bits(q, pc, j) : 0xFFFFFFFFu;
-            const bool lt = b < thr, eq = b == thr;
+            const unsigned bj = b >> 21;
+            const bool lt = j < n_points && bj < (unsigned)bin, eq = j < n_points && bj == (unsigned)bin;
             const unsigned m_lt = __ballot_sync(0xffffffffu, lt), m_eq = __ballot_sync(0xffffffffu, eq);
             if (lt) out[n_lt + __popc(m_lt & lt_mask)] = j;
-            const int e = n_eq + __popc(m_eq & lt_mask);
-            if (eq && e < need) out[base_eq + e] = j;
+            if (eq) {
+                const int e = n_c + __popc(m_eq & lt_mask);
+                cand_key[e] = b;
+                cand_idx[e] = (unsigned)j;
+            }
             n_lt += __popc(m_lt);
-            n_eq += __popc(m_eq);
+            n_c += __popc(m_eq);
         }
+        __syncwarp();
+        // rank of every candidate by (key, index); the `need` smallest follow the strictly-lower bins
+        for (int c0 = 0; c0 < n_c; c0 += 32) {
+            const int c = c0 + lane;
+            if (c < n_c) {
+                const unsigned key = cand_key[c], idx = cand_idx[c];
+                int rank = 0;
+                for (int o = 0; o < n_c; ++o) {
+                    const unsigned ko = cand_key[o], io = cand_idx[o];
+                    rank += (ko < key || (ko == key && io < idx)) ? 1 : 0;
+                }
+                if (rank < need) out[below + rank] = (long long)idx;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -371,8 +457,10 @@ extern "C" int cppf_knn(const float* pc, int n_points, int k, int64_t* out_idx, 
     int blocks = (n_points + pe::kKnnWarps - 1) / pe::kKnnWarps;
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    pe::knn_kernel<<<blocks, pe::kKnnWarps * 32, 0, (cudaStream_t)stream>>>(pc, n_points, k,
-                                                                             reinterpret_cast<long long*>(out_idx));
+    const size_t smem = (size_t)pe::kKnnWarps * (pe::kKnnBins + 2 * pe::kKnnCand) * sizeof(unsigned);
+    CPPF_RETURN_IF(cudaFuncSetAttribute(pe::knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pe::knn_kernel<<<blocks, pe::kKnnWarps * 32, smem, (cudaStream_t)stream>>>(pc, n_points, k,
+                                                                                reinterpret_cast<long long*>(out_idx));
     CPPF_LAUNCH_CHECK();
     return 0;
 }

@@ -83,3 +83,18 @@ def test_knn_ties_resolve_to_lowest_indices():
     assert idx[0].tolist() == [0, 1, 2, 3, 4, 5]
     # query 20 (cluster 5): 4 at d=0; clusters 4 and 6 tie at d=1 -> lowest indices 16, 17
     assert idx[20].tolist() == [16, 17, 20, 21, 22, 23]
+
+
+def test_knn_boundary_bin_overflow_falls_back_to_radix_select():
+    """500 points at exactly the same distance from a small cluster: the k-th neighbour's coarse-histogram bin holds more
+    points than the shared-memory candidate list, so the query takes the full radix-select path -- same answer (ties to
+    the lowest indices)."""
+    pts = np.zeros((510, 3), np.float32)
+    ang = np.linspace(0, 2 * np.pi, 500, endpoint=False)
+    pts[10:, 0], pts[10:, 1] = np.cos(ang), np.sin(ang)          # |p| = 1 up to rounding -> nearly identical d^2 from the origin
+    pts[10:] = np.float32([1, 0, 0])                              # make them exactly identical: 500 coincident points
+    t = torch.from_numpy(pts).to(DEV)
+    pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(DEV)
+    idx = torch.sort(pe.knn(t), dim=1)[0].cpu().numpy()
+    assert idx[0].tolist() == list(range(60))                    # 10 at d=0, then the 50 lowest-index coincident points
+    assert idx[300].tolist() == list(range(10, 70))              # a coincident point: 60 lowest indices among its 500 twins
