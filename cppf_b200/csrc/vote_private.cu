@@ -651,6 +651,7 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
                      int idx_is_64, float* grid, void* scratch, const float* corner, float res, int n_points,
                      int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, const Geom* geom, int max_cells,
                      cudaStream_t stream, int slab_cells, long long total_cells) {
+    if (n_pairs <= 0) return 0;                     // empty pair list: nothing to vote (pointers may be null)
     const bool slabs = slab_cells > 0;
     long long cells = geom ? (long long)(slabs ? slab_cells : max_cells) : (long long)gx * gy * gz;
     int pps = 0, n_slabs = 1;

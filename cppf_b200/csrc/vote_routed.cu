@@ -454,6 +454,7 @@ int vote_routed_launch(const float* points, const float* mu_nu, const uint8_t* b
                        int idx_is_64, unsigned long long* acc, void* pool_mem, int64_t pool_bytes, const float* corner,
                        float res, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
                        const Geom* geom, cudaStream_t stream) {
+    if (n_pairs <= 0) return 0;
     RoutedPlan pl{1, 1};
     if (!geom && !routed_plan(gx, gy, gz, &pl)) return (int)cudaErrorInvalidValue;
     if (n_rots > kMaxRotsP || n_rots <= 0) return (int)cudaErrorInvalidValue;

@@ -69,3 +69,67 @@ def test_config5_dense_stress_shape(n):
     corner, dims = synth.vote_grid_geometry(pc, cfg.res)
     cell = np.array(np.unravel_index(one["argmax_flat"], dims))
     assert np.all(np.abs(corner + cell * cfg.res) <= 1.5 * cfg.res)
+
+
+def test_full_size_vote_properties_n4096_dense():
+    """BASELINE config 2 at full size (N = 4096, all 16.8 M ordered pairs), where the oracle is too slow: size-independent
+    properties of the fixed-point vote.  (1) order independence: the same pairs as an explicitly permuted index list give
+    the bit-identical accumulator; (2) additivity: the accumulators of two halves of the pair list add up exactly to the
+    accumulator of the whole; (3) run-to-run determinism; (4) the routed and slab-pass variants agree bit for bit."""
+    from cppf_b200 import fast
+    n, res = 4096, synth.BOTTLE["res"]
+    pc, _ = synth.synth_bottle(n, 0)
+    corner, dims = synth.vote_grid_geometry(pc, res)
+    pcd, cd = torch.from_numpy(pc).to(DEV), torch.from_numpy(corner).to(DEV)
+    lut = fast.decode_lut(synth.BOTTLE["vote_range"]).to(DEV)
+    bins = torch.zeros(n * n, 4, dtype=torch.uint8, device=DEV)
+    bins[:, :3] = synth.trained_like_bins_dense_torch(pcd, synth.BOTTLE)
+    cells = dims[0] * dims[1] * dims[2]
+
+    def vote(idx, b):
+        grid = torch.zeros(dims, device=DEV)
+        acc = torch.zeros(cells, dtype=torch.int64, device=DEV)
+        fast.vote_fast(pcd, idx, grid, cd, res, bins=b, lut=lut, scratch=acc)
+        return grid, acc.clone()
+    g_dense, a_dense = vote(None, bins)
+    g_again, a_again = vote(None, bins)
+    assert torch.equal(a_dense, a_again) and torch.equal(g_dense, g_again)                       # (3)
+    perm = torch.randperm(n * n, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    idx_all = torch.stack([perm // n, perm % n], -1).to(torch.int32).contiguous()
+    g_perm, a_perm = vote(idx_all, bins[perm].contiguous())
+    assert torch.equal(a_dense, a_perm) and torch.equal(g_dense, g_perm)                         # (1)
+    half = n * n // 2
+    _, a_lo = vote(idx_all[:half].contiguous(), bins[perm[:half]].contiguous())
+    _, a_hi = vote(idx_all[half:].contiguous(), bins[perm[half:]].contiguous())
+    assert torch.equal(a_lo + a_hi, a_dense)                                                     # (2)
+    # every in-bounds candidate deposits 8 weights that sum to 2^14 (+- rounding): the mass counts the candidates
+    n_cand = float(a_dense.sum().item()) / 16384.0
+    assert 15.0 < n_cand / (n * n) < 30.0                                                         # ~22 per pair (SURVEY 8d)
+    assert abs(float(g_dense.double().sum().item()) - n_cand) < 1e-3 * n_cand
+    # the trained-like peak is the cell of the object's origin
+    cell = np.array(np.unravel_index(int(torch.argmax(g_dense).item()), dims))
+    assert np.all(np.abs(corner + cell * res) <= 1.5 * res)
+
+
+def test_degenerate_and_empty_inputs():
+    """Edge cases of the reference kernels (models/voting.py:21: pairs with |ab| < 1e-7 are dropped silently): a pair list
+    made only of (a, a) pairs votes nothing, keeps no survivor and still yields a finite record; zero pairs are a no-op."""
+    from cppf_b200 import fast, voting
+    cfg = PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=5000))
+    est = _est(0, cfg)
+    pc, nrm = synth.synth_bottle(300, 2)
+    same = np.repeat(np.arange(300, dtype=np.int32)[:, None], 2, 1)
+    for staged in (False, True):
+        out = est.estimate_fused(pc, nrm, seed=0, idxs=same, staged=staged)
+        assert out["n_survivors"] == 0 and out["argmax_flat"] == 0
+        assert np.isfinite(out["RT"]).all() and np.isfinite(out["scales"]).all()
+    corner, dims = synth.vote_grid_geometry(pc, cfg.res)
+    grid = torch.zeros(dims, device=DEV)
+    empty_idx = torch.zeros((0, 2), dtype=torch.int32, device=DEV)
+    fast.vote_fast(torch.from_numpy(pc).to(DEV), empty_idx, grid, torch.from_numpy(corner).to(DEV), cfg.res,
+                   mu_nu=torch.zeros((0, 2), device=DEV))
+    voting.ppf_vote(torch.from_numpy(pc).to(DEV), torch.zeros((0, 2), device=DEV), empty_idx, grid,
+                    torch.from_numpy(corner).to(DEV), cfg.res, 72, True)
+    assert float(grid.abs().sum()) == 0.0
+    with pytest.raises(RuntimeError):                     # fewer points than neighbours: the kNN refuses (k > N)
+        est.estimate_fused(pc[:40], nrm[:40], seed=0)
