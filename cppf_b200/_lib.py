@@ -32,6 +32,9 @@ SIGNATURES = {
     "cppf_backvote": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _i, _i64, _i, _i, _i, _i, _p, _f, _p]),
     "cppf_compact_scratch_bytes": (_i64, [_i64]),
     "cppf_compact_pairs": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _p, _p]),
+    "cppf_compact_count": (_i, [_p, _i64, _p, _p, _p]),
+    "cppf_rot_hist_mask": (_i, [_p, _p, _p, _p, _i, _p, _p, _i64, _p, _p, _p, _i, _i, _i, _i, _i64, C.c_uint64, _f, _p, _p]),
+    "cppf_survivor_stats_mask": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i64, _p]),
     "cppf_rot_vote": (_i, [_p, _p, _p, _p, _i, _i64, _i, _p]),
     "cppf_sphere_count": (_i, [_p, _i64, _p, _i, _f, _p, _p]),
     "cppf_findpeak": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
@@ -65,7 +68,7 @@ SIGNATURES = {
     "cppf_scene_proposals": (_i, [_p, _i, _i, _i, _f, _i, _f, _i, _p, _p, _p]),
     "cppf_pose_record_doubles": (_i, []),
     "cppf_pose_args_bytes": (_i, []),
-    "cppf_pose_workspace_bytes": (_i64, [_i, _i64, _i, _i, _i, _i, _i]),
+    "cppf_pose_workspace_bytes": (_i64, [_i, _i64, _i, _i, _i, _i, _i, _i64]),
     "cppf_pose_fused": (_i, [_p, _p]),
     "cppf_timing_create": (_p, []),
     "cppf_timing_destroy": (None, [_p]),

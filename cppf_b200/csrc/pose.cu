@@ -162,7 +162,7 @@ struct Workspace {
 };
 
 static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells, int n_rots,
-                       int n_sphere) {
+                       int n_sphere, int64_t rot_subsample) {
     const int cap_cells = max_cells > routed_max_cells ? max_cells : routed_max_cells;
     Carver c{reinterpret_cast<unsigned char*>(base)};
     Workspace w;
@@ -174,7 +174,8 @@ static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int m
     w.bins = c.take<uint8_t>((size_t)n_pairs * 4);
     w.tail = c.take<float>((size_t)n_pairs * 5);
     w.mask = c.take<uint8_t>((size_t)n_pairs);
-    w.pos = c.take<long long>((size_t)n_pairs);
+    // survivors are addressed through the mask; only the <= rot_subsample sampled positions are materialised
+    w.pos = c.take<long long>((size_t)(rot_subsample > 0 && rot_subsample < n_pairs ? rot_subsample : n_pairs));
     w.compact_scratch = c.take<unsigned char>((size_t)cppf_compact_scratch_bytes(n_pairs));
     w.grid = c.take<float>((size_t)cap_cells);
     w.acc = c.take<unsigned long long>((size_t)cap_cells);
@@ -215,9 +216,9 @@ extern "C" int cppf_pose_record_doubles(void) { return 16; }
 extern "C" int cppf_pose_args_bytes(void) { return (int)sizeof(cppf_pose_args); }
 
 extern "C" int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells,
-                                             int n_rots, int n_sphere) {
+                                             int n_rots, int n_sphere, int64_t rot_subsample) {
     if (n_pairs <= 0) n_pairs = (int64_t)n_points * n_points;
-    return (int64_t)carve(nullptr, n_points, n_pairs, knn, max_cells, routed_max_cells, n_rots, n_sphere).bytes;
+    return (int64_t)carve(nullptr, n_points, n_pairs, knn, max_cells, routed_max_cells, n_rots, n_sphere, rot_subsample).bytes;
 }
 
 extern "C" void* cppf_timing_create(void) { return new Timing(); }
@@ -268,7 +269,7 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     if (a->max_cells <= 0 || a->max_cells > cppf_vote_private_max_cells()) return (int)cudaErrorInvalidValue;
     if (a->n_sphere <= 0 || a->record == nullptr || a->workspace == nullptr) return (int)cudaErrorInvalidValue;
     if (a->routed_max_cells < 0 || a->routed_max_cells > kMaxSlabs * slab_cap_cells()) return (int)cudaErrorInvalidValue;
-    const Workspace w = carve(a->workspace, n, n_pairs, a->knn, a->max_cells, a->routed_max_cells, a->n_rots, a->n_sphere);
+    const Workspace w = carve(a->workspace, n, n_pairs, a->knn, a->max_cells, a->routed_max_cells, a->n_rots, a->n_sphere, a->rot_subsample);
     const int cap_cells = a->max_cells > a->routed_max_cells ? a->max_cells : a->routed_max_cells;
     if ((int64_t)w.bytes > a->workspace_bytes) return (int)cudaErrorInvalidValue;
     Timing* tm = reinterpret_cast<Timing*>(a->timing);
@@ -320,24 +321,25 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
                                   reinterpret_cast<const int64_t*>(w.flat), a->res, a->tol, n, n_pairs, a->n_rots, 0, 0, 0,
                                   w.geom, stream));
     CPPF_TRY(mark());
-    CPPF_TRY(cppf_compact_pairs(w.mask, a->idx, a->idx_is_64, n, n_pairs, nullptr, reinterpret_cast<int64_t*>(w.pos),
-                                reinterpret_cast<int64_t*>(w.count), w.compact_scratch, stream));
+    // survivors stay addressed through the mask: per-block counts + scan instead of a materialised list (:230-231)
+    CPPF_TRY(cppf_compact_count(w.mask, n_pairs, reinterpret_cast<int64_t*>(w.count), w.compact_scratch, stream));
     CPPF_TRY(mark());
     CPPF_RETURN_IF(cudaMemsetAsync(w.counts, 0, (size_t)a->n_sphere * 2 * sizeof(float), stream));
     const int64_t max_samples = a->rot_subsample > 0 ? a->rot_subsample : n_pairs;
     for (int j = 0; j < n_dirs; ++j) {
-        CPPF_TRY(cppf_rot_hist(a->pc, w.bins, a->lut, a->idx, a->idx_is_64, reinterpret_cast<const int64_t*>(w.pos),
-                               reinterpret_cast<const int64_t*>(w.count), a->sphere, w.counts + (size_t)j * a->n_sphere, n,
-                               a->n_rots, a->n_sphere, j, max_samples < n_pairs ? max_samples : n_pairs,
-                               a->seed * 7919ull + (uint64_t)j, a->cos_thr, stream));
+        CPPF_TRY(cppf_rot_hist_mask(a->pc, w.bins, a->lut, a->idx, a->idx_is_64, w.mask,
+                                    reinterpret_cast<const int64_t*>(w.compact_scratch), n_pairs,
+                                    reinterpret_cast<const int64_t*>(w.count), a->sphere, w.counts + (size_t)j * a->n_sphere, n,
+                                    a->n_rots, a->n_sphere, j, max_samples < n_pairs ? max_samples : n_pairs,
+                                    a->seed * 7919ull + (uint64_t)j, a->cos_thr, reinterpret_cast<int64_t*>(w.pos), stream));
         CPPF_TRY(grid_argmax_launch(w.counts + (size_t)j * a->n_sphere, a->n_sphere, nullptr,
                                     reinterpret_cast<int64_t*>(w.best + j), nullptr, stream));
     }
     CPPF_TRY(mark());
-    CPPF_TRY(cppf_survivor_stats(a->pc, a->nrm, w.tail, a->idx, a->idx_is_64, reinterpret_cast<const int64_t*>(w.pos),
-                                 reinterpret_cast<const int64_t*>(w.count), a->sphere, reinterpret_cast<const int64_t*>(w.best),
-                                 n_dirs > 1 ? reinterpret_cast<const int64_t*>(w.best + 1) : nullptr, w.stats, n, n_pairs,
-                                 stream));
+    CPPF_TRY(cppf_survivor_stats_mask(a->pc, a->nrm, w.tail, a->idx, a->idx_is_64, w.mask, a->sphere,
+                                      reinterpret_cast<const int64_t*>(w.best),
+                                      n_dirs > 1 ? reinterpret_cast<const int64_t*>(w.best + 1) : nullptr, w.stats, n, n_pairs,
+                                      stream));
     pack_record_kernel<<<1, 1, 0, stream>>>(w.geom, w.flat, w.best, w.stats, n_dirs, a->record);
     CPPF_LAUNCH_CHECK();
     CPPF_TRY(mark());

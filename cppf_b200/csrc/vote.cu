@@ -621,6 +621,22 @@ extern "C" int64_t cppf_compact_scratch_bytes(int64_t n_pairs) {
     return nb * (int64_t)(sizeof(int) + sizeof(long long)) + 64;
 }
 
+// count + scan only: *out_count = number of set mask bytes, scratch[0 : nb] (int64) = exclusive survivor offsets of the
+// 2048-pair blocks -- all the fused path needs to address "the r-th survivor" without materialising the list
+extern "C" int cppf_compact_count(const uint8_t* mask, int64_t n_pairs, int64_t* out_count, void* scratch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pairs <= 0) return (int)cudaMemsetAsync(out_count, 0, sizeof(int64_t), stream);
+    const int64_t nb = (n_pairs + kCompactBlock * kCompactItems - 1) / (kCompactBlock * kCompactItems);
+    if (nb > 0x7FFFFFFF) return (int)cudaErrorInvalidValue;
+    long long* block_offsets = reinterpret_cast<long long*>(scratch);
+    int* block_counts = reinterpret_cast<int*>(block_offsets + nb);
+    compact_count_kernel<<<(int)nb, kCompactBlock, 0, stream>>>(mask, (long long)n_pairs, block_counts);
+    CPPF_LAUNCH_CHECK();
+    compact_scan_kernel<<<1, 1024, 0, stream>>>(block_counts, (int)nb, block_offsets, reinterpret_cast<long long*>(out_count));
+    CPPF_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int cppf_compact_pairs(const uint8_t* mask, const void* idx, int idx_is_64, int n_points, int64_t n_pairs,
                                   int32_t* out_idx, int64_t* out_pos, int64_t* out_count, void* scratch,
                                   void* stream_) {

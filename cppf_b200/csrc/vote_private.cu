@@ -16,6 +16,9 @@
 
 namespace cppf {
 
+constexpr int kSelectBlockBytes = 2048;  // = kCompactBlock * kCompactItems of vote.cu (cppf_compact_count)
+constexpr int kSelectBlock = kSelectBlockBytes;
+
 struct VotePParams {
     const float2* rot_tab;
     const float* points;
@@ -441,13 +444,88 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
 // window |y_s - c_y| <= d can count.  Each thread takes candidates, binary-searches that window in shared
 // memory and tests its bins with the same dot-product expression as the full scan -> identical counts at
 // 1/35 of the work.  A sphere whose y is not monotone (any other `sphere` array) falls back to the full scan.
+// positions of the sub-sampled survivors, one warp per sample: sample j is survivor r_j = (off + j * stride) mod count
+// (the same bijection as rot_hist_kernel), found as the r_j-th set byte of the mask -- block by binary search over the
+// exclusive block offsets, then the warp scans the block 512 bytes at a time (popc of 0/1 bytes + warp prefix)
+__global__ void __launch_bounds__(256) select_samples_kernel(const uint8_t* __restrict__ mask,
+                                                             const long long* __restrict__ block_offsets, int n_blocks,
+                                                             long long n_pairs, const long long* __restrict__ count_ptr,
+                                                             long long max_samples, unsigned long long offset_seed,
+                                                             long long* __restrict__ out_pos) {
+    const long long count = *count_ptr;
+    const long long m = count < max_samples ? count : max_samples;
+    const int lane = threadIdx.x & 31;
+    unsigned long long stride = 1000003ull;
+    if (count % 1000003ll == 0) stride = 999983ull;
+    if (m == count) stride = 1ull;
+    const unsigned long long off = m == count ? 0ull : offset_seed % (unsigned long long)(count > 0 ? count : 1);
+    for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < m;
+         j += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const long long r = (long long)((off + (unsigned long long)j * stride) % (unsigned long long)count);
+        int lo = 0, hi = n_blocks - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (block_offsets[mid] <= r) lo = mid; else hi = mid - 1;
+        }
+        const long long base = (long long)lo * kSelectBlockBytes;
+        int need = (int)(r - block_offsets[lo]);
+        long long found = n_pairs - 1;
+        for (int c = 0; c < kSelectBlockBytes; c += 512) {
+            const long long q = base + c + lane * 16;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (q + 16 <= n_pairs) {
+                w = __ldg(reinterpret_cast<const uint4*>(mask + q));
+            } else {
+                unsigned char b[16];
+                for (int t = 0; t < 16; ++t) b[t] = q + t < n_pairs ? mask[q + t] : 0;
+                w = make_uint4(b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24, b[4] | b[5] << 8 | b[6] << 16 | b[7] << 24,
+                               b[8] | b[9] << 8 | b[10] << 16 | b[11] << 24, b[12] | b[13] << 8 | b[14] << 16 | b[15] << 24);
+            }
+            const int cnt = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (need >= total) {
+                need -= total;
+                continue;
+            }
+            const int excl = incl - cnt;
+            const bool mine = need >= excl && need < incl;              // exactly one lane
+            if (mine) {
+                int k = need - excl;
+                const unsigned words[4] = {w.x, w.y, w.z, w.w};
+                for (int t = 0; t < 16; ++t)
+                    if ((words[t >> 2] >> ((t & 3) * 8)) & 1u) {
+                        if (k-- == 0) {
+                            found = q + t;
+                            break;
+                        }
+                    }
+            }
+            const unsigned src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+            found = __shfl_sync(0xffffffffu, found, src);
+            break;
+        }
+        if (lane == 0) out_pos[j] = found;
+    }
+}
+
 struct RotHistParams {
     const float2* rot_tab;
     const float* points;
     const uint8_t* bins;
     const float* lut;            // up angles lut[64:100], right angles lut[100:136]
     const void* idx;
-    const long long* pos;        // compacted survivor pair positions
+    const long long* pos;        // compacted survivor pair positions, or nullptr: survivor r = r-th set byte of `mask`
+    int pos_is_sample;           //   1: pos[j] already is the j-th sub-sampled survivor (select_samples_kernel)
+    const uint8_t* mask;         //   found through the exclusive per-2048-pair block offsets of cppf_compact_count
+    const long long* block_offsets;
+    int n_blocks;
+    long long n_pairs;
     const long long* count;      // number of survivors (device)
     const float* sphere;         // [n_bins][3]
     float* counts;               // [n_bins] float (exact integers)
@@ -460,6 +538,33 @@ struct RotHistParams {
 
 constexpr int kRotHistPairs = 64;
 constexpr int kRotHistThreads = 512;
+
+// position of the r-th (0-based) surviving pair, in pair order: block by binary search over the exclusive block
+// offsets, then a scan of that block's 0/1 mask bytes, 16 at a time
+__device__ __forceinline__ long long select_survivor(const uint8_t* __restrict__ mask, const long long* __restrict__ block_offsets,
+                                                     int n_blocks, long long n_pairs, long long r) {
+    int lo = 0, hi = n_blocks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (block_offsets[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    const long long base = (long long)lo * kSelectBlock;
+    int need = (int)(r - block_offsets[lo]);
+    for (int c = 0; c < kSelectBlock; c += 16) {
+        const long long q = base + c;
+        if (q + 16 <= n_pairs) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(mask + q));
+            const int cnt = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+            if (need >= cnt) {
+                need -= cnt;
+                continue;
+            }
+        }
+        for (int b = 0; b < 16 && q + b < n_pairs; ++b)
+            if (mask[q + b] && need-- == 0) return q + b;
+    }
+    return n_pairs - 1;      // unreachable for r < count
+}
 
 template <bool IDX64>
 __global__ void __launch_bounds__(kRotHistThreads) rot_hist_kernel(const RotHistParams prm) {
@@ -488,7 +593,9 @@ __global__ void __launch_bounds__(kRotHistThreads) rot_hist_kernel(const RotHist
         fr[10] = 0.f;
         const long long j = j0 + threadIdx.x;
         if (j < m) {
-            const long long p = prm.pos[(off + (unsigned long long)j * stride) % (unsigned long long)count];
+            const long long r = (long long)((off + (unsigned long long)j * stride) % (unsigned long long)count);
+            const long long p = prm.pos ? prm.pos[prm.pos_is_sample ? j : r]
+                                        : select_survivor(prm.mask, prm.block_offsets, prm.n_blocks, prm.n_pairs, r);
             int ia, ib;
             pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
             const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
@@ -561,7 +668,8 @@ struct StatsParams {
     const float* nrm;
     const float* tail;           // [5][n_pairs]
     const void* idx;
-    const long long* pos;
+    const long long* pos;        // compacted survivor positions, or nullptr: every pair p with mask[p] != 0
+    const uint8_t* mask;
     const long long* count;
     const float* sphere;
     const long long* best_up;    // argmax of the up histogram (device)
@@ -573,7 +681,7 @@ struct StatsParams {
 
 template <bool IDX64>
 __global__ void __launch_bounds__(256) survivor_stats_kernel(const StatsParams prm) {
-    const long long count = *prm.count;
+    const long long count = prm.pos ? *prm.count : prm.n_pairs;      // mask mode walks every pair
     const long long bu = *prm.best_up;
     const f3 du = {__ldg(prm.sphere + 3 * bu), __ldg(prm.sphere + 3 * bu + 1), __ldg(prm.sphere + 3 * bu + 2)};
     f3 dr = {0.f, 0.f, 0.f};
@@ -588,7 +696,10 @@ __global__ void __launch_bounds__(256) survivor_stats_kernel(const StatsParams p
     for (long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; j0 < count; j0 += 4 * stride) {
         long long p[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) p[u] = j0 + u * stride < count ? prm.pos[j0 + u * stride] : -1;
+        for (int u = 0; u < 4; ++u) {
+            const long long j = j0 + u * stride;
+            p[u] = j < count ? (prm.pos ? prm.pos[j] : (prm.mask[j] ? j : -1)) : -1;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (p[u] < 0) continue;
@@ -776,18 +887,21 @@ extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, cons
                                 n_rots, gx, gy, gz, nullptr, (cudaStream_t)stream_);
 }
 
-extern "C" int cppf_rot_hist(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
-                             const int64_t* pos, const int64_t* count, const float* sphere, float* counts, int n_points,
-                             int n_rots, int n_bins, int which, int64_t max_samples, uint64_t offset_seed, float thr,
-                             void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace cppf {
+int rot_hist_launch(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                    const int64_t* pos, const uint8_t* mask, const int64_t* block_offsets, int64_t n_pairs, const int64_t* count,
+                    const float* sphere, float* counts, int n_points, int n_rots, int n_bins, int which, int64_t max_samples,
+                    uint64_t offset_seed, float thr, cudaStream_t stream, int pos_is_sample = 0) {
     if (n_rots > kMaxRotsP || n_rots <= 0 || max_samples <= 0 || n_bins <= 0) return (int)cudaErrorInvalidValue;
+    if (pos == nullptr && (mask == nullptr || block_offsets == nullptr)) return (int)cudaErrorInvalidValue;
     int terr = 0;
     const float2* rot_tab = rot_table_device(stream, &terr);
     if (terr) return terr;
     // half-width of the y window: |c - s|^2 < |c|^2 + |s|^2 - 2 thr with |c|, |s| <= 1 + 2e-6, plus slack
     const float ywin = thr > 0.f ? sqrtf(fmaxf(0.f, 2.00002f - 2.f * thr)) + 1e-4f : 4.f;
-    RotHistParams prm{rot_tab, points, bins, lut, idx, reinterpret_cast<const long long*>(pos),
+    const int n_blocks = (int)((n_pairs + kSelectBlock - 1) / kSelectBlock);
+    RotHistParams prm{rot_tab, points, bins, lut, idx, reinterpret_cast<const long long*>(pos), pos_is_sample, mask,
+                      reinterpret_cast<const long long*>(block_offsets), n_blocks, (long long)n_pairs,
                       reinterpret_cast<const long long*>(count), sphere, counts, n_points, n_rots, n_bins, which,
                       (long long)max_samples, offset_seed, thr, ywin};
     const long long blocks = (max_samples + kRotHistPairs - 1) / kRotHistPairs;
@@ -801,13 +915,13 @@ extern "C" int cppf_rot_hist(const float* points, const uint8_t* bins, const flo
     return 0;
 }
 
-extern "C" int cppf_survivor_stats(const float* points, const float* nrm, const float* tail, const void* idx,
-                                   int idx_is_64, const int64_t* pos, const int64_t* count, const float* sphere,
-                                   const int64_t* best_up, const int64_t* best_right, double* out, int n_points,
-                                   int64_t n_pairs, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+int survivor_stats_launch(const float* points, const float* nrm, const float* tail, const void* idx, int idx_is_64,
+                          const int64_t* pos, const uint8_t* mask, const int64_t* count, const float* sphere,
+                          const int64_t* best_up, const int64_t* best_right, double* out, int n_points, int64_t n_pairs,
+                          cudaStream_t stream) {
+    if (pos == nullptr && mask == nullptr) return (int)cudaErrorInvalidValue;
     CPPF_RETURN_IF(cudaMemsetAsync(out, 0, 6 * sizeof(double), stream));
-    StatsParams prm{points, nrm, tail, idx, reinterpret_cast<const long long*>(pos),
+    StatsParams prm{points, nrm, tail, idx, reinterpret_cast<const long long*>(pos), mask,
                     reinterpret_cast<const long long*>(count), sphere, reinterpret_cast<const long long*>(best_up),
                     reinterpret_cast<const long long*>(best_right), out, n_points, (long long)n_pairs};
     const int blocks = sm_count() * 8;
@@ -816,3 +930,51 @@ extern "C" int cppf_survivor_stats(const float* points, const float* nrm, const 
     CPPF_LAUNCH_CHECK();
     return 0;
 }
+}  // namespace cppf
+
+extern "C" int cppf_rot_hist(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                             const int64_t* pos, const int64_t* count, const float* sphere, float* counts, int n_points,
+                             int n_rots, int n_bins, int which, int64_t max_samples, uint64_t offset_seed, float thr,
+                             void* stream_) {
+    if (pos == nullptr) return (int)cudaErrorInvalidValue;
+    return rot_hist_launch(points, bins, lut, idx, idx_is_64, pos, nullptr, nullptr, 0, count, sphere, counts, n_points, n_rots,
+                           n_bins, which, max_samples, offset_seed, thr, (cudaStream_t)stream_);
+}
+
+extern "C" int cppf_rot_hist_mask(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                                  const uint8_t* mask, const int64_t* block_offsets, int64_t n_pairs, const int64_t* count,
+                                  const float* sphere, float* counts, int n_points, int n_rots, int n_bins, int which,
+                                  int64_t max_samples, uint64_t offset_seed, float thr, int64_t* sample_scratch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (mask == nullptr || block_offsets == nullptr || max_samples <= 0) return (int)cudaErrorInvalidValue;
+    if (sample_scratch == nullptr)                  // no room for the sample list: every thread selects its own survivor
+        return rot_hist_launch(points, bins, lut, idx, idx_is_64, nullptr, mask, block_offsets, n_pairs, count, sphere, counts,
+                               n_points, n_rots, n_bins, which, max_samples, offset_seed, thr, stream);
+    const int n_blocks = (int)((n_pairs + kSelectBlockBytes - 1) / kSelectBlockBytes);
+    long long blocks = (max_samples + 7) / 8;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    select_samples_kernel<<<(int)blocks, 256, 0, stream>>>(mask, reinterpret_cast<const long long*>(block_offsets), n_blocks,
+                                                          (long long)n_pairs, reinterpret_cast<const long long*>(count),
+                                                          (long long)max_samples, offset_seed,
+                                                          reinterpret_cast<long long*>(sample_scratch));
+    CPPF_LAUNCH_CHECK();
+    return rot_hist_launch(points, bins, lut, idx, idx_is_64, sample_scratch, nullptr, nullptr, n_pairs, count, sphere, counts,
+                           n_points, n_rots, n_bins, which, max_samples, offset_seed, thr, stream, 1);
+}
+
+extern "C" int cppf_survivor_stats(const float* points, const float* nrm, const float* tail, const void* idx,
+                                   int idx_is_64, const int64_t* pos, const int64_t* count, const float* sphere,
+                                   const int64_t* best_up, const int64_t* best_right, double* out, int n_points,
+                                   int64_t n_pairs, void* stream_) {
+    if (pos == nullptr) return (int)cudaErrorInvalidValue;
+    return survivor_stats_launch(points, nrm, tail, idx, idx_is_64, pos, nullptr, count, sphere, best_up, best_right, out,
+                                 n_points, n_pairs, (cudaStream_t)stream_);
+}
+
+extern "C" int cppf_survivor_stats_mask(const float* points, const float* nrm, const float* tail, const void* idx,
+                                        int idx_is_64, const uint8_t* mask, const float* sphere, const int64_t* best_up,
+                                        const int64_t* best_right, double* out, int n_points, int64_t n_pairs, void* stream_) {
+    return survivor_stats_launch(points, nrm, tail, idx, idx_is_64, nullptr, mask, nullptr, sphere, best_up, best_right, out,
+                                 n_points, n_pairs, (cudaStream_t)stream_);
+}
+

@@ -297,7 +297,7 @@ class PoseEstimator:
         """One workspace per (device, stream), shared by every estimator (categories differ only in weights) and
         grown on demand: work on one stream is ordered, so successive objects can reuse it."""
         nb = _lib.lib().cppf_pose_workspace_bytes(n, n_pairs, self.cfg.knn, max_cells, routed_max_cells, self.cfg.num_rots,
-                                                  self.sphere.shape[0])
+                                                  self.sphere.shape[0], int(self.cfg.rot_subsample or 0))
         slot = (self.device.index or 0, torch.cuda.current_stream(self.device).cuda_stream)
         ws = _WORKSPACES.get(slot)
         if ws is None or ws.numel() < nb:

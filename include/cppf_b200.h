@@ -109,6 +109,11 @@ int64_t cppf_compact_scratch_bytes(int64_t n_pairs);
 int cppf_compact_pairs(const uint8_t* mask, const void* idx, int idx_is_64, int n_points, int64_t n_pairs,
                        int32_t* out_idx, int64_t* out_pos, int64_t* out_count, void* scratch, void* stream);
 
+/* The first two steps of cppf_compact_pairs only: *out_count and, in scratch[0 : ceil(n_pairs / 2048)] (int64), the
+ * exclusive survivor offsets of the 2048-pair blocks -- enough for cppf_rot_hist_mask / cppf_survivor_stats_mask to
+ * address the survivors without the materialised list. */
+int cppf_compact_count(const uint8_t* mask, int64_t n_pairs, int64_t* out_count, void* scratch, void* stream);
+
 /* replaces rot_voting_kernel (models/voting.py:119-147): outputs_up [n_pairs, n_rots, 3]. */
 int cppf_rot_vote(const float* points, const float* preds_rot, float* outputs_up, const void* idx, int idx_is_64,
                   int64_t n_pairs, int n_rots, void* stream);
@@ -218,6 +223,17 @@ int cppf_rot_hist(const float* points, const uint8_t* bins, const float* lut, co
                   int n_rots, int n_bins, int which, int64_t max_samples, uint64_t offset_seed, float thr,
                   void* stream);
 
+/* cppf_rot_hist / cppf_survivor_stats with the survivors given as the back-vote mask itself (uint8 [n_pairs]) instead of
+ * the compacted list: survivor r is the r-th set byte (block_offsets from cppf_compact_count); same sample, same sums.
+ * sample_scratch: int64 [max_samples] for the positions of the sub-sampled survivors (NULL: slower in-kernel selection). */
+int cppf_rot_hist_mask(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
+                       const uint8_t* mask, const int64_t* block_offsets, int64_t n_pairs, const int64_t* count,
+                       const float* sphere, float* counts, int n_points, int n_rots, int n_bins, int which,
+                       int64_t max_samples, uint64_t offset_seed, float thr, int64_t* sample_scratch, void* stream);
+int cppf_survivor_stats_mask(const float* points, const float* nrm, const float* tail, const void* idx, int idx_is_64,
+                             const uint8_t* mask, const float* sphere, const int64_t* best_up, const int64_t* best_right,
+                             double* out, int n_points, int64_t n_pairs, void* stream);
+
 /* nocs/inference.py:286-302,335 over the survivors: out[0:3] = sum of log-scales, out[3] =
  * count, out[4] = S_up, out[5] = S_right, S = sum aux*(2t-1); down_loss < up_loss <=> S < 0. */
 int cppf_survivor_stats(const float* points, const float* nrm, const float* tail, const void* idx, int idx_is_64,
@@ -272,7 +288,7 @@ typedef struct cppf_pose_args {
 int cppf_pose_record_doubles(void);
 int cppf_pose_args_bytes(void);            /* sizeof(cppf_pose_args) as compiled: lets a binding check its mirror of the struct */
 int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells, int n_rots,
-                                  int n_sphere);
+                                  int n_sphere, int64_t rot_subsample);
 int cppf_pose_fused(const cppf_pose_args* args, void* stream);
 
 /* Stage timing for cppf_pose_fused: CUDA events recorded on the launching stream around every stage.

@@ -38,5 +38,5 @@ def test_pose_args_struct_mirror_matches_the_compiled_layout():
     assert C.sizeof(_lib.PoseArgs) == L.cppf_pose_args_bytes()
     assert L.cppf_pose_record_doubles() == 16
     assert L.cppf_timing_stages() == 10 and L.cppf_timing_stage_name(3) == b"encode_sample"
-    assert L.cppf_pose_workspace_bytes(4096, 0, 60, 17820, 0, 72, 480) > 5 * 4096 * 4096
+    assert L.cppf_pose_workspace_bytes(4096, 0, 60, 17820, 0, 72, 480, 10000) > 5 * 4096 * 4096
     assert L.cppf_vote_routed_supported(64, 64, 64) == 1 and L.cppf_vote_routed_supported(640, 640, 640) == 0

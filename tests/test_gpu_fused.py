@@ -273,7 +273,7 @@ def test_one_call_pipeline_equals_staged_pipeline(regress_right, dense):
         assert one["n_survivors"] == staged["n_survivors"] > 0
         np.testing.assert_allclose(one["T_host"], staged["T_host"], rtol=0, atol=0)
         np.testing.assert_allclose(one["pred_scale"], staged["pred_scale"], rtol=1e-6)
-        np.testing.assert_array_equal(one["RT"], staged["RT"])
+        np.testing.assert_allclose(one["RT"], staged["RT"], rtol=1e-6, atol=1e-9)     # scale sums: different summation order
     # asynchronous use: several objects in flight, records read afterwards
     pend = [est.estimate_fused(pc, nrm, seed=4, idxs=idxs, uniforms=u, inject_bins=inj, sync=False) for _ in range(3)]
     for q in pend:
