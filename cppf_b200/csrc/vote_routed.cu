@@ -28,12 +28,12 @@ namespace cppf {
 int vote_finalize_launch(const unsigned long long* acc, float* grid, int cells, const Geom* geom, int only_mode,
                          cudaStream_t stream);
 
-constexpr int kChunk = 128;                          // candidates per chunk (2 KB)
-constexpr int kRouteWarps = 20;
+constexpr int kChunk = 512;                          // candidates per chunk (8 KB)
+constexpr int kRouteWarps = 32;
 constexpr int kRouteThreads = kRouteWarps * 32;
 constexpr int kRouteBatch = 2 * kRouteThreads;       // pairs sorted between two block barriers
 constexpr int kRouteKeys = kMaxRotsP + 1;
-constexpr int kStage = 64;                           // per-warp per-slab staging ring (float4 slots)
+constexpr int kStage = 64;                           // per-warp ring of in-bounds candidates (float4 slots)
 
 struct RouteCounters {
     unsigned n_chunks;               // chunks reserved so far
@@ -63,21 +63,19 @@ struct RouteParams {
     const Geom* geom;                // optional: device-side geometry (mode 1) overrides corner / dims / bounds / slabs
 };
 
-// per-warp, per-slab staging state (shared memory): ring head / tail, next pool entry of the open chunk, entries
-// left in it
+// per-warp, per-slab write cursor (shared memory): the open chunk of the warp for that slab
 struct SlabState {
-    unsigned head, tail;
-    int chunk_left;
-    unsigned chunk_pos;              // pool entry index (max_chunks * 128 < 2^32), 0xFFFFFFFF = pool exhausted
+    unsigned base;                   // first pool entry of the open chunk; kNoChunk = none open (or pool exhausted)
+    int used;                        // entries written into it
 };
+constexpr unsigned kNoChunk = 0xFFFFFFFFu;
 
 template <bool IDX64, bool BINS>
 __global__ void __launch_bounds__(kRouteThreads, 1) route_kernel(const RouteParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tab = reinterpret_cast<float2*>(smem_raw);
     float* s_lut = reinterpret_cast<float*>(s_tab + kRotTabP);
-    float4* s_stage = reinterpret_cast<float4*>(s_lut + 64);                    // [warp][slab][kStage]
-    float4* s_queue = s_stage + kRouteWarps * kMaxSlabs * kStage;               // [warp][kStage]: in-bounds candidates (d)
+    float4* s_queue = reinterpret_cast<float4*>(s_lut + 64);                    // [warp][kStage]: in-bounds candidates (d)
     unsigned short* s_perm = reinterpret_cast<unsigned short*>(s_queue + kRouteWarps * kStage);
     __shared__ int s_hist[kRouteKeys + 3], s_start[kRouteKeys + 3], s_nlut[32];
     __shared__ int s_total, s_next;
@@ -107,51 +105,30 @@ __global__ void __launch_bounds__(kRouteThreads, 1) route_kernel(const RoutePara
     if (threadIdx.x < kRouteKeys + 3) s_hist[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kRouteWarps * kMaxSlabs; i += blockDim.x) {
         SlabState* st = &s_state[0][0] + i;
-        st->head = st->tail = 0u;
-        st->chunk_left = 0;
-        st->chunk_pos = 0u;
+        st->base = kNoChunk;
+        st->used = 0;
     }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(s_stage + warp * kMaxSlabs * kStage);
     const unsigned q_addr = (unsigned)__cvta_generic_to_shared(s_queue + warp * kStage);
     SlabState* my_state = s_state[warp];
     const float cx = __ldg(corner), cy = __ldg(corner + 1), cz = __ldg(corner + 2);
 
-    // one 512-byte row of slab s (warp-uniform s): staged entries [head, head+count) -> pool, reserving a chunk when needed
-    auto flush_row = [&](int s, int count) {
-        SlabState st = my_state[s];
-        if (st.chunk_left == 0) {
-            unsigned id = 0;
-            if (lane == 0) {
-                id = atomicAdd(&prm.counters->n_chunks, 1u);
-                if (id < prm.max_chunks) {
-                    prm.chunk_slab[id] = (uint8_t)s;
-                    atomicAdd(&prm.counters->slab_chunks[s], 1u);
-                } else {
-                    prm.counters->overflow = 1u;
-                }
-            }
-            id = __shfl_sync(0xffffffffu, id, 0);
-            st.chunk_pos = id < prm.max_chunks ? id * (unsigned)kChunk : 0xFFFFFFFFu;
-            st.chunk_left = kChunk;
-        }
-        float4 e = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);      // NaN x = padding
-        if (lane < count) e = ld_shared_f4(stage_addr + ((s * kStage + ((st.head + lane) & (kStage - 1))) << 4));
-        if (st.chunk_pos != 0xFFFFFFFFu) {
-            prm.pool[(size_t)st.chunk_pos + lane] = e;
-            st.chunk_pos += 32u;
-        }
-        st.chunk_left -= 32;
-        st.head += (unsigned)count;
+    const float4 pad = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);      // NaN x = padding entry
+    // close the warp's open chunk of slab s (warp-uniform s): NaN-pad its unused tail so that chunks are dense
+    auto close_chunk = [&](int s) {
+        const SlabState st = my_state[s];
+        if (st.base != kNoChunk)
+            for (int e = st.used + lane; e < kChunk; e += 32) prm.pool[(size_t)st.base + e] = pad;
         __syncwarp();
-        if (lane == 0) my_state[s] = st;
+        if (lane == 0) my_state[s] = SlabState{kNoChunk, 0};
         __syncwarp();
     };
-    // 32 queued candidates (d = candidate - corner): the reference's `/ res`, its exact in-bounds test, then each
-    // survivor goes to the staging ring of the slab that owns floor(g.x); full rows are written out
+    // 32 queued candidates (d = candidate - corner): the reference's `/ res`, its exact in-bounds test, then every
+    // survivor is written straight into the open chunk of the slab that owns floor(g.x) -- lanes of the same slab get
+    // consecutive entries (match_any rank), so a call writes a few contiguous runs of 16-byte entries
     auto route32 = [&](unsigned q_head, int count) {
         bool ok = lane < count;
         float gxf = 0.f, gyf = 0.f, gzf = 0.f;
@@ -164,20 +141,33 @@ __global__ void __launch_bounds__(kRouteThreads, 1) route_kernel(const RoutePara
         }
         const int slab = ok ? (int)s_slab_of_x[(int)gxf & 1023] : (kMaxSlabs + lane);    // misses: private keys
         const unsigned peers = __match_any_sync(0xffffffffu, slab);
-        if (ok) {
-            const unsigned t = my_state[slab].tail;
-            st_shared_f4(stage_addr + ((slab * kStage + ((t + __popc(peers & lt_mask)) & (kStage - 1))) << 4), gxf, gyf, gzf);
+        const bool leader = ok && (peers & lt_mask) == 0u;
+        if (leader && my_state[slab].base == kNoChunk) {                       // open a chunk for this slab
+            const unsigned id = atomicAdd(&prm.counters->n_chunks, 1u);
+            if (id < prm.max_chunks) {
+                prm.chunk_slab[id] = (uint8_t)slab;
+                atomicAdd(&prm.counters->slab_chunks[slab], 1u);
+                my_state[slab] = SlabState{id * (unsigned)kChunk, 0};
+            } else {
+                prm.counters->overflow = 1u;                                   // pool exhausted: the votes are dropped
+            }
         }
         __syncwarp();
-        if (ok && (peers & lt_mask) == 0u) my_state[slab].tail += __popc(peers);        // one leader per slab
+        if (ok) {
+            const SlabState st = my_state[slab];
+            if (st.base != kNoChunk) prm.pool[(size_t)st.base + st.used + __popc(peers & lt_mask)] = make_float4(gxf, gyf, gzf, 0.f);
+        }
         __syncwarp();
-        unsigned full = 0u;
-        if (lane < n_slabs) full = my_state[lane].tail - my_state[lane].head >= 32u ? 1u : 0u;
-        unsigned todo = __ballot_sync(0xffffffffu, full != 0u);
+        if (leader) my_state[slab].used += __popc(peers);
+        __syncwarp();
+        // a chunk that cannot take another 32 entries is closed now, so the next call never has to split a run
+        bool full = false;
+        if (lane < n_slabs) full = my_state[lane].base != kNoChunk && my_state[lane].used > kChunk - 32;
+        unsigned todo = __ballot_sync(0xffffffffu, full);
         while (todo) {
             const int s = __ffs(todo) - 1;
             todo &= todo - 1u;
-            flush_row(s, 32);
+            close_chunk(s);
         }
     };
 
@@ -297,12 +287,7 @@ __global__ void __launch_bounds__(kRouteThreads, 1) route_kernel(const RoutePara
         if (q_tail != q_head) route32(q_head, (int)(q_tail - q_head));
         __syncthreads();
     }
-    // drain: the staged remainders, then NaN padding up to the end of every open chunk
-    for (int s = 0; s < n_slabs; ++s) {
-        const int rem = (int)(my_state[s].tail - my_state[s].head);
-        if (rem > 0) flush_row(s, rem);
-        while (my_state[s].chunk_left > 0 && my_state[s].chunk_left < kChunk) flush_row(s, 0);
-    }
+    for (int s = 0; s < n_slabs; ++s) close_chunk(s);      // NaN-pad whatever is still open
 }
 
 struct SplatParams {
@@ -376,9 +361,13 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
     const float fx0 = (float)x0;
     __shared__ unsigned s_list[kSplatThreads];
     __shared__ unsigned s_count;
-    // a round = 1024 chunk tags per CTA (<= 1024 chunks x 128 candidates = 131 072 votes per cell, below the
-    // 2^32 - 2^30 headroom the guard leaves): the chunks of this slab are compacted into a list, then the warps
-    // take them round-robin (every chunk is the same amount of work)
+    // a round = 1024 chunk tags per CTA: the chunks of this slab are compacted into a list, then the warps take them
+    // round-robin (every chunk is the same amount of work).  Overflow guard: `pending` bounds the votes any cell can have
+    // received since the last scan (every listed candidate could hit the same cell); before a round could push a cell past
+    // 2^32, the cells holding >= 2^28 units are flushed to the global accumulator.
+    constexpr unsigned kSplatFlushAt = 1u << 28;
+    constexpr unsigned kHeadroomVotes = (0xFFFFFFFFu >> kFixShift) - 1024u;
+    unsigned pending = 0;
     for (unsigned long long r0 = 0;; ++r0) {
         const unsigned long long first = (r0 * (unsigned long long)m + (unsigned long long)j) * 1024ull;
         if (first >= n_chunks) break;
@@ -393,21 +382,38 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
         if (mine) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = threadIdx.x;
         __syncthreads();
         const unsigned count = s_count;
-        for (unsigned c = warp; c < count; c += kSplatThreads / 32) {
-            const float4* ch = prm.pool + (first + s_list[c]) * kChunk;
-            float4 g[kChunk / 32];
+        for (unsigned c0 = 0; c0 < count; c0 += 256u) {                       // <= 256 chunks (131 072 votes) between guard checks
+            const unsigned c1 = min(count, c0 + 256u);
+            if (pending + (c1 - c0) * (unsigned)kChunk > kHeadroomVotes) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+                    const unsigned v = s_grid[i];
+                    if (v >= kSplatFlushAt) {
+                        atomicAdd(prm.acc + (long long)x0 * gyz + i, (unsigned long long)v);
+                        s_grid[i] = 0u;
+                    }
+                }
+                __syncthreads();
+                pending = kSplatFlushAt >> kFixShift;                          // what an unflushed cell may still hold
+            }
+            pending += (c1 - c0) * (unsigned)kChunk;
+            for (unsigned c = c0 + warp; c < c1; c += kSplatThreads / 32) {
+                const float4* ch = prm.pool + (first + s_list[c]) * kChunk;
+                float4 g[4], nx[4];
 #pragma unroll
-            for (int q = 0; q < kChunk / 32; ++q) g[q] = __ldg(ch + q * 32 + lane);
+                for (int q = 0; q < 4; ++q) g[q] = __ldg(ch + q * 32 + lane);
+#pragma unroll 1
+                for (int part = 0; part < kChunk / 128; ++part) {
+                    if (part + 1 < kChunk / 128) {
 #pragma unroll
-            for (int q = 0; q < kChunk / 32; ++q)
-                if (g[q].x == g[q].x) splat_fixed(s_grid, g[q].x - fx0, g[q].y, g[q].z, gyz, gz);   // NaN = padding
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-            const unsigned v = s_grid[i];
-            if (v >= (1u << 30)) {
-                atomicAdd(prm.acc + (long long)x0 * gyz + i, (unsigned long long)v);
-                s_grid[i] = 0u;
+                        for (int q = 0; q < 4; ++q) nx[q] = __ldg(ch + (part + 1) * 128 + q * 32 + lane);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (g[q].x == g[q].x) splat_fixed(s_grid, g[q].x - fx0, g[q].y, g[q].z, gyz, gz);   // NaN = padding
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) g[q] = nx[q];
+                }
             }
         }
     }
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
 }
 
 static size_t route_smem() {
-    return (size_t)kRotTabP * 8 + 64 * 4 + (size_t)kRouteWarps * (kMaxSlabs + 1) * kStage * 16 + (size_t)kRouteBatch * 2;
+    return (size_t)kRotTabP * 8 + 64 * 4 + (size_t)kRouteWarps * kStage * 16 + (size_t)kRouteBatch * 2;
 }
 
 struct RoutedPlan {
@@ -437,7 +443,7 @@ static bool routed_plan(int gx, int gy, int gz, RoutedPlan* pl) {
     return pl->n_slabs <= kMaxSlabs;
 }
 
-static int64_t routed_slack_chunks() { return (int64_t)sm_count() * kRouteWarps * kMaxSlabs * 2; }   // partly filled chunks
+static int64_t routed_slack_chunks() { return (int64_t)sm_count() * kRouteWarps * kMaxSlabs + 64; }   // open chunks
 static int64_t routed_min_pairs() { return (int64_t)sm_count() * kRouteBatch; }
 
 // bytes of counters + chunk tags + pool for `pairs` pairs per pass
