@@ -39,7 +39,7 @@ UNIT = "pairs/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch and the utilisation of the resource that binds each kernel,
 # from the committed `ncu --set full` capture of this pipeline (profiles/r1d_kernels_ncu.md), N=4096 dense
 TRAFFIC_NCU = {"encode_sample": 3.378432e6 + 348.861184e6, "vote": 67.368704e6 + 0.92416e6,
-               "backvote": 67.202816e6 + 3.360256e6, "stats": 402.321152e6 + 3.837952e6}
+               "backvote": 67.202816e6 + 3.360256e6, "stats": 285.0e6 + 3.8e6}
 BINDING_NCU = {"encode_sample": {"issue_slots_busy": 0.473, "tensor_pipe_active": 0.326, "warps_per_sm": 16},
                "vote": {"shared_memory_wavefronts_of_peak": 0.729, "issue_slots_busy": 0.749,
                         "wavefronts_per_ATOMS": 4.02},
@@ -108,17 +108,21 @@ class ClockSampler:
         rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
         sm, mx, reasons, all_sm = [], [], set(), []
+        parsed = []
         for r in rows:
             try:
                 ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                c, m = float(r[1]), float(r[2])
+                parsed.append((ts, float(r[1]), float(r[2]), r[5:9]))
             except Exception:
                 continue
-            all_sm.append(c)
-            if t0 is not None and not (t0 <= ts <= t1):
-                continue
+        inside = [q for q in parsed if t0 is None or t0 <= q[0] <= t1]
+        if len(inside) < 2:                          # polling too coarse for the window: take the samples nearest to it
+            mid = 0.5 * ((t0 or 0) + (t1 or 0))
+            inside = sorted(parsed, key=lambda q: abs(q[0] - mid))[:4]
+        all_sm = [q[1] for q in parsed]
+        for ts, c, m, cells in inside:
             sm.append(c); mx.append(m)
-            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), cells):
                 if "Active" in cell and "Not" not in cell:
                     reasons.add(name)
         if sm:
@@ -237,6 +241,8 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
+    # nvidia-smi needs up to a second to deliver its first sample on a fresh box: start it before the inputs are built
+    sampler = ClockSampler(local) if rank == 0 else None
     torch.manual_seed(0)
     pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(dev).eval()
     ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).to(dev).eval()
@@ -272,7 +278,6 @@ def main():
         The fused path enqueues every step with ONE library call (cppf_pose_fused) and never waits for the GPU
         inside the loop: the records come back through pinned buffers and are read after the last enqueue."""
         records = []
-        sampler = ClockSampler(local) if rank == 0 else None
         resident = [(p.to(dev), q.to(dev)) for p, q in pinned] if leg == "hbm" else None
         timers = {}
         if args.path == "fused":
@@ -307,7 +312,7 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop(t0, time.time()) if sampler else None
+        clocks = (t0, time.time())           # window of this leg; the samples are filtered when the sampler stops
         launches = _lib.launch_count() - l0
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if dist_on:
@@ -327,7 +332,8 @@ def main():
                     stage_ms[name] = {"avg_ms": sum(durs) / len(durs), "launches": len(durs)}
         return float(t.item()), launches, clocks, stage_ms
 
-    ms_hbm, launches, clocks, timers = run("hbm")
+    ms_hbm, launches, window, timers = run("hbm")
+    clocks = sampler.stop(*window) if sampler else None
     ms_e2e, _, _, _ = run("e2e")
     ms_net = None
     if args.votes == "trained_like" and args.path == "fused":
