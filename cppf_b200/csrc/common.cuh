@@ -65,8 +65,14 @@ struct Geom {
 template <bool IDX64>
 __device__ __forceinline__ void pair_ab(const void* __restrict__ idx, int64_t p, int n_points, int& a, int& b) {
     if (idx == nullptr) {
-        a = (int)(p / n_points);
-        b = (int)(p - (int64_t)a * n_points);
+        if (((uint64_t)p >> 32) == 0) {                 // N < 65 536: a 32-bit divide is a third of the 64-bit one
+            const uint32_t q = (uint32_t)p / (uint32_t)n_points;
+            a = (int)q;
+            b = (int)((uint32_t)p - q * (uint32_t)n_points);
+        } else {
+            a = (int)(p / n_points);
+            b = (int)(p - (int64_t)a * n_points);
+        }
     } else if (IDX64) {
         const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(idx) + p);
         a = (int)v.x;
