@@ -48,6 +48,8 @@ constexpr int kVoteThreads = 1024;
 constexpr int kVoteBatch = 2 * kVoteThreads;       // pairs sorted and voted between two block barriers
 constexpr int kVoteQueue = 64;                     // per-warp ring of in-bounds candidates (float4 slots)
 constexpr int kVoteKeys = kMaxRotsP + 1;           // sort key = rotation count of the pair (0..72)
+constexpr int kTileA = 128, kTileB = 16;           // dense mode: a batch is a kTileA x kTileB tile of the pair matrix
+static_assert(kTileA * kTileB == kVoteBatch, "tile = batch");
 // Overflow guard: after every batch each cell holding >= 2^30 units is flushed to the global u64 accumulator.
 // A batch adds at most kVoteBatch * 72 candidates * 2^14 units = 2.42e9 < 2^32 - 2^30 to any one cell.
 constexpr unsigned kFlushAt = 1u << 30;
@@ -133,17 +135,31 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     unsigned* s_lane = s_grid + (lane & 1) * rep;
     const unsigned q_addr = (unsigned)__cvta_generic_to_shared(s_queue + (threadIdx.x >> 5) * kVoteQueue);
     const float cx = __ldg(corner), cy = __ldg(corner + 1), cz = __ldg(corner + 2);
-    const long long n_batches = (prm.n_pairs + kVoteBatch - 1) / kVoteBatch;
+    // A batch is 2048 consecutive entries of the pair list, or -- dense mode -- a 128 x 16 tile of the pair matrix
+    // (128 different points a): pairs that share a reach the vote peak in the same iterations, and mixing the a's of a
+    // batch takes another 9 % off the same-cell replays of the splat (tools/sim_vote_banks.py: 4.0 -> 3.65 per ATOMS).
+    const bool tiled = prm.idx == nullptr;
+    const int tiles_x = (prm.n_points + kTileB - 1) / kTileB;
+    const long long n_batches = tiled ? (long long)((prm.n_points + kTileA - 1) / kTileA) * tiles_x
+                                      : (prm.n_pairs + kVoteBatch - 1) / kVoteBatch;
+    auto pair_index = [&](long long batch, int local) -> long long {      // -1: no such pair
+        if (!tiled) {
+            const long long q = batch * kVoteBatch + local;
+            return q < prm.n_pairs ? q : -1;
+        }
+        const int tr = (int)(batch / tiles_x), tc = (int)(batch - (long long)tr * tiles_x);
+        const int a = tr * kTileA + (local / kTileB), b = tc * kTileB + (local % kTileB);
+        return (a < prm.n_points && b < prm.n_points) ? (long long)a * prm.n_points + b : -1;
+    };
 
     for (long long batch = part; batch < n_batches; batch += parts) {
-        const long long base = batch * kVoteBatch;
         // ---- (1a) keys + ranks: n of each of this thread's two pairs
         int key[2], rank[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const long long p = base + threadIdx.x + j * kVoteThreads;
+            const long long p = pair_index(batch, threadIdx.x + j * kVoteThreads);
             key[j] = -1;
-            if (p < prm.n_pairs) {
+            if (p >= 0) {
                 int n;
                 if (BINS) {
                     n = s_nlut[__ldg(prm.bins + 4 * p + 1) & 31];
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
             int n = 0;
             f3 c = {0.f, 0.f, 0.f}, x = c, y = c;
             if (item < total) {
-                const long long p = base + s_perm[item];
+                const long long p = pair_index(batch, s_perm[item]);
                 int ia, ib;
                 pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
                 float mu, nu;
