@@ -33,6 +33,8 @@ constexpr int kRouteWarps = 32;
 constexpr int kRouteThreads = kRouteWarps * 32;
 constexpr int kRouteBatch = 2 * kRouteThreads;       // pairs sorted between two block barriers
 constexpr int kRouteKeys = kMaxRotsP + 1;
+constexpr int kRTileA = 128, kRTileB = 16;           // dense mode: kRTileA * kRTileB == kRouteBatch
+static_assert(kRTileA * kRTileB == kRouteBatch, "tile = batch");
 constexpr int kStage = 64;                           // per-warp ring of in-bounds candidates (float4 slots)
 
 struct RouteCounters {
@@ -56,7 +58,8 @@ struct RouteParams {
     float lo, hx, hy, hz;            // exact bounds on g (models/voting.py:36-39)
     float dlo, dhx, dhy, dhz;        // conservative bounds on candidate - corner
     int n_points;
-    long long pair_begin, pair_end;  // this super-batch
+    long long batch_begin, batch_end;  // this pass, in 2048-pair batches (dense mode: 128 x 16 tiles of the pair matrix)
+    long long n_pairs;
     int n_rots, adaptive;
     int gx, planes_per_slab, n_slabs;
     unsigned max_chunks;
@@ -171,15 +174,26 @@ __global__ void __launch_bounds__(kRouteThreads, 1) route_kernel(const RoutePara
         }
     };
 
-    const long long n_batches = (prm.pair_end - prm.pair_begin + kRouteBatch - 1) / kRouteBatch;
-    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-        const long long base = prm.pair_begin + batch * kRouteBatch;
+    // a batch: 2048 consecutive entries of the pair list, or -- dense mode -- a 128 x 16 tile of the pair matrix, like
+    // vote_private_kernel (mixing the points a of a batch decorrelates the lanes' candidates)
+    const bool tiled = prm.idx == nullptr;
+    const int tiles_x = (prm.n_points + kRTileB - 1) / kRTileB;
+    auto pair_index = [&](long long batch, int local) -> long long {      // -1: no such pair
+        if (!tiled) {
+            const long long q = batch * kRouteBatch + local;
+            return q < prm.n_pairs ? q : -1;
+        }
+        const int tr = (int)(batch / tiles_x), tc = (int)(batch - (long long)tr * tiles_x);
+        const int a = tr * kRTileA + (local / kRTileB), b = tc * kRTileB + (local % kRTileB);
+        return (a < prm.n_points && b < prm.n_points) ? (long long)a * prm.n_points + b : -1;
+    };
+    for (long long batch = prm.batch_begin + blockIdx.x; batch < prm.batch_end; batch += gridDim.x) {
         int key[2], rank[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const long long p = base + threadIdx.x + j * kRouteThreads;
+            const long long p = pair_index(batch, threadIdx.x + j * kRouteThreads);
             key[j] = -1;
-            if (p < prm.pair_end) {
+            if (p >= 0) {
                 int n;
                 if (BINS) {
                     n = s_nlut[__ldg(prm.bins + 4 * p + 1) & 31];
@@ -239,7 +253,7 @@ __global__ void __launch_bounds__(kRouteThreads, 1) route_kernel(const RoutePara
             int n = 0;
             f3 c = {0.f, 0.f, 0.f}, x = c, y = c;
             if (item < total) {
-                const long long p = base + s_perm[item];
+                const long long p = pair_index(batch, s_perm[item]);
                 int ia, ib;
                 pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
                 float mu, nu;
@@ -500,14 +514,18 @@ int vote_routed_launch(const float* points, const float* mu_nu, const uint8_t* b
     const long long slab_cells = geom ? slab_cap_cells() : (long long)(pl.planes_per_slab + 1) * gy * gz;
     const size_t ssmem = (size_t)slab_cells * 4;
     CPPF_RETURN_IF(cudaFuncSetAttribute(slab_splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-    for (int64_t p0 = 0; p0 < n_pairs; p0 += batch_pairs) {
-        const int64_t p1 = p0 + batch_pairs < n_pairs ? p0 + batch_pairs : n_pairs;
+    const int64_t total_batches = idx == nullptr
+                                      ? (int64_t)((n_points + kRTileA - 1) / kRTileA) * ((n_points + kRTileB - 1) / kRTileB)
+                                      : (n_pairs + kRouteBatch - 1) / kRouteBatch;
+    const int64_t pass_batches = batch_pairs / kRouteBatch;
+    for (int64_t p0 = 0; p0 < total_batches; p0 += pass_batches) {
+        const int64_t p1 = p0 + pass_batches < total_batches ? p0 + pass_batches : total_batches;
         CPPF_RETURN_IF(cudaMemsetAsync(counters, 0, sizeof(RouteCounters), stream));
         RouteParams rp{rot_tab, points, mu_nu, bins, lut, idx, corner, pool, chunk_slab, counters, res,
                        (float)(1.0 / (double)res), lo, hx, hy, hz, dlo, dhx, dhy, dhz, n_points,
-                       (long long)p0, (long long)p1, n_rots, adaptive, gx, pl.planes_per_slab, pl.n_slabs,
+                       (long long)p0, (long long)p1, (long long)n_pairs, n_rots, adaptive, gx, pl.planes_per_slab, pl.n_slabs,
                        (unsigned)max_chunks, geom};
-        long long blocks = (p1 - p0 + kRouteBatch - 1) / kRouteBatch;
+        long long blocks = p1 - p0;
         if (blocks > sm_count()) blocks = sm_count();
         route<<<(int)blocks, kRouteThreads, rsmem, stream>>>(rp);
         CPPF_LAUNCH_CHECK();
