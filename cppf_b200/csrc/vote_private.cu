@@ -693,6 +693,7 @@ struct StatsParams {
     double* out;                 // [6]
     int n_points;
     long long n_pairs;
+    int vec4;                    // dense pairs through the mask with 16-byte aligned buffers and n_points % 4 == 0
 };
 
 template <bool IDX64>
@@ -709,6 +710,44 @@ __global__ void __launch_bounds__(256) survivor_stats_kernel(const StatsParams p
     // cross-thread reduction; 4 survivors in flight per thread hide the pos -> tail gather latency
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const long long stride = (long long)gridDim.x * blockDim.x;
+    // one survivor: nocs/inference.py:286-302 (flip the normal towards ab, sign of its component along the best axis)
+    auto add_pair = [&](f3 a, f3 b, f3 n, float aux_u, float aux_r, float s0, float s1, float s2) {
+        const f3 ab = a - b;
+        const float inv = sqrtf(dot3(ab, ab)) + 1e-7f;                         // :288-289 (float32 numpy)
+        const f3 abn = {ab.x / inv, ab.y / inv, ab.z / inv};
+        if (dot3(n, abn) < 0.f) n = {-n.x, -n.y, -n.z};                        // :291-292
+        acc[0] += s0; acc[1] += s1; acc[2] += s2;
+        acc[3] += 1.f;
+        acc[4] += aux_u * (dot3(n, du) > 0.f ? 1.f : -1.f);                    // :295
+        if (prm.best_right) acc[5] += aux_r * (dot3(n, dr) > 0.f ? 1.f : -1.f);
+    };
+    if (prm.vec4) {
+        // dense pairs addressed through the mask: 4 consecutive pairs per thread (same point a, 4 consecutive points b) so
+        // that the mask, the five tail planes and the b coordinates arrive as 32-bit / 128-bit loads
+        const long long n4 = prm.n_pairs >> 2;
+        const float* t0 = prm.tail; const float* t1 = prm.tail + prm.n_pairs;
+        const float* t2 = prm.tail + 2 * prm.n_pairs; const float* t3 = prm.tail + 3 * prm.n_pairs;
+        const float* t4 = prm.tail + 4 * prm.n_pairs;
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+            const unsigned m4 = __ldg(reinterpret_cast<const unsigned*>(prm.mask) + q);
+            if (m4 == 0u) continue;
+            const long long p0 = q << 2;
+            int ia, ib;
+            pair_ab<IDX64>(nullptr, p0, prm.n_points, ia, ib);
+            const f3 a = ld3(prm.points, ia), n = ld3(prm.nrm, ia);
+            const float4* pb = reinterpret_cast<const float4*>(prm.points + 3 * (long long)ib);       // ib % 4 == 0: 16-byte aligned
+            const float4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+            const float4 au = __ldg(reinterpret_cast<const float4*>(t0 + p0));
+            float4 ar = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (prm.best_right) ar = __ldg(reinterpret_cast<const float4*>(t1 + p0));
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(t2 + p0)), s1 = __ldg(reinterpret_cast<const float4*>(t3 + p0)),
+                         s2 = __ldg(reinterpret_cast<const float4*>(t4 + p0));
+            if (m4 & 0x000000ffu) add_pair(a, f3{b0.x, b0.y, b0.z}, n, au.x, ar.x, s0.x, s1.x, s2.x);
+            if (m4 & 0x0000ff00u) add_pair(a, f3{b0.w, b1.x, b1.y}, n, au.y, ar.y, s0.y, s1.y, s2.y);
+            if (m4 & 0x00ff0000u) add_pair(a, f3{b1.z, b1.w, b2.x}, n, au.z, ar.z, s0.z, s1.z, s2.z);
+            if (m4 & 0xff000000u) add_pair(a, f3{b2.y, b2.z, b2.w}, n, au.w, ar.w, s0.w, s1.w, s2.w);
+        }
+    } else
     for (long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; j0 < count; j0 += 4 * stride) {
         long long p[4];
 #pragma unroll
@@ -937,9 +976,11 @@ int survivor_stats_launch(const float* points, const float* nrm, const float* ta
                           cudaStream_t stream) {
     if (pos == nullptr && mask == nullptr) return (int)cudaErrorInvalidValue;
     CPPF_RETURN_IF(cudaMemsetAsync(out, 0, 6 * sizeof(double), stream));
+    const bool aligned = (((uintptr_t)points | (uintptr_t)tail | (uintptr_t)mask) & 15u) == 0;
+    const int vec4 = (pos == nullptr && idx == nullptr && (n_points & 3) == 0 && aligned) ? 1 : 0;
     StatsParams prm{points, nrm, tail, idx, reinterpret_cast<const long long*>(pos), mask,
                     reinterpret_cast<const long long*>(count), sphere, reinterpret_cast<const long long*>(best_up),
-                    reinterpret_cast<const long long*>(best_right), out, n_points, (long long)n_pairs};
+                    reinterpret_cast<const long long*>(best_right), out, n_points, (long long)n_pairs, vec4};
     const int blocks = sm_count() * 8;
     if (idx_is_64) survivor_stats_kernel<true><<<blocks, 256, 0, stream>>>(prm);
     else survivor_stats_kernel<false><<<blocks, 256, 0, stream>>>(prm);
