@@ -367,6 +367,10 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
     const float tx = (float)((double)cx + (double)ix * (double)prm.res);
     const float ty = (float)((double)cy + (double)iy * (double)prm.res);
     const float tz = (float)((double)cz + (double)iz * (double)prm.res);
+    // is the tolerance ball around the winning cell at least one cell away from every face of the grid?
+    const int gxi = prm.geom != nullptr ? prm.geom->gx : prm.gx;
+    const int marg = (int)(prm.tol * prm.inv_res) + 2;
+    const bool interior = ix >= marg && iy >= marg && iz >= marg && ix < gxi - 1 - marg && iy < gy - 1 - marg && iz < gz - 1 - marg;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < prm.n_pairs;
          p += (long long)gridDim.x * blockDim.x) {
         int ia, ib;
@@ -394,10 +398,13 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
             const f3 v = {tx - c.x, ty - c.y, tz - c.z};
             const f3 ey = cross3(ex, ab);
             const float dpl = dot3(v, ab), px = dot3(v, ex), py = dot3(v, ey);
-            const float vv = dpl * dpl + px * px + py * py;
+            const float vv = dot3(v, v);
             const float tol2 = prm.tol * prm.tol;
             const float kq = 0.5f * (nu * nu + vv - tol2) - (0.02f * tol2 + 1e-6f * (nu * nu + vv));   // K minus rounding slack
-            if (n > 12) {
+            // the shortcuts below assume |ex| = |ey| = 1; the reference's `+ 1e-7` normaliser shrinks ex when ab is within
+            // ~1e-3 rad of the x axis -- such pairs take the plain scan with the reference's arithmetic only
+            const bool unit_frame = dot3(ex, ex) > 0.9999f;
+            if (n > 12 && unit_frame) {
                 const float rho = sqrtf(px * px + py * py);
                 const float room = tol2 * 1.01f + 1e-12f - dpl * dpl - (nu - rho) * (nu - rho);   // >= 2 nu rho (1 - cos d) for a hit
                 const float two_nr = 2.f * fabsf(nu) * rho;
@@ -430,7 +437,16 @@ __global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParam
                 i = i < 0 ? i + n : (i >= n ? i - n : i);
                 i = i < 0 ? i + n : (i >= n ? i - n : i);
                 const float2 cs = tab[i];
-                if (nu * fmaf(px, cs.x, py * cs.y) < kq) continue;              // cannot be within tol (see above)
+                if (unit_frame) {
+                    const float qv = nu * fmaf(px, cs.x, py * cs.y);
+                    if (qv < kq) continue;                                     // cannot be within tol (see above)
+                    // well inside the tolerance ball of an interior centre: in bounds by construction, offset of length
+                    // |nu| != 0 -- the reference's tests (:102-109) hold with a 10 % margin, no need to evaluate them
+                    if (interior && nu != 0.f && fmaf(-2.f, qv, nu * nu + vv) <= 0.9f * tol2) {
+                        hit = true;
+                        break;
+                    }
+                }
                 const f3 off = x * cs.x + y * cs.y;
                 const f3 pc = c + off;
                 const f3 dlt = {pc.x - tx, pc.y - ty, pc.z - tz};
