@@ -170,6 +170,9 @@ def cpu_reference_step(pc, nrm, sd_pe, sd_ppf, idxs, cfg, sphere, seed):
 
 
 def run_cpu_reference(args, steps, warmup, sample_pairs):
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core, both in torch and in
+    # the OpenMP voting library (which reads the variable when it is first loaded)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from cppf_b200 import model, synth
     from oracle import ref_model
     torch.set_num_threads(os.cpu_count() or 1)
