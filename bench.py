@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 METRIC = "point_pairs_per_sec"
 UNIT = "pairs/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch and the utilisation of the resource that binds each kernel,
-# from the committed `ncu --set full` capture of this pipeline (profiles/r1d_kernels_ncu.md), N=4096 dense
+# from the committed `ncu --set full` capture of this pipeline (profiles/r1e_kernels_ncu.md), N=4096 dense
 TRAFFIC_NCU = {"encode_sample": 3.378432e6 + 348.861184e6, "vote": 67.368704e6 + 0.92416e6,
                "backvote": 67.202816e6 + 3.360256e6, "stats": 285.0e6 + 3.8e6}
 BINDING_NCU = {"encode_sample": {"issue_slots_busy": 0.473, "tensor_pipe_active": 0.326, "warps_per_sm": 16},
@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--n-points", type=int, default=4096)
     ap.add_argument("--cpu-sample-pairs", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra legs (network votes, 100k sampled pairs): "
+                                                                "for runs under a profiler")
     ap.add_argument("--votes", default="trained_like", choices=["trained_like", "network"],
                     help="trained_like: after sampling, the (mu,nu,up) bins are replaced by the geometric targets a trained "
                          "network would emit (SURVEY.md 8d i) so that voting runs under a realistic load; network: votes "
@@ -339,10 +341,10 @@ def main():
     clocks = sampler.stop(*window) if sampler else None
     ms_e2e, _, _, _ = run("e2e")
     ms_net = None
-    if args.votes == "trained_like" and args.path == "fused":
+    if args.votes == "trained_like" and args.path == "fused" and not args.no_variants:
         ms_net, _, _, _ = run("hbm", votes_injected=False)
     sampled = None
-    if args.path == "fused":
+    if args.path == "fused" and not args.no_variants:
         # the reference's own inference regime (nocs/inference.py:177): 100 000 random pairs per object, from pinned host
         # clouds; one cppf_pose_fused call per object, all objects of the run enqueued back to back.  The kernels of one
         # such object are short (0.5 ms in ~25 launches), so objects are also dealt round-robin to a few CUDA streams.
