@@ -41,9 +41,9 @@ UNIT = "pairs/s"
 TRAFFIC_NCU = {"encode_sample": 3.378432e6 + 348.861184e6, "vote": 67.368704e6 + 0.92416e6,
                "backvote": 67.202816e6 + 3.360256e6, "stats": 285.0e6 + 3.8e6}
 BINDING_NCU = {"encode_sample": {"issue_slots_busy": 0.473, "tensor_pipe_active": 0.326, "warps_per_sm": 16},
-               "vote": {"shared_memory_wavefronts_of_peak": 0.729, "issue_slots_busy": 0.749,
-                        "wavefronts_per_ATOMS": 4.02},
-               "backvote": {"issue_slots_busy": 0.799}, "stats": {"dram_read_tbs": 2.89}}
+               "vote": {"shared_memory_wavefronts_of_peak": 0.722, "issue_slots_busy": 0.795,
+                        "wavefronts_per_ATOMS": 3.64},
+               "backvote": {"issue_slots_busy": 0.778}, "stats": {"dram_read_tbs": 2.86}}
 
 
 def parse():
@@ -414,7 +414,7 @@ def main():
         algo_flops = {"encode_sample": pairs_per_obj * 23968.0, "ppf_encode_pass1": pairs_per_obj * (23968.0 - 2 * 16 * 77)}
         binding = {"encode_sample": "tensor pipe issue + MMA round-trip latency (tcgen05 3xTF32 chain)" if args.encoder == "tc"
                                     else "fp32 FMA pipe",
-                   "vote": "shared-memory pipe (73 % of peak wavefronts; 4.0 bank/same-cell replays per ATOMS)",
+                   "vote": "shared-memory pipe (72 % of peak wavefronts, 3.6 bank/same-cell replays per ATOMS) and issue slots (79 %)",
                    "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput", "stats": "HBM gather (2.9 TB/s)",
                    "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "torch ops (cdist/topk/LayerNorm), launch-bound"}
         detail = {}
