@@ -60,15 +60,18 @@ constexpr int kOffWs1 = kOffWp + 2 * 96 * 8;      // N = 64,  K = 32
 constexpr int kOffWs2 = kOffWs1 + 2 * 64 * 32;    // N = 32,  K = 32
 constexpr int kOffWh = kOffWs2 + 2 * 32 * 32;     // N = 112, K = 32: mu 32 | nu 32 | up 36 | tail 5 | 0 x 7
 constexpr int kOffWr = kOffWh + 2 * 112 * 32;     // N = 48,  K = 32: right 36 | 0 x 12
-constexpr int kOffBias = kOffWr + 2 * 48 * 32;    // bh 112 | br 48 | pad -> 256
-constexpr int kSmemFloats = kOffBias + 256;
+// head biases as MMA operands: B[N x 8] with the bias in k = 0 (hi block then lo block); the A side is a constant
+// "ones" operand (k = 0 of every row = 1), so D = 1 . bias^T initialises the accumulators of the head step
+constexpr int kOffBh = kOffWr + 2 * 48 * 32;      // N = 112, K = 8
+constexpr int kOffBr = kOffBh + 2 * 112 * 8;      // N = 48,  K = 8
+constexpr int kSmemFloats = kOffBr + 2 * 48 * 8;
 constexpr int kBlobFloats = kOffSmem + kSmemFloats;
-constexpr int kBiasH = 0, kBiasR = 112;
 
 constexpr int kAPlane = kTile * 16;               // bytes of one K plane of an A operand
 constexpr int kABytes = 8 * kAPlane;              // K = 32
 constexpr int kGroupBytes = 2 * kABytes;          // hi + lo
-constexpr int kSmemBytes = kSmemFloats * 4 + kGroups * kGroupBytes;
+constexpr int kOnesBytes = 2 * kAPlane;            // the shared ones operand: K = 8 (two planes), hi only (lo == 0)
+constexpr int kSmemBytes = kSmemFloats * 4 + kOnesBytes + kGroups * kGroupBytes;
 constexpr int kTmemColsPerGroup = 128;
 
 struct Params {
@@ -119,6 +122,15 @@ __device__ __forceinline__ void issue3(uint32_t tmem_d, uint32_t a_hi, uint32_t 
             mma_tf32(tmem_d, kdesc(a + j * 2 * kAPlane, kAPlane), kdesc(b + j * 2 * bplane, bplane), idesc,
                      (ACC_INIT || (ps | j) != 0) ? 1u : 0u);
     }
+}
+
+// D[128 x N] = ones[128 x 8] . Bias[N x 8]^T: every row of D becomes the bias vector (hi + lo, exact: the A side is 1.0)
+template <int N>
+__device__ __forceinline__ void issue_bias(uint32_t tmem_d, uint32_t ones, uint32_t b_hi) {
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+    constexpr uint32_t bplane = N * 16;
+    mma_tf32(tmem_d, kdesc(ones, kAPlane), kdesc(b_hi, bplane), idesc, 0u);
+    mma_tf32(tmem_d, kdesc(ones, kAPlane), kdesc(b_hi + N * 8 * 4, bplane), idesc, 1u);
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -252,12 +264,15 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     float* sblob = reinterpret_cast<float*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int g = tid >> 7, tg = tid & 127;             // group, row within the tile
-    unsigned char* a_hi = smem + kSmemFloats * 4 + g * kGroupBytes;
+    unsigned char* s_ones = smem + kSmemFloats * 4;
+    unsigned char* a_hi = s_ones + kOnesBytes + g * kGroupBytes;
 
     {   // weights -> shared memory (one copy per CTA), TMEM allocation, barriers
         const float4* src = reinterpret_cast<const float4*>(prm.blob + kOffSmem);
         float4* dst = reinterpret_cast<float4*>(sblob);
         for (int i = tid; i < kSmemFloats / 4; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < kOnesBytes / 16; i += kThreads)          // plane 0: (1, 0, 0, 0) per row; plane 1: zeros
+            reinterpret_cast<float4*>(s_ones)[i] = make_float4(i < kTile ? 1.f : 0.f, 0.f, 0.f, 0.f);
         if (warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                          "r"(kGroups * kTmemColsPerGroup)
@@ -276,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     const uint32_t bar = smem_u32(&s_bar[g]);
     const uint32_t sA = smem_u32(a_hi), sAl = sA + kABytes;
     const uint32_t sW = smem_u32(sblob);
-    const float4* sbias = reinterpret_cast<const float4*>(sblob + kOffBias);
+    const uint32_t sOnes = smem_u32(s_ones);
     const bool leader = tg == 0;
     uint32_t phase = 0;
 
@@ -375,32 +390,17 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
         for (int q = 4; q < 8; ++q)           // r2 = t[16:32]        (k 16..31)
             st_chunk(a_hi, q, tg, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
         // ---- step 3: `final` o fc2_2 on [u2 ; r2] (models/model.py:31,137): mu | nu | up | tail -> columns 0:112
-        CPPF_TC_STEP((issue3<112, 32>(tm, sA, sAl, sW + kOffWh * 4)));
+        CPPF_TC_STEP((issue_bias<112>(tm, sOnes, sW + kOffBh * 4), issue3<112, 32, true>(tm, sA, sAl, sW + kOffWh * 4)));
         uchar4 bins = make_uchar4(0, 0, 0, 0);
         if (prm.heads & 1) {
-            tmem_ld32(tml, x);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 bq = sbias[kBiasH / 4 + q];
-                x[4 * q] += bq.x; x[4 * q + 1] += bq.y; x[4 * q + 2] += bq.z; x[4 * q + 3] += bq.w;
-            }
+            tmem_ld32(tml, x);                 // the biases are already in the accumulators (issue_bias)
             bins.x = (unsigned char)sample_regs<32>(x, u4.x);
             tmem_ld32(tml + 32, x);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 bq = sbias[kBiasH / 4 + 8 + q];
-                x[4 * q] += bq.x; x[4 * q + 1] += bq.y; x[4 * q + 2] += bq.z; x[4 * q + 3] += bq.w;
-            }
             bins.y = (unsigned char)sample_regs<32>(x, u4.y);
         }
         if (prm.heads & (2 | 8)) {
             float y[16];                       // columns 96..111: up bins 32..35, tail 0..4, padding
             tmem_ld16(tml + 96, y);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 bq = sbias[kBiasH / 4 + 24 + q];
-                y[4 * q] += bq.x; y[4 * q + 1] += bq.y; y[4 * q + 2] += bq.z; y[4 * q + 3] += bq.w;
-            }
             if ((prm.heads & 8) && valid) {
 #pragma unroll
                 for (int k = 0; k < 5; ++k) prm.tail[(long long)k * prm.n_pairs + p] = y[4 + k];
@@ -411,32 +411,23 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
                     float z[32];
                     tmem_ld32(tml + 64, z);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 bq = sbias[kBiasH / 4 + 16 + q];
-                        l[4 * q] = z[4 * q] + bq.x; l[4 * q + 1] = z[4 * q + 1] + bq.y;
-                        l[4 * q + 2] = z[4 * q + 2] + bq.z; l[4 * q + 3] = z[4 * q + 3] + bq.w;
-                    }
+                    for (int q = 0; q < 32; ++q) l[q] = z[q];
                 }
                 l[32] = y[0]; l[33] = y[1]; l[34] = y[2]; l[35] = y[3];
                 bins.z = (unsigned char)sample_regs<36>(l, u4.z);
             }
         }
         if (prm.heads & 4) {                   // right head: one more MMA into columns 0:48 (mu/nu already consumed)
-            CPPF_TC_STEP((issue3<48, 32>(tm, sA, sAl, sW + kOffWr * 4)));
+            CPPF_TC_STEP((issue_bias<48>(tm, sOnes, sW + kOffBr * 4), issue3<48, 32, true>(tm, sA, sAl, sW + kOffWr * 4)));
             float l[36];
             {
                 float z[32];
                 tmem_ld32(tml, z);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 bq = sbias[kBiasR / 4 + q];
-                    l[4 * q] = z[4 * q] + bq.x; l[4 * q + 1] = z[4 * q + 1] + bq.y;
-                    l[4 * q + 2] = z[4 * q + 2] + bq.z; l[4 * q + 3] = z[4 * q + 3] + bq.w;
-                }
+                for (int q = 0; q < 32; ++q) l[q] = z[q];
                 float y[16];
                 tmem_ld16(tml + 32, y);
-                const float4 bq = sbias[kBiasR / 4 + 8];
-                l[32] = y[0] + bq.x; l[33] = y[1] + bq.y; l[34] = y[2] + bq.z; l[35] = y[3] + bq.w;
+                l[32] = y[0]; l[33] = y[1]; l[34] = y[2]; l[35] = y[3];
             }
             bins.w = (unsigned char)sample_regs<36>(l, u4.w);
         }

@@ -168,11 +168,14 @@ def pack_tc_weights(sd) -> np.ndarray:
     parts += _canon_hi_lo(f32(W10_2 @ W2_1), 32, 32)                  # Ws2
     parts += _canon_hi_lo(f32(WH), 112, 32)
     parts += _canon_hi_lo(f32(WR), 48, 32)
-    bias = np.zeros(256, np.float32)
-    bias[0:r_rt] = f32(bf[:r_rt] * LOG2E)
-    bias[r_rt:r_rt + 5] = f32(bf[r_tail:])
-    bias[112:112 + ROT_BINS] = f32(bf[r_rt:r_tail] * LOG2E)
-    parts.append(bias)
+    # head biases as K = 8 MMA operands (bias in k = 0), multiplied by a constant ones operand in the kernel
+    bh = np.zeros((112, 8))
+    bh[0:r_rt, 0] = bf[:r_rt] * LOG2E
+    bh[r_rt:r_rt + 5, 0] = bf[r_tail:]
+    br_ = np.zeros((48, 8))
+    br_[0:ROT_BINS, 0] = bf[r_rt:r_tail] * LOG2E
+    parts += _canon_hi_lo(f32(bh), 112, 8)
+    parts += _canon_hi_lo(f32(br_), 48, 8)
     blob = np.concatenate([np.ascontiguousarray(q, dtype=np.float32).reshape(-1) for q in parts])
     assert blob.size == _lib.lib().cppf_tc_blob_floats(), blob.size
     return blob
