@@ -60,18 +60,20 @@ constexpr int kOffWs1 = kOffWp + 2 * 96 * 8;      // N = 64,  K = 32
 constexpr int kOffWs2 = kOffWs1 + 2 * 64 * 32;    // N = 32,  K = 32
 constexpr int kOffWh = kOffWs2 + 2 * 32 * 32;     // N = 112, K = 32: mu 32 | nu 32 | up 36 | tail 5 | 0 x 7
 constexpr int kOffWr = kOffWh + 2 * 112 * 32;     // N = 48,  K = 32: right 36 | 0 x 12
-// head biases as MMA operands: B[N x 8] with the bias in k = 0 (hi block then lo block); the A side is a constant
-// "ones" operand (k = 0 of every row = 1), so D = 1 . bias^T initialises the accumulators of the head step
+// Row-constant addends as MMA operands: B[N x 8] holds the hi part of a vector v in k = 0 and its lo part in k = 4; the A
+// side is a constant "ones" operand (k = 0 and k = 4 of every row = 1), so ONE MMA D = ones . B^T puts v (exact, hi + lo)
+// into every row of the accumulators.  Used for the head biases and, in dense mode, for the a-side table row of a tile.
 constexpr int kOffBh = kOffWr + 2 * 48 * 32;      // N = 112, K = 8
-constexpr int kOffBr = kOffBh + 2 * 112 * 8;      // N = 48,  K = 8
-constexpr int kSmemFloats = kOffBr + 2 * 48 * 8;
+constexpr int kOffBr = kOffBh + 112 * 8;          // N = 48,  K = 8
+constexpr int kSmemFloats = kOffBr + 48 * 8;
 constexpr int kBlobFloats = kOffSmem + kSmemFloats;
 
 constexpr int kAPlane = kTile * 16;               // bytes of one K plane of an A operand
 constexpr int kABytes = 8 * kAPlane;              // K = 32
 constexpr int kGroupBytes = 2 * kABytes;          // hi + lo
-constexpr int kOnesBytes = 2 * kAPlane;            // the shared ones operand: K = 8 (two planes), hi only (lo == 0)
-constexpr int kSmemBytes = kSmemFloats * 4 + kOnesBytes + kGroups * kGroupBytes;
+constexpr int kOnesBytes = 2 * kAPlane;            // the shared ones operand: K = 8 (two planes)
+constexpr int kTaBytes = 2 * 96 * 16;              // per group: the a-side table row of the tile as a [96 x 8] B operand
+constexpr int kSmemBytes = kSmemFloats * 4 + kOnesBytes + kGroups * (kGroupBytes + kTaBytes);
 constexpr int kTmemColsPerGroup = 128;
 
 struct Params {
@@ -124,13 +126,11 @@ __device__ __forceinline__ void issue3(uint32_t tmem_d, uint32_t a_hi, uint32_t 
     }
 }
 
-// D[128 x N] = ones[128 x 8] . Bias[N x 8]^T: every row of D becomes the bias vector (hi + lo, exact: the A side is 1.0)
+// D[128 x N] = ones[128 x 8] . V[N x 8]^T: every row of D becomes the vector packed in V (k = 0: hi, k = 4: lo; exact)
 template <int N>
-__device__ __forceinline__ void issue_bias(uint32_t tmem_d, uint32_t ones, uint32_t b_hi) {
+__device__ __forceinline__ void issue_bias(uint32_t tmem_d, uint32_t ones, uint32_t v) {
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
-    constexpr uint32_t bplane = N * 16;
-    mma_tf32(tmem_d, kdesc(ones, kAPlane), kdesc(b_hi, bplane), idesc, 0u);
-    mma_tf32(tmem_d, kdesc(ones, kAPlane), kdesc(b_hi + N * 8 * 4, bplane), idesc, 1u);
+    mma_tf32(tmem_d, kdesc(ones, kAPlane), kdesc(v, N * 16), idesc, 0u);
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -256,7 +256,7 @@ __device__ __forceinline__ void ppf_of(f3 pa, f3 pb, f3 na, f3 nb, float (&ppf)[
     ppf[3] = dn;
 }
 
-template <bool IDX64>
+template <bool IDX64, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Params prm) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar[kGroups];
@@ -265,14 +265,17 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     const int tid = threadIdx.x, warp = tid >> 5;
     const int g = tid >> 7, tg = tid & 127;             // group, row within the tile
     unsigned char* s_ones = smem + kSmemFloats * 4;
-    unsigned char* a_hi = s_ones + kOnesBytes + g * kGroupBytes;
+    unsigned char* s_ta = s_ones + kOnesBytes + g * kTaBytes;                 // this group's a-side row operand (dense mode)
+    unsigned char* a_hi = s_ones + kOnesBytes + kGroups * kTaBytes + g * kGroupBytes;
 
     {   // weights -> shared memory (one copy per CTA), TMEM allocation, barriers
         const float4* src = reinterpret_cast<const float4*>(prm.blob + kOffSmem);
         float4* dst = reinterpret_cast<float4*>(sblob);
         for (int i = tid; i < kSmemFloats / 4; i += kThreads) dst[i] = __ldg(src + i);
-        for (int i = tid; i < kOnesBytes / 16; i += kThreads)          // plane 0: (1, 0, 0, 0) per row; plane 1: zeros
-            reinterpret_cast<float4*>(s_ones)[i] = make_float4(i < kTile ? 1.f : 0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < kOnesBytes / 16; i += kThreads)          // k = 0 and k = 4 of every row are 1
+            reinterpret_cast<float4*>(s_ones)[i] = make_float4(1.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < kGroups * kTaBytes / 16; i += kThreads)  // only k = 0 / k = 4 of these rows are ever rewritten
+            reinterpret_cast<float4*>(s_ones + kOnesBytes)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                          "r"(kGroups * kTmemColsPerGroup)
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     const uint32_t bar = smem_u32(&s_bar[g]);
     const uint32_t sA = smem_u32(a_hi), sAl = sA + kABytes;
     const uint32_t sW = smem_u32(sblob);
-    const uint32_t sOnes = smem_u32(s_ones);
+    const uint32_t sOnes = smem_u32(s_ones), sTa = smem_u32(s_ta);
     const bool leader = tg == 0;
     uint32_t phase = 0;
 
@@ -313,12 +316,25 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                     \
     } while (0)
 
-    const long long n_tiles = (prm.n_pairs + kTile - 1) / kTile;
+    // dense mode: a tile is 128 consecutive points b of ONE point a (ragged at the end of a row), so that the a-side table row
+    // is a row constant of the tile and enters through the ones-operand MMA instead of 96 FADDs per pair
+    const int tiles_per_row = (prm.n_points + kTile - 1) / kTile;
+    const long long n_tiles = DENSE ? (long long)prm.n_points * tiles_per_row : (prm.n_pairs + kTile - 1) / kTile;
     for (long long tile = (long long)blockIdx.x * kGroups + g; tile < n_tiles; tile += (long long)gridDim.x * kGroups) {
-        const long long p = tile * kTile + tg;
-        const bool valid = p < prm.n_pairs;
+        long long p;
+        bool valid;
         int a = 0, b = 0;
-        if (valid) pair_ab<IDX64>(prm.idx, p, prm.n_points, a, b);
+        if (DENSE) {
+            a = (int)(tile / tiles_per_row);
+            b = (int)(tile - (long long)a * tiles_per_row) * kTile + tg;
+            valid = b < prm.n_points;
+            p = (long long)a * prm.n_points + b;
+            if (!valid) b = 0;
+        } else {
+            p = tile * kTile + tg;
+            valid = p < prm.n_pairs;
+            if (valid) pair_ab<IDX64>(prm.idx, p, prm.n_points, a, b);
+        }
         float ppf[4];
         ppf_of(ld3(prm.pc, a), ld3(prm.pc, b), ld3(prm.nrm, a), ld3(prm.nrm, b), ppf);
         float4 u4;
@@ -340,43 +356,62 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
         // ---- step 0: ppf columns of v1 | q1 | q2 (K = 8, N = 96) -> h = relu(fc1_0(x))            models/model.py:27,29
         st_chunk(a_hi, 0, tg, ppf[0], ppf[1], ppf[2], ppf[3]);
         st_chunk(a_hi, 1, tg, 0.f, 0.f, 0.f, 0.f);
+        if (DENSE) {
+            if (tg < 24) {                     // rows 4 tg .. 4 tg + 3 of the [96 x 8] operand: k = 0 <- hi, k = 4 <- lo
+                const float4 v = __ldg(TA + tg * ts);
+                const float vs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            ta[q] = __ldg(TA + q * ts);
-            tb[q] = __ldg(TB + q * ts);
+                for (int j = 0; j < 4; ++j) {
+                    const float h = tf32_hi(vs[j]);
+                    *reinterpret_cast<float*>(s_ta + (4 * tg + j) * 16) = h;
+                    *reinterpret_cast<float*>(s_ta + 96 * 16 + (4 * tg + j) * 16) = vs[j] - h;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                ta[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tb[q] = __ldg(TB + q * ts);
+            }
+            CPPF_TC_STEP((issue_bias<96>(tm, sOnes, sTa), issue3<96, 8, true>(tm, sA, sAl, sW + kOffWp * 4)));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                ta[q] = __ldg(TA + q * ts);
+                tb[q] = __ldg(TB + q * ts);
+            }
+            CPPF_TC_STEP((issue3<96, 8>(tm, sA, sAl, sW + kOffWp * 4)));
         }
-        CPPF_TC_STEP((issue3<96, 8>(tm, sA, sAl, sW + kOffWp * 4)));
         tmem_ld32(tml, x);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-            st_chunk(a_hi, q, tg, fmaxf(ta[q].x + tb[q].x + x[4 * q], 0.f), fmaxf(ta[q].y + tb[q].y + x[4 * q + 1], 0.f),
-                     fmaxf(ta[q].z + tb[q].z + x[4 * q + 2], 0.f), fmaxf(ta[q].w + tb[q].w + x[4 * q + 3], 0.f));
+            st_chunk(a_hi, q, tg, fmaxf((DENSE ? tb[q].x : ta[q].x + tb[q].x) + x[4 * q], 0.f), fmaxf((DENSE ? tb[q].y : ta[q].y + tb[q].y) + x[4 * q + 1], 0.f),
+                     fmaxf((DENSE ? tb[q].z : ta[q].z + tb[q].z) + x[4 * q + 2], 0.f), fmaxf((DENSE ? tb[q].w : ta[q].w + tb[q].w) + x[4 * q + 3], 0.f));
         // ---- step 1: [W1_1 W2_0 ; W10_2 W2_0] h accumulated onto q1 | q2 -> u = relu(fc1_1(x1))
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            ta[q] = __ldg(TA + (8 + q) * ts);
+            if (!DENSE) ta[q] = __ldg(TA + (8 + q) * ts);
             tb[q] = __ldg(TB + (8 + q) * ts);
         }
         CPPF_TC_STEP((issue3<64, 32, true>(tm + 32, sA, sAl, sW + kOffWs1 * 4)));
         tmem_ld32(tml + 32, x);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-            st_chunk(a_hi, q, tg, fmaxf(ta[q].x + tb[q].x + x[4 * q], 0.f), fmaxf(ta[q].y + tb[q].y + x[4 * q + 1], 0.f),
-                     fmaxf(ta[q].z + tb[q].z + x[4 * q + 2], 0.f), fmaxf(ta[q].w + tb[q].w + x[4 * q + 3], 0.f));
+            st_chunk(a_hi, q, tg, fmaxf((DENSE ? tb[q].x : ta[q].x + tb[q].x) + x[4 * q], 0.f), fmaxf((DENSE ? tb[q].y : ta[q].y + tb[q].y) + x[4 * q + 1], 0.f),
+                     fmaxf((DENSE ? tb[q].z : ta[q].z + tb[q].z) + x[4 * q + 2], 0.f), fmaxf((DENSE ? tb[q].w : ta[q].w + tb[q].w) + x[4 * q + 3], 0.f));
         // ---- step 2: (W10_2 W2_1) u accumulated onto q2 + (W10_2 W2_0) h -> t = [fc1_2(x2) ; fc0_2(x2) + fc2_2.b]
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            ta[q] = __ldg(TA + (16 + q) * ts);
+            if (!DENSE) ta[q] = __ldg(TA + (16 + q) * ts);
             tb[q] = __ldg(TB + (16 + q) * ts);
         }
         CPPF_TC_STEP((issue3<32, 32, true>(tm + 64, sA, sAl, sW + kOffWs2 * 4)));
         tmem_ld32(tml + 64, x);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            x[4 * q] += ta[q].x + tb[q].x;
-            x[4 * q + 1] += ta[q].y + tb[q].y;
-            x[4 * q + 2] += ta[q].z + tb[q].z;
-            x[4 * q + 3] += ta[q].w + tb[q].w;
+            x[4 * q] += (DENSE ? tb[q].x : ta[q].x + tb[q].x);
+            x[4 * q + 1] += (DENSE ? tb[q].y : ta[q].y + tb[q].y);
+            x[4 * q + 2] += (DENSE ? tb[q].z : ta[q].z + tb[q].z);
+            x[4 * q + 3] += (DENSE ? tb[q].w : ta[q].w + tb[q].w);
         }
         if (prm.dbg_t != nullptr && valid) {
 #pragma unroll
@@ -479,10 +514,14 @@ extern "C" int cppf_encode_sample_tc(const float* pc, const float* nrm, const fl
     if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     if ((heads & 8) && tail == nullptr) return (int)cudaErrorInvalidValue;
     tc::Params prm{pc, nrm, table, tc_blob, idx, uniforms, seed, bins, tail, dbg_t, n_points, (long long)n_pairs, heads};
-    const long long n_tiles = (n_pairs + tc::kTile - 1) / tc::kTile;
+    const bool dense = idx == nullptr;
+    const long long n_tiles = dense ? (long long)n_points * ((n_points + tc::kTile - 1) / tc::kTile)
+                                    : (n_pairs + tc::kTile - 1) / tc::kTile;
     long long ctas = (n_tiles + tc::kGroups - 1) / tc::kGroups;
     if (ctas > sm_count()) ctas = sm_count();
-    auto kern = idx_is_64 ? tc::encode_sample_tc_kernel<true> : tc::encode_sample_tc_kernel<false>;
+    void (*kern)(const tc::Params);
+    if (dense) kern = tc::encode_sample_tc_kernel<false, true>;
+    else kern = idx_is_64 ? tc::encode_sample_tc_kernel<true, false> : tc::encode_sample_tc_kernel<false, false>;
     CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
     kern<<<(int)ctas, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>(prm);
     CPPF_LAUNCH_CHECK();

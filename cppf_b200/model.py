@@ -103,6 +103,18 @@ def pack_head_weights(sd) -> np.ndarray:
     return blob
 
 
+def _row_constant_operand(v: np.ndarray, n_pad: int) -> np.ndarray:
+    """Vector v -> [2 K planes][n_pad][4] B operand of csrc/encode_tc.cu's ones-operand MMA: k = 0 holds the tf32 `hi` part
+    of v, k = 4 its fp32 remainder `lo` (the A side is 1 in k = 0 and k = 4), everything else zero."""
+    m = np.zeros(n_pad, np.float32)
+    m[:v.shape[0]] = v
+    hi = (m.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    out = np.zeros((2, n_pad, 4), np.float32)
+    out[0, :, 0] = hi
+    out[1, :, 0] = m - hi
+    return out.reshape(-1)
+
+
 def _canon_hi_lo(w: np.ndarray, n_pad: int, k_pad: int) -> list:
     """nn.Linear weight [n, k] -> tcgen05 no-swizzle K-major operand [k_pad/4][n_pad][4], split into the
     tf32 `hi` part (low 13 mantissa bits cleared) and the fp32 remainder `lo` (csrc/encode_tc.cu)."""
@@ -174,8 +186,7 @@ def pack_tc_weights(sd) -> np.ndarray:
     bh[r_rt:r_rt + 5, 0] = bf[r_tail:]
     br_ = np.zeros((48, 8))
     br_[0:ROT_BINS, 0] = bf[r_rt:r_tail] * LOG2E
-    parts += _canon_hi_lo(f32(bh), 112, 8)
-    parts += _canon_hi_lo(f32(br_), 48, 8)
+    parts += [_row_constant_operand(f32(bh[:, 0]), 112), _row_constant_operand(f32(br_[:, 0]), 48)]
     blob = np.concatenate([np.ascontiguousarray(q, dtype=np.float32).reshape(-1) for q in parts])
     assert blob.size == _lib.lib().cppf_tc_blob_floats(), blob.size
     return blob

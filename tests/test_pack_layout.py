@@ -129,10 +129,11 @@ def test_tc_blob_chain_algebra_matches_oracle():
     ws2 = _tc_operand(blob, o, 32, 32); o += 2 * 32 * 32
     wh = _tc_operand(blob, o, 112, 32); o += 2 * 112 * 32
     wr = _tc_operand(blob, o, 48, 32); o += 2 * 48 * 32
-    bh = _tc_operand(blob, o, 112, 8); o += 2 * 112 * 8
-    br = _tc_operand(blob, o, 48, 8); o += 2 * 48 * 8
-    assert o == blob.size and not bh[:, 1:].any() and not br[:, 1:].any()     # the bias sits in k = 0 of its operand
-    bias = np.concatenate([bh[:, 0], br[:, 0]])
+    bh = blob[o:o + 112 * 8].reshape(2, 112, 4).astype(np.float64); o += 112 * 8      # k = 0: hi, k = 4: lo
+    br = blob[o:o + 48 * 8].reshape(2, 48, 4).astype(np.float64); o += 48 * 8
+    assert o == blob.size and not bh[:, :, 1:].any() and not br[:, :, 1:].any()
+    assert not (blob[o - 48 * 8 - 112 * 8:o - 48 * 8 - 112 * 4].view(np.uint32) & 0x1FFF).any()     # hi plane is tf32-exact
+    bias = np.concatenate([bh[0, :, 0] + bh[1, :, 0], br[0, :, 0] + br[1, :, 0]])
     assert not wp[:, 4:].any()                                      # K padding of the ppf operand
     d = np.concatenate([ppf, np.zeros((p, 4), np.float32)], 1).astype(np.float64) @ wp.T          # step 0
     h = np.maximum(d[:, :32] + ta[:, :32] + tb[:, :32], 0)
