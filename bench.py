@@ -75,7 +75,7 @@ def workload_config(args):
             "out_dim": 141, "parallelism": f"objects sharded over {args.gpus} rank(s), one NCCL all_gather of pose records",
             "path": args.path, "votes": args.votes, "encoder": args.encoder,
             "weights": "torch.manual_seed(0) default init of the reference architecture (no checkpoints exist offline)",
-            "l2_policy": "per-step working set (bins + tail logits of 16.7M pairs = 403 MB, + 134 MB survivor list) exceeds the "
+            "l2_policy": "per-step working set (bins + tail logits of 16.7M pairs = 403 MB, + 17 MB survivor mask) exceeds the "
                          "126 MB L2; each step is a different cloud"}
 
 
@@ -416,7 +416,7 @@ def main():
                                     else "fp32 FMA pipe",
                    "vote": "shared-memory pipe (72 % of peak wavefronts, 3.6 bank/same-cell replays per ATOMS) and issue slots (79 %)",
                    "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput", "stats": "HBM gather (2.9 TB/s)",
-                   "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "torch ops (cdist/topk/LayerNorm), launch-bound"}
+                   "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "FP32/issue (two-sweep kNN select + one-warp-per-point SPRIN MLP)"}
         detail = {}
         for k, v in kern.items():
             t = v["avg_ms"] * 1e-3

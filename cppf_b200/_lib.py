@@ -50,6 +50,7 @@ SIGNATURES = {
     "cppf_vote_scratch_bytes": (_i64, [_i, _i, _i]),
     "cppf_vote_private_max_cells": (_i, []),
     "cppf_vote_fast": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),
+    "cppf_vote_finalize": (_i, [_p, _p, _i64, _p]),
     "cppf_vote_routed_supported": (_i, [_i, _i, _i]),
     "cppf_vote_routed_scratch_bytes": (_i64, [_i64, _i, _i, _i, _i]),
     "cppf_vote_routed": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _i64, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),

@@ -935,6 +935,13 @@ extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uin
                             gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, 0, 0);
 }
 
+extern "C" int cppf_vote_finalize(const void* acc, float* grid, int64_t cells, void* stream_) {
+    if (cells <= 0) return 0;
+    if (acc == nullptr || grid == nullptr || cells > 0x7fffffffll) return (int)cudaErrorInvalidValue;
+    return vote_finalize_launch(reinterpret_cast<const unsigned long long*>(acc), grid, (int)cells, nullptr, -1,
+                                (cudaStream_t)stream_);
+}
+
 extern "C" int cppf_vote_slabs_supported(int gx, int gy, int gz) {
     const long long gyz = (long long)gy * gz;
     const long long pps = cppf_vote_private_max_cells() / gyz - 1;

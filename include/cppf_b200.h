@@ -187,6 +187,13 @@ int cppf_vote_fast(const float* points, const float* mu_nu, const uint8_t* bins,
                    const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
                    int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, void* stream);
 
+/* On return from cppf_vote_fast / cppf_vote_slabs / cppf_vote_routed the first gx*gy*gz 64-bit words of `scratch` hold the exact vote
+ * sums in units of 2^-14 (unsigned).  A caller that splits the pairs of ONE object over several GPUs (SURVEY.md
+ * section 8e, second axis) sums those integer grids across ranks and converts once:
+ *     grid[i] += (float)((double)acc[i] * 2^-14)
+ * -- the same single rounding, hence bit for bit the same grid, as one call over all pairs. */
+int cppf_vote_finalize(const void* acc, float* grid, int64_t cells, void* stream);
+
 /* The same contract for grids of up to eight shared-memory slabs (e.g. the 64^3 grid of BASELINE config 3, 1 MB):
  * candidates are routed through HBM to the x-slab that owns them (32 B per in-bounds candidate) and accumulated
  * in that slab's shared-memory copy (csrc/vote_routed.cu).  Same fixed-point sums, hence the same grid as
