@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcppf_b200.so")
+# CPPF_B200_LIB: developer override used by tools/build_variants.py to A/B compile-time variants of the library
+LIB_PATH = os.environ.get("CPPF_B200_LIB") or os.path.join(_HERE, "libcppf_b200.so")
 _lib = None
 
 _p = C.c_void_p

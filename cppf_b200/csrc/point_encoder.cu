@@ -49,7 +49,13 @@ constexpr int kWa = kEo + 32;                // GlobalInfoProp linear [32][8] k-
 constexpr int kBa = kWa + 32 * 8;
 constexpr int kBlobFloats = kBa + 8;
 
-constexpr int kWarps = 8;
+#ifndef CPPF_PE_LOCAL_MAX
+#define CPPF_PE_LOCAL_MAX 1
+#endif
+#ifndef CPPF_PE_WARPS
+#define CPPF_PE_WARPS 8
+#endif
+constexpr int kWarps = CPPF_PE_WARPS;
 constexpr int kWarpFloats = 32 * XS + 64 * XS + 64 + 64;      // P[32][XS], Q[64][XS], nbr feats [2][32], contraction [64]
 constexpr float kLnEps = 1e-5f;                               // torch.nn.LayerNorm default
 
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) point_encode_kernel(const Para
     __syncthreads();
     const int og = lane & 7, pb = (lane >> 3) * 8;
     const float inv_k = 1.f / (float)prm.k;
+    float tmax = -INFINITY;                   // running max of this warp's GlobalInfoProp columns (lanes 0..7)
 
     for (int n = blockIdx.x * kWarps + warp; n < prm.n_points; n += gridDim.x * kWarps) {
         const f3 ctr = ld3(prm.pc, n), nc = ld3(prm.nrm, n);
@@ -261,8 +268,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) point_encode_kernel(const Para
             const float yk = __shfl_sync(0xffffffffu, y, k);
             if (lane < 8) t = fmaf(yk, sW[kWa + k * 8 + lane], t);
         }
+#if CPPF_PE_LOCAL_MAX
+        tmax = (t > tmax || t != t) ? t : tmax;               // NaN sticks, like torch.max
+    }
+    if (lane < 8) atomic_max_float(prm.glob + lane, tmax);    // one set of atomics per warp instead of one per point
+#else
         if (lane < 8) atomic_max_float(prm.glob + lane, t);
     }
+    (void)tmax;
+#endif
 }
 
 __global__ void __launch_bounds__(256) point_glob_kernel(float* __restrict__ feat, const float* __restrict__ glob, int n_points) {
@@ -284,7 +298,10 @@ __device__ __forceinline__ unsigned d2_bits(f3 q, const float* __restrict__ pc, 
     return __float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
 }
 
-constexpr int kKnnWarps = 8;
+#ifndef CPPF_KNN_WARPS
+#define CPPF_KNN_WARPS 16
+#endif
+constexpr int kKnnWarps = CPPF_KNN_WARPS;
 constexpr int kKnnBins = 1024;           // coarse histogram: sign (0) + exponent + 2 mantissa bits of d^2 = bits >> 21
 constexpr int kKnnCand = 256;            // candidates of the boundary bin kept in shared memory
 

@@ -44,11 +44,21 @@ struct VotePParams {
     int n_slabs;
 };
 
-constexpr int kVoteThreads = 1024;
+#ifndef CPPF_VOTE_THREADS
+#define CPPF_VOTE_THREADS 1024
+#endif
+#ifndef CPPF_VOTE_UNROLL
+#define CPPF_VOTE_UNROLL 4
+#endif
+constexpr int kVoteThreads = CPPF_VOTE_THREADS;
+constexpr int kVoteUnroll = CPPF_VOTE_UNROLL;     // unroll factor of the rotation walk
 constexpr int kVoteBatch = 2 * kVoteThreads;       // pairs sorted and voted between two block barriers
 constexpr int kVoteQueue = 64;                     // per-warp ring of in-bounds candidates (float4 slots)
 constexpr int kVoteKeys = kMaxRotsP + 1;           // sort key = rotation count of the pair (0..72)
-constexpr int kTileA = 128, kTileB = 16;           // dense mode: a batch is a kTileA x kTileB tile of the pair matrix
+#ifndef CPPF_VOTE_TILEB
+#define CPPF_VOTE_TILEB 16
+#endif
+constexpr int kTileB = CPPF_VOTE_TILEB, kTileA = kVoteBatch / kTileB;          // dense mode: a batch is a kTileA x kTileB tile of the pair matrix
 static_assert(kTileA * kTileB == kVoteBatch, "tile = batch");
 // Overflow guard: after every batch each cell holding >= 2^30 units is flushed to the global u64 accumulator.
 // A batch adds at most kVoteBatch * 72 candidates * 2^14 units = 2.42e9 < 2^32 - 2^30 to any one cell.
@@ -269,6 +279,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
             // vote peak in the same iterations -- and was measured: fewer ATOMS replays, but a slower kernel overall.)
             const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
             const int n_max = __reduce_max_sync(0xffffffffu, n);
+#pragma unroll kVoteUnroll
             for (int i = 0; i < n_max; ++i) {
                 const float2 cs = tab[i];
                 const f3 off = x * cs.x + y * cs.y;                            // :34
@@ -341,8 +352,12 @@ struct BackvotePParams {
     const Geom* geom;                // optional: device-side geometry overrides corner / dims / bounds
 };
 
+#ifndef CPPF_BV_THREADS
+#define CPPF_BV_THREADS 256
+#endif
+
 template <bool IDX64>
-__global__ void __launch_bounds__(256) backvote_bins_kernel(const BackvotePParams prm) {
+__global__ void __launch_bounds__(CPPF_BV_THREADS) backvote_bins_kernel(const BackvotePParams prm) {
     __shared__ float2 s_tab[kRotTabP];
     __shared__ float s_lut[64];
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
@@ -917,11 +932,11 @@ int backvote_bins_launch(const float* points, const uint8_t* bins, const float* 
     BackvotePParams prm{rot_tab, points, bins, lut, idx, out_mask, corner, reinterpret_cast<const long long*>(argmax_flat), res,
                         (float)(1.0 / (double)res), tol, (float)(gx - 1), (float)(gy - 1), (float)(gz - 1), n_points,
                         (long long)n_pairs, n_rots, gx, gy, gz, geom};
-    long long blocks = (n_pairs + 255) / 256;
-    const long long cap = (long long)sm_count() * 8;
+    long long blocks = (n_pairs + CPPF_BV_THREADS - 1) / CPPF_BV_THREADS;
+    const long long cap = (long long)sm_count() * (2048 / CPPF_BV_THREADS);
     if (blocks > cap) blocks = cap;
-    if (idx_is_64) backvote_bins_kernel<true><<<(int)blocks, 256, 0, stream>>>(prm);
-    else backvote_bins_kernel<false><<<(int)blocks, 256, 0, stream>>>(prm);
+    if (idx_is_64) backvote_bins_kernel<true><<<(int)blocks, CPPF_BV_THREADS, 0, stream>>>(prm);
+    else backvote_bins_kernel<false><<<(int)blocks, CPPF_BV_THREADS, 0, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     return 0;
 }

@@ -1,20 +1,19 @@
 #!/bin/bash
-# A/B of run-time switches on one box: bench (no variants, no CPU arm) per setting -> gpurun_out/ab_<name>.json
+# A/B of library variants (tools/build_variants.py) on one box: bench (no variants, no CPU arm) per library
+# -> gpurun_out/ab_<name>.json.  Usage: tools/gpu_ab.sh base name1 name2 ...   ("base" = the regular library)
 mkdir -p gpurun_out
-run() {   # name, env...
-    local name=$1; shift
-    env "$@" python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-variants > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+for name in "$@"; do
+    lib=""
+    [ "$name" != base ] && [ "$name" != base2 ] && lib="$PWD/cppf_b200/_variants/libcppf_$name.so"
+    CPPF_B200_LIB=$lib python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-variants > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
     python - "$name" <<'PY'
 import json, sys
 try:
     d = json.loads(open(f"gpurun_out/ab_{sys.argv[1]}.json").read().strip().splitlines()[-1])
-    print(sys.argv[1], round(d["ms_per_step"], 4), {k: round(v["avg_ms"], 4) for k, v in d["kernels"].items()})
+    k = d["kernels"]
+    print(f"{sys.argv[1]:10s} step {d['ms_per_step']:.4f}  enc {k['encode_sample']['avg_ms']:.4f}  vote {k['vote']['avg_ms']:.4f}  "
+          f"bv {k['backvote']['avg_ms']:.4f}  pe {k['point_encoder']['avg_ms']:.4f}")
 except Exception as e:
     print(sys.argv[1], "failed", e)
 PY
-}
-run base CPPF_TC_WAIT_HINT=0
-run hint1k CPPF_TC_WAIT_HINT=1000
-run hint100k CPPF_TC_WAIT_HINT=100000
-run hint10m CPPF_TC_WAIT_HINT=10000000
-run base2 CPPF_TC_WAIT_HINT=0
+done
