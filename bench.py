@@ -37,13 +37,13 @@ if ROOT not in sys.path:
 METRIC = "point_pairs_per_sec"
 UNIT = "pairs/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch and the utilisation of the resource that binds each kernel,
-# from the committed `ncu --set full` capture of this pipeline (profiles/r1e_kernels_ncu.md), N=4096 dense
-TRAFFIC_NCU = {"encode_sample": 3.378432e6 + 348.861184e6, "vote": 67.368704e6 + 0.92416e6,
-               "backvote": 67.202816e6 + 3.360256e6, "stats": 285.0e6 + 3.8e6}
-BINDING_NCU = {"encode_sample": {"issue_slots_busy": 0.473, "tensor_pipe_active": 0.326, "warps_per_sm": 16},
-               "vote": {"shared_memory_wavefronts_of_peak": 0.722, "issue_slots_busy": 0.795,
+# from the committed `ncu --set full` capture of this pipeline (profiles/r1f_kernels_ncu.md), N=4096 dense
+TRAFFIC_NCU = {"encode_sample": 3.3728e6 + 345.649152e6, "vote": 67.36128e6 + 0.84736e6,
+               "backvote": 67.252736e6 + 3.7312e6, "stats": 285.441792e6 + 7.912192e6}
+BINDING_NCU = {"encode_sample": {"issue_slots_busy": 0.456, "tensor_pipe_active": 0.438, "warps_per_sm": 16},
+               "vote": {"shared_memory_wavefronts_of_peak": 0.738, "issue_slots_busy": 0.772,
                         "wavefronts_per_ATOMS": 3.64},
-               "backvote": {"issue_slots_busy": 0.778}, "stats": {"dram_read_tbs": 2.86}}
+               "backvote": {"issue_slots_busy": 0.778}, "stats": {"dram_read_tbs": 2.88}}
 
 
 def parse():

@@ -159,6 +159,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same 32 columns as two 16-column loads: the second is in flight while the caller consumes the first
+// (`tmem_ld32_second` waits for it and hands the registers over; the "+r" operands keep every use behind the wait)
+__device__ __forceinline__ void tmem_ld32_first(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr + 16)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_second(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+#ifndef CPPF_TC_ST_CS
+#define CPPF_TC_ST_CS 1      // tail logits leave with st.global.cs: 335 MB per object that should not push the bins out of L2
+#endif
+#ifndef CPPF_TC_LD_PIPE
+#define CPPF_TC_LD_PIPE 2    // TMEM -> register loads of the step epilogues split in two, the second in flight while the first is consumed
+#endif
+#ifndef CPPF_TC_TB_LDCG
+#define CPPF_TC_TB_LDCG 1    // table rows bypass L1 (ld.global.cg): with 224 KB of shared memory the L1 is too small to keep them
+#endif
+__device__ __forceinline__ float4 ld_tab(const float4* p) {
+#if CPPF_TC_TB_LDCG
+    return __ldcg(p);
+#else
+    return __ldg(p);
+#endif
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -370,42 +411,84 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 ta[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                tb[q] = __ldg(TB + q * ts);
+                tb[q] = ld_tab(TB + q * ts);
             }
             CPPF_TC_STEP((issue_bias<96>(tm, sOnes, sTa), issue3<96, 8, true>(tm, sA, sAl, sW + kOffWp * 4)));
         } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                ta[q] = __ldg(TA + q * ts);
-                tb[q] = __ldg(TB + q * ts);
+                ta[q] = ld_tab(TA + q * ts);
+                tb[q] = ld_tab(TB + q * ts);
             }
             CPPF_TC_STEP((issue3<96, 8>(tm, sA, sAl, sW + kOffWp * 4)));
         }
+#if CPPF_TC_LD_PIPE
+        {
+            uint32_t xr[32];
+            tmem_ld32_first(tml, xr);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q == 4) tmem_ld32_second(xr);
+                st_chunk(a_hi, q, tg, fmaxf((DENSE ? tb[q].x : ta[q].x + tb[q].x) + __uint_as_float(xr[4 * q]), 0.f),
+                         fmaxf((DENSE ? tb[q].y : ta[q].y + tb[q].y) + __uint_as_float(xr[4 * q + 1]), 0.f),
+                         fmaxf((DENSE ? tb[q].z : ta[q].z + tb[q].z) + __uint_as_float(xr[4 * q + 2]), 0.f),
+                         fmaxf((DENSE ? tb[q].w : ta[q].w + tb[q].w) + __uint_as_float(xr[4 * q + 3]), 0.f));
+            }
+        }
+#else
         tmem_ld32(tml, x);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             st_chunk(a_hi, q, tg, fmaxf((DENSE ? tb[q].x : ta[q].x + tb[q].x) + x[4 * q], 0.f), fmaxf((DENSE ? tb[q].y : ta[q].y + tb[q].y) + x[4 * q + 1], 0.f),
                      fmaxf((DENSE ? tb[q].z : ta[q].z + tb[q].z) + x[4 * q + 2], 0.f), fmaxf((DENSE ? tb[q].w : ta[q].w + tb[q].w) + x[4 * q + 3], 0.f));
+#endif
         // ---- step 1: [W1_1 W2_0 ; W10_2 W2_0] h accumulated onto q1 | q2 -> u = relu(fc1_1(x1))
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            if (!DENSE) ta[q] = __ldg(TA + (8 + q) * ts);
-            tb[q] = __ldg(TB + (8 + q) * ts);
+            if (!DENSE) ta[q] = ld_tab(TA + (8 + q) * ts);
+            tb[q] = ld_tab(TB + (8 + q) * ts);
         }
         CPPF_TC_STEP((issue3<64, 32, true>(tm + 32, sA, sAl, sW + kOffWs1 * 4)));
+#if CPPF_TC_LD_PIPE
+        {
+            uint32_t xr[32];
+            tmem_ld32_first(tml + 32, xr);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q == 4) tmem_ld32_second(xr);
+                st_chunk(a_hi, q, tg, fmaxf((DENSE ? tb[q].x : ta[q].x + tb[q].x) + __uint_as_float(xr[4 * q]), 0.f),
+                         fmaxf((DENSE ? tb[q].y : ta[q].y + tb[q].y) + __uint_as_float(xr[4 * q + 1]), 0.f),
+                         fmaxf((DENSE ? tb[q].z : ta[q].z + tb[q].z) + __uint_as_float(xr[4 * q + 2]), 0.f),
+                         fmaxf((DENSE ? tb[q].w : ta[q].w + tb[q].w) + __uint_as_float(xr[4 * q + 3]), 0.f));
+            }
+        }
+#else
         tmem_ld32(tml + 32, x);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             st_chunk(a_hi, q, tg, fmaxf((DENSE ? tb[q].x : ta[q].x + tb[q].x) + x[4 * q], 0.f), fmaxf((DENSE ? tb[q].y : ta[q].y + tb[q].y) + x[4 * q + 1], 0.f),
                      fmaxf((DENSE ? tb[q].z : ta[q].z + tb[q].z) + x[4 * q + 2], 0.f), fmaxf((DENSE ? tb[q].w : ta[q].w + tb[q].w) + x[4 * q + 3], 0.f));
+#endif
         // ---- step 2: (W10_2 W2_1) u accumulated onto q2 + (W10_2 W2_0) h -> t = [fc1_2(x2) ; fc0_2(x2) + fc2_2.b]
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            if (!DENSE) ta[q] = __ldg(TA + (16 + q) * ts);
-            tb[q] = __ldg(TB + (16 + q) * ts);
+            if (!DENSE) ta[q] = ld_tab(TA + (16 + q) * ts);
+            tb[q] = ld_tab(TB + (16 + q) * ts);
         }
         CPPF_TC_STEP((issue3<32, 32, true>(tm + 64, sA, sAl, sW + kOffWs2 * 4)));
+#if CPPF_TC_LD_PIPE >= 2
+        {
+            uint32_t xr[32];
+            tmem_ld32_first(tml + 64, xr);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) x[q] = __uint_as_float(xr[q]);
+            tmem_ld32_second(xr);
+#pragma unroll
+            for (int q = 16; q < 32; ++q) x[q] = __uint_as_float(xr[q]);
+        }
+#else
         tmem_ld32(tml + 64, x);
+#endif
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             x[4 * q] += (DENSE ? tb[q].x : ta[q].x + tb[q].x);
@@ -438,7 +521,13 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
             tmem_ld16(tml + 96, y);
             if ((prm.heads & 8) && valid) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) prm.tail[(long long)k * prm.n_pairs + p] = y[4 + k];
+                for (int k = 0; k < 5; ++k) {
+#if CPPF_TC_ST_CS
+                    __stcs(prm.tail + (long long)k * prm.n_pairs + p, y[4 + k]);
+#else
+                    prm.tail[(long long)k * prm.n_pairs + p] = y[4 + k];
+#endif
+                }
             }
             if (prm.heads & 2) {
                 float l[36];
