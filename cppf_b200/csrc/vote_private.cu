@@ -447,10 +447,10 @@ __global__ void __launch_bounds__(CPPF_BV_THREADS) backvote_bins_kernel(const Ba
                     }
                 }
             }
-            for (int k = 0; k < i_cnt; ++k) {
-                int i = i_lo + k;
-                i = i < 0 ? i + n : (i >= n ? i - n : i);
-                i = i < 0 ? i + n : (i >= n ? i - n : i);
+            // start of the window into [0, n) (i_lo is in [-w, n] with w < n / 2): one wrap test per candidate below
+            i_lo = i_lo < 0 ? i_lo + n : (i_lo >= n ? i_lo - n : i_lo);
+            for (int k = 0, i = i_lo; k < i_cnt; ++k, ++i) {
+                if (i >= n) i -= n;
                 const float2 cs = tab[i];
                 if (unit_frame) {
                     const float qv = nu * fmaf(px, cs.x, py * cs.y);
