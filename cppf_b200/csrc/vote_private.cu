@@ -355,9 +355,27 @@ struct BackvotePParams {
 #ifndef CPPF_BV_THREADS
 #define CPPF_BV_THREADS 256
 #endif
+#ifndef CPPF_BV_BLOCKS_PER_SM
+#define CPPF_BV_BLOCKS_PER_SM 8
+#endif
+#ifndef CPPF_BV_MIN_BLOCKS
+#define CPPF_BV_MIN_BLOCKS 1
+#endif
+#ifndef CPPF_STATS_BLOCKS_PER_SM
+#define CPPF_STATS_BLOCKS_PER_SM 4      // one full wave of the 4 resident blocks that 64 registers allow
+#endif
+#ifndef CPPF_STATS_MIN_BLOCKS
+#define CPPF_STATS_MIN_BLOCKS 4
+#endif
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <bool IDX64>
-__global__ void __launch_bounds__(CPPF_BV_THREADS) backvote_bins_kernel(const BackvotePParams prm) {
+__global__ void __launch_bounds__(CPPF_BV_THREADS, CPPF_BV_MIN_BLOCKS) backvote_bins_kernel(const BackvotePParams prm) {
     __shared__ float2 s_tab[kRotTabP];
     __shared__ float s_lut[64];
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
@@ -420,7 +438,7 @@ __global__ void __launch_bounds__(CPPF_BV_THREADS) backvote_bins_kernel(const Ba
             // ~1e-3 rad of the x axis -- such pairs take the plain scan with the reference's arithmetic only
             const bool unit_frame = dot3(ex, ex) > 0.9999f;
             if (n > 12 && unit_frame) {
-                const float rho = sqrtf(px * px + py * py);
+                const float rho = sqrt_approx(px * px + py * py);    // window placement only: every shortcut here has slack
                 const float room = tol2 * 1.01f + 1e-12f - dpl * dpl - (nu - rho) * (nu - rho);   // >= 2 nu rho (1 - cos d) for a hit
                 const float two_nr = 2.f * fabsf(nu) * rho;
                 if (room < 0.f) {
@@ -428,21 +446,21 @@ __global__ void __launch_bounds__(CPPF_BV_THREADS) backvote_bins_kernel(const Ba
                 } else if (room < 1.9f * two_nr) {
                     // half-width of the arc: acos(1 - q) <= sqrt(2q) (1 + 0.22 q) on [0, 1.9] (no acosf, no atan2f: a
                     // polynomial atan2 good to 2e-4 rad only has to place the centre of the window)
-                    const float q = room / two_nr;
-                    const float dmax = sqrtf(2.f * q) * fmaf(0.22f, q, 1.f) + 1e-5f;
-                    const float step = 6.2831853f / (float)n;
+                    const float q = __fdividef(room, two_nr);
+                    const float dmax = sqrt_approx(2.f * q) * fmaf(0.22f, q, 1.f) + 1e-5f;
+                    const float inv_step = (float)n * 0.159154943f;             // 1 / (2 pi / n)
                     const float apx = fabsf(px), apy = fabsf(py);
                     const float mx = fmaxf(apx, apy), mn = fminf(apx, apy);
-                    const float t = mn / fmaxf(mx, 1e-30f), t2 = t * t;
+                    const float t = __fdividef(mn, fmaxf(mx, 1e-30f)), t2 = t * t;
                     float th = fmaf(fmaf(fmaf(-0.0464964749f, t2, 0.15931422f), t2, -0.327622764f) * t2, t, t);
                     if (apy > apx) th = 1.57079633f - th;
                     if (px < 0.f) th = 3.14159265f - th;
                     if (py < 0.f) th = -th;
                     if (nu < 0.f) th += 3.14159265f;                             // x, y carry the sign of nu
                     if (th < 0.f) th += 6.2831853f;
-                    const int w = (int)(dmax / step + 0.52f) + 1;
+                    const int w = (int)(dmax * inv_step + 0.52f) + 1;
                     if (2 * w + 1 < n) {
-                        i_lo = (int)(th / step + 0.5f) - w;
+                        i_lo = (int)(th * inv_step + 0.5f) - w;
                         i_cnt = 2 * w + 1;
                     }
                 }
@@ -728,7 +746,7 @@ struct StatsParams {
 };
 
 template <bool IDX64>
-__global__ void __launch_bounds__(256) survivor_stats_kernel(const StatsParams prm) {
+__global__ void __launch_bounds__(256, CPPF_STATS_MIN_BLOCKS) survivor_stats_kernel(const StatsParams prm) {
     const long long count = prm.pos ? *prm.count : prm.n_pairs;      // mask mode walks every pair
     const long long bu = *prm.best_up;
     const f3 du = {__ldg(prm.sphere + 3 * bu), __ldg(prm.sphere + 3 * bu + 1), __ldg(prm.sphere + 3 * bu + 2)};
@@ -933,7 +951,7 @@ int backvote_bins_launch(const float* points, const uint8_t* bins, const float* 
                         (float)(1.0 / (double)res), tol, (float)(gx - 1), (float)(gy - 1), (float)(gz - 1), n_points,
                         (long long)n_pairs, n_rots, gx, gy, gz, geom};
     long long blocks = (n_pairs + CPPF_BV_THREADS - 1) / CPPF_BV_THREADS;
-    const long long cap = (long long)sm_count() * (2048 / CPPF_BV_THREADS);
+    const long long cap = (long long)sm_count() * CPPF_BV_BLOCKS_PER_SM;
     if (blocks > cap) blocks = cap;
     if (idx_is_64) backvote_bins_kernel<true><<<(int)blocks, CPPF_BV_THREADS, 0, stream>>>(prm);
     else backvote_bins_kernel<false><<<(int)blocks, CPPF_BV_THREADS, 0, stream>>>(prm);
@@ -1019,7 +1037,7 @@ int survivor_stats_launch(const float* points, const float* nrm, const float* ta
     StatsParams prm{points, nrm, tail, idx, reinterpret_cast<const long long*>(pos), mask,
                     reinterpret_cast<const long long*>(count), sphere, reinterpret_cast<const long long*>(best_up),
                     reinterpret_cast<const long long*>(best_right), out, n_points, (long long)n_pairs, vec4};
-    const int blocks = sm_count() * 8;
+    const int blocks = sm_count() * CPPF_STATS_BLOCKS_PER_SM;
     if (idx_is_64) survivor_stats_kernel<true><<<blocks, 256, 0, stream>>>(prm);
     else survivor_stats_kernel<false><<<blocks, 256, 0, stream>>>(prm);
     CPPF_LAUNCH_CHECK();

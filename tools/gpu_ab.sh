@@ -12,7 +12,7 @@ try:
     d = json.loads(open(f"gpurun_out/ab_{sys.argv[1]}.json").read().strip().splitlines()[-1])
     k = d["kernels"]
     print(f"{sys.argv[1]:10s} step {d['ms_per_step']:.4f}  enc {k['encode_sample']['avg_ms']:.4f}  vote {k['vote']['avg_ms']:.4f}  "
-          f"bv {k['backvote']['avg_ms']:.4f}  pe {k['point_encoder']['avg_ms']:.4f}")
+          f"bv {k['backvote']['avg_ms']:.4f}  pe {k['point_encoder']['avg_ms']:.4f}  stats {k['stats']['avg_ms']:.4f}  rot {k['rot_hist']['avg_ms']:.4f}")
 except Exception as e:
     print(sys.argv[1], "failed", e)
 PY
