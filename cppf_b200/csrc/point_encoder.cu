@@ -299,7 +299,7 @@ __device__ __forceinline__ unsigned d2_bits(f3 q, const float* __restrict__ pc, 
 }
 
 #ifndef CPPF_KNN_WARPS
-#define CPPF_KNN_WARPS 16
+#define CPPF_KNN_WARPS 14     // one CTA per SM is resident: 4096 queries / 14 = 293 CTAs = 1.98 waves of 148
 #endif
 constexpr int kKnnWarps = CPPF_KNN_WARPS;
 constexpr int kKnnBins = 1024;           // coarse histogram: sign (0) + exponent + 2 mantissa bits of d^2 = bits >> 21
