@@ -414,7 +414,7 @@ def main():
         algo_flops = {"encode_sample": pairs_per_obj * 23968.0, "ppf_encode_pass1": pairs_per_obj * (23968.0 - 2 * 16 * 77)}
         binding = {"encode_sample": "tensor pipe issue + MMA round-trip latency (tcgen05 3xTF32 chain)" if args.encoder == "tc"
                                     else "fp32 FMA pipe",
-                   "vote": "shared-memory pipe (72 % of peak wavefronts, 3.6 bank/same-cell replays per ATOMS) and issue slots (79 %)",
+                   "vote": "shared-memory pipe (74 % of peak wavefronts, 3.6 bank/same-cell replays per ATOMS) and issue slots (77 %)",
                    "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput", "stats": "HBM gather (2.9 TB/s)",
                    "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "FP32/issue (two-sweep kNN select + one-warp-per-point SPRIN MLP)"}
         detail = {}
