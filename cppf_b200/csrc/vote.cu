@@ -8,6 +8,8 @@
 
 #include <math.h>
 
+#include <mutex>
+
 namespace cppf {
 
 // ---------------------------------------------------------------------------
@@ -30,14 +32,23 @@ __global__ void rot_table_init_kernel() {
     g_rot_table[t] = make_float2(cosf(ang), sinf(ang));
 }
 
+// Once per device.  The first call waits for the table (unless the stream is being captured, in which case the
+// initialisation is simply repeated by later calls), so a concurrent first call on another stream cannot run ahead of it.
 static int ensure_rot_table(cudaStream_t stream) {
+    static std::mutex mu;
     static bool ready[64] = {false};
     int dev = 0;
     CPPF_RETURN_IF(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
     if (dev < 64 && ready[dev]) return 0;
     rot_table_init_kernel<<<(kRotTableSize + 255) / 256, 256, 0, stream>>>();
     CPPF_LAUNCH_CHECK();
-    if (dev < 64) ready[dev] = true;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CPPF_RETURN_IF(cudaStreamIsCapturing(stream, &cap));
+    if (cap == cudaStreamCaptureStatusNone) {
+        CPPF_RETURN_IF(cudaStreamSynchronize(stream));
+        if (dev < 64) ready[dev] = true;
+    }
     return 0;
 }
 

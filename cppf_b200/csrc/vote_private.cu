@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "vote_common.cuh"
 
+#include <mutex>
+
 #include "../../include/cppf_b200.h"
 
 #include <math.h>
@@ -47,6 +49,9 @@ struct VotePParams {
 #ifndef CPPF_VOTE_THREADS
 #define CPPF_VOTE_THREADS 1024
 #endif
+#ifndef CPPF_VOTE_CONST_TAB
+#define CPPF_VOTE_CONST_TAB 1     // rotation table read from constant memory (the lanes of a sorted chunk share the entry): 2.49 -> 2.46 ms
+#endif
 #ifndef CPPF_VOTE_UNROLL
 #define CPPF_VOTE_UNROLL 4
 #endif
@@ -79,6 +84,10 @@ static_assert((unsigned long long)kVoteBatch * kMaxRotsP * (1ull << kFixShift) <
 // Without the ring the splat runs under the divergence of the in-bounds test (about a third of the lanes
 // active); with it the atomics always issue from full warps.  Integer sums are order-independent, so neither
 // the sort nor the dynamic chunk assignment changes the result.
+#if CPPF_VOTE_CONST_TAB
+__constant__ float2 c_rot_tab[kRotTabP];     // the rotation table in constant memory: lanes of a sorted chunk read the same entry
+#endif
+
 template <bool IDX64, bool BINS, bool SLABS>
 __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const VotePParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -277,11 +286,17 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
             // row n of the rotation table; reads past column n stay inside the table.  (Starting every lane at a different
             // phase of its circle would decorrelate the splat addresses -- the pairs of a warp share point a and reach the
             // vote peak in the same iterations -- and was measured: fewer ATOMS replays, but a slower kernel overall.)
-            const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
+            const int row = n > 0 ? n * (n - 1) / 2 : 0;
+            const float2* tab = s_tab + row;
             const int n_max = __reduce_max_sync(0xffffffffu, n);
 #pragma unroll kVoteUnroll
             for (int i = 0; i < n_max; ++i) {
+#if CPPF_VOTE_CONST_TAB
+                const float2 cs = c_rot_tab[row + i];
+                (void)tab;
+#else
                 const float2 cs = tab[i];
+#endif
                 const f3 off = x * cs.x + y * cs.y;                            // :34
                 const float dx = c.x + off.x - cx, dy = c.y + off.y - cy, dz = c.z + off.z - cz;   // :35 before `/ res`
                 // conservative: every candidate the exact test of phase 2 accepts passes here
@@ -897,6 +912,25 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
     const float2* rot_tab = rot_table_device(stream, &terr);
     if (terr) return terr;
     CPPF_RETURN_IF(cudaMemsetAsync(scratch, 0, (size_t)total_cells * 8, stream));
+#if CPPF_VOTE_CONST_TAB
+    {   // once per device: copy the table into this module's constant bank; the first call waits for the copy so that a
+        // concurrent first call on another stream cannot run ahead of it
+        static std::mutex mu;
+        static bool ready[64] = {false};
+        int dev = 0;
+        CPPF_RETURN_IF(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 64 || !ready[dev]) {
+            CPPF_RETURN_IF(cudaMemcpyToSymbolAsync(c_rot_tab, rot_tab, sizeof(float2) * kRotTabP, 0, cudaMemcpyDeviceToDevice, stream));
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            CPPF_RETURN_IF(cudaStreamIsCapturing(stream, &cap));
+            if (cap == cudaStreamCaptureStatusNone) {
+                CPPF_RETURN_IF(cudaStreamSynchronize(stream));
+                if (dev < 64) ready[dev] = true;
+            }
+        }
+    }
+#endif
     const float lo = float_ceil_p(0.01);
     float hx = 0.f, hy = 0.f, hz = 0.f, dhx = 0.f, dhy = 0.f, dhz = 0.f;
     if (!geom) {
