@@ -412,7 +412,7 @@ def main():
                       "stats": pairs_per_obj * 24,
                       "ppf_encode_pass1": pairs_per_obj * 64 * 4, "ppf_vote": pairs_per_obj * 8}
         algo_flops = {"encode_sample": pairs_per_obj * 23968.0, "ppf_encode_pass1": pairs_per_obj * (23968.0 - 2 * 16 * 77)}
-        binding = {"encode_sample": "tensor pipe issue + MMA round-trip latency (tcgen05 3xTF32 chain)" if args.encoder == "tc"
+        binding = {"encode_sample": "SIMT epilogues between the tcgen05 MMA steps (3xTF32 chain; issue slots 46 %, tensor pipe 44 %)" if args.encoder == "tc"
                                     else "fp32 FMA pipe",
                    "vote": "shared-memory pipe (74 % of peak wavefronts, 3.6 bank/same-cell replays per ATOMS) and issue slots (77 %)",
                    "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput", "stats": "HBM gather (2.9 TB/s)",

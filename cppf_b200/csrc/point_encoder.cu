@@ -2,8 +2,10 @@
 // rotation-invariant convolution of models/model.py:46-77 + models/sprin.py:40-107, one warp per point.
 //
 //   cppf_knn            : for each point the k smallest exact squared distances (self included, like
-//                         torch.topk(dist, k, largest=False) at models/model.py:47), by a 4 x 8-bit radix
-//                         select on the float bits -- 5 sweeps over the cloud per query, no N x N matrix.
+//                         torch.topk(dist, k, largest=False) at models/model.py:47), one warp per query, no
+//                         N x N matrix: two sweeps over the cloud (1024-bin histogram of the top bits of d^2, then
+//                         collection + ranking of the boundary bin); a 4 x 8-bit radix select on the float bits
+//                         (5 sweeps) is the fallback when the boundary bin overflows.
 //   cppf_point_encode   : models/model.py:63-77 for one neighbour list: neighbour features
 //                         [|p_k - p|, n_k . n] (:49-53), rifeat invariants (sprin.py:40-60), the kernel MLP
 //                         6 -> 32 -> 64 -> 32 -> 32 -> 32 with LayerNorm + ReLU between layers (sprin.py:63-71)
