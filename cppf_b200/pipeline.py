@@ -66,7 +66,10 @@ _WORKSPACES = {}          # (device index, stream) -> uint8 workspace of cppf_po
 
 
 def release_workspaces():
+    """Drop the cached device buffers (cppf_pose_fused workspaces, the row-split pair lists)."""
     _WORKSPACES.clear()
+    from . import rowsplit
+    rowsplit._PAIRS_CACHE.clear()
 
 
 class PendingPose:
