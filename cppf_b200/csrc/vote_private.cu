@@ -91,8 +91,12 @@ __constant__ float2 c_rot_tab[kRotTabP];     // the rotation table in constant m
 template <bool IDX64, bool BINS, bool SLABS>
 __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const VotePParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#if CPPF_VOTE_CONST_TAB
+    float* s_lut = reinterpret_cast<float*>(smem_raw);          // the rotation table lives in constant memory
+#else
     float2* s_tab = reinterpret_cast<float2*>(smem_raw);
     float* s_lut = reinterpret_cast<float*>(s_tab + kRotTabP);
+#endif
     float4* s_queue = reinterpret_cast<float4*>(s_lut + 64);
     unsigned short* s_perm = reinterpret_cast<unsigned short*>(s_queue + (kVoteThreads / 32) * kVoteQueue);
     unsigned* s_grid = reinterpret_cast<unsigned*>(s_perm + kVoteBatch);
@@ -131,7 +135,9 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     const int cells = (SLABS ? min(gx, x0 + pps + 1) - x0 : gx) * gy * gzd;
     const long long acc_off = SLABS ? (long long)x0 * gy * gzd : 0ll;
     const float fx0 = (float)x0;
+#if !CPPF_VOTE_CONST_TAB
     for (int i = threadIdx.x; i < kRotTabP; i += blockDim.x) s_tab[i] = __ldg(prm.rot_tab + i);
+#endif
     if (BINS && threadIdx.x < 64) s_lut[threadIdx.x] = __ldg(prm.lut + threadIdx.x);
     if (BINS && threadIdx.x < 32) {
         int n = prm.n_rots;
@@ -287,13 +293,14 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
             // phase of its circle would decorrelate the splat addresses -- the pairs of a warp share point a and reach the
             // vote peak in the same iterations -- and was measured: fewer ATOMS replays, but a slower kernel overall.)
             const int row = n > 0 ? n * (n - 1) / 2 : 0;
+#if !CPPF_VOTE_CONST_TAB
             const float2* tab = s_tab + row;
+#endif
             const int n_max = __reduce_max_sync(0xffffffffu, n);
 #pragma unroll kVoteUnroll
             for (int i = 0; i < n_max; ++i) {
 #if CPPF_VOTE_CONST_TAB
                 const float2 cs = c_rot_tab[row + i];
-                (void)tab;
 #else
                 const float2 cs = tab[i];
 #endif
@@ -865,7 +872,8 @@ using namespace cppf;
 extern "C" int64_t cppf_vote_scratch_bytes(int gx, int gy, int gz) { return (int64_t)gx * gy * gz * 8; }
 
 static size_t vote_private_fixed_smem() {
-    return (size_t)kRotTabP * 8 + 64 * 4 + (size_t)(kVoteThreads / 32) * kVoteQueue * 16 + (size_t)kVoteBatch * 2;
+    return (CPPF_VOTE_CONST_TAB ? 0 : (size_t)kRotTabP * 8) + 64 * 4 + (size_t)(kVoteThreads / 32) * kVoteQueue * 16 +
+           (size_t)kVoteBatch * 2;
 }
 
 extern "C" int cppf_vote_private_max_cells(void) { return (int)((225 * 1024 - vote_private_fixed_smem() - 1024) / 4); }
