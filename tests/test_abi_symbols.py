@@ -40,3 +40,18 @@ def test_pose_args_struct_mirror_matches_the_compiled_layout():
     assert L.cppf_timing_stages() == 10 and L.cppf_timing_stage_name(3) == b"encode_sample"
     assert L.cppf_pose_workspace_bytes(4096, 0, 60, 17820, 0, 72, 480, 10000) > 5 * 4096 * 4096
     assert L.cppf_vote_routed_supported(64, 64, 64) == 1 and L.cppf_vote_routed_supported(640, 640, 640) == 0
+
+
+def test_missing_library_fails_loudly_and_nothing_falls_back():
+    """No CPU / PyTorch fallback: without the built .so the binding raises on first use."""
+    import subprocess
+    import sys
+    code = ("import os; os.environ['CPPF_B200_LIB'] = '/nonexistent/libcppf_b200.so'\n"
+            "from cppf_b200 import _lib\n"
+            "try:\n"
+            "    _lib.lib()\n"
+            "except RuntimeError as e:\n"
+            "    assert 'missing' in str(e) and 'no CPU or PyTorch fallback' in str(e); print('raised')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "raised" in out.stdout, out.stderr
