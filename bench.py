@@ -436,6 +436,16 @@ def main():
                                "algorithmic_flops_per_launch": algo_flops[k],
                                "note": "canonical fp32 pair-MLP FLOPs against the measured dense bf16 peak; the kernel runs "
                                        "tf32 (half the bf16 rate) in 3 passes for fp32-grade logits"}
+            if k == "vote" and args.votes == "trained_like" and args.path == "fused" and args.n_points == 4096:
+                # the vote phase is measured in atomics/s against a same-box microbenchmark
+                # (tools/atomics_bench.cu -> profiles/r1_atomics_microbench.json); the count per launch is ncu's
+                # predicated-on thread count of the ATOMS instructions of this workload (profiles/r1f_kernels_ncu.md)
+                n_atom = 3.0246e9
+                d["atomics"] = {"per_launch_ncu": n_atom, "achieved": n_atom / t / 1e9, "unit": "G atomics/s",
+                                "peak_shared_u32_trilinear_pattern_microbench": 2813.4, "frac": n_atom / t / 1e9 / 2813.4,
+                                "global_fp32_red_microbench": {"uniform_71KB": 93.9, "concentrated_71KB": 16.4},
+                                "note": "shared-memory u32 atomics of the privatised grid; the microbenchmark peak is the bare "
+                                        "8-corner splat pattern with nothing else in the loop"}
             detail[k] = d
         roof = None
         timed = [k for k in kern if k in algo_bytes]
