@@ -88,3 +88,25 @@ def test_sharded_gather_world2_gloo(n_obj, mode):
 def test_single_process_path_needs_no_process_group():
     out = shard.estimate_sharded(_fake_record, [1.0, 2.0, 3.0])
     np.testing.assert_array_equal(out, np.stack([_fake_record(i) for i in range(3)]))
+
+
+def test_assignment_properties_hypothesis():
+    """Any cost list, any world size: a partition; greedy never exceeds the list-scheduling bound
+    mean load + largest object; round robin deals object i to rank i % world."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.floats(min_value=0.0, max_value=1e9, allow_nan=False), max_size=40), st.integers(1, 9))
+    def check(costs, world):
+        for mode in ("greedy", "round_robin"):
+            parts = shard.assign_objects(costs, world, mode)
+            assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+            assert all(p == sorted(p) for p in parts)
+        g = shard.assign_objects(costs, world, "greedy")
+        if costs:
+            load = max(sum(costs[i] for i in p) for p in g)
+            assert load <= sum(costs) / world + max(costs) + 1e-6 * (1 + sum(costs))
+        rr = shard.assign_objects(costs, world, "round_robin")
+        assert all(i % world == r for r, p in enumerate(rr) for i in p)
+
+    check()
