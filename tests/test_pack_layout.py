@@ -150,3 +150,25 @@ def test_tc_blob_chain_algebra_matches_oracle():
     want = ref_model.pair_mlp(x, {k: v for k, v in sd.items()}).numpy()
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
     assert not heads[:, 105:].any() and not right[:, 36:].any()     # zero padding columns stay zero
+
+
+def test_packed_blobs_follow_the_weights():
+    """The packed operand blobs are cached per module and rebuilt when the weights change in place
+    (load_state_dict, optimiser-style updates) -- a stale blob would silently run old weights."""
+    import torch
+    from cppf_b200 import model
+    torch.manual_seed(1)
+    m = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).eval()
+    b0 = m.tc_blob("cpu")
+    assert m.tc_blob("cpu") is b0                                   # cached
+    ref0 = torch.from_numpy(model.pack_tc_weights(m.state_dict()))
+    assert torch.equal(b0, ref0)
+    other = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141)
+    m.load_state_dict(other.state_dict())                           # in-place copy: version counters move
+    b1 = m.tc_blob("cpu")
+    assert b1 is not b0 and torch.equal(b1, torch.from_numpy(model.pack_tc_weights(other.state_dict())))
+    with torch.no_grad():
+        m.final.weight.mul_(2.0)
+    b2 = m.tc_blob("cpu")
+    assert b2 is not b1 and not torch.equal(b2, b1)
+    assert torch.equal(b2, torch.from_numpy(model.pack_tc_weights(m.state_dict())))
