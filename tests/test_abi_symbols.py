@@ -55,3 +55,23 @@ def test_missing_library_fails_loudly_and_nothing_falls_back():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "raised" in out.stdout, out.stderr
+
+
+def test_dropin_package_shadows_the_reference_module_paths():
+    """`from models.model import PPFEncoder, PointEncoder` / `from models.voting import ...` (nocs/inference.py:3,17)
+    resolve to this implementation when <repo>/dropin is ahead on sys.path; constructors take the reference's kwargs."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from models.model import PPFEncoder, PointEncoder\n"
+            "from models.voting import rot_voting_kernel, backvote_kernel, ppf_kernel, findpeak_kernel\n"
+            "import cppf_b200.model as m\n"
+            "assert PPFEncoder is m.PPFEncoder and PointEncoder is m.PointEncoder\n"
+            "pe = PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32)\n"
+            "ppf = PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141)\n"
+            "assert 'final.weight' in ppf.state_dict() and any(k.startswith('spconvs.0.') for k in pe.state_dict())\n"
+            "assert all(callable(k) for k in (rot_voting_kernel, backvote_kernel, ppf_kernel, findpeak_kernel))\n"
+            "print('ok')\n") % (root, os.path.join(root, "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
