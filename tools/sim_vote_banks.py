@@ -6,8 +6,13 @@ maximum number of lanes per bank (same-address lanes serialise too).  It reprodu
 ATOMS, profiles/r1c_vote_sorted_ncu.md) and was used to evaluate alternatives before spending GPU time: padded strides
 (no gain: the replays are same-CELL collisions, a quarter of the lanes of a splat share their base cell), a hot box
 around the peak (4.4-4.6), two / four grid replicas by lane parity (4.0 / 3.7; two fit in shared memory and were
-adopted: vote 2.92 -> 2.65 ms).  Pure numpy, no GPU."""
+adopted: vote 2.92 -> 2.65 ms).  `--tile A B` regenerates the batches as A x B tiles of the dense pair matrix, the
+layout the kernel uses in dense mode (128 x 16: 3.65 with two replicas, ncu 3.64).  Pure numpy, no GPU."""
 import numpy as np, sys
+TILE = None
+if '--tile' in sys.argv:
+    k = sys.argv.index('--tile')
+    TILE = (int(sys.argv[k + 1]), int(sys.argv[k + 2]))
 sys.path.insert(0,'/root/repo')
 from cppf_b200 import synth
 n=1024
@@ -18,8 +23,13 @@ gx,gy,gz=dims
 rng=np.random.default_rng(0)
 # emulate one CTA batch: 2048 consecutive dense pairs (same a mostly), sorted by n desc, chunks of 32
 def batch_candidates(a, b0):
-    b=np.arange(b0,b0+2048)%n
-    idx=np.stack([np.full(2048,a),b],-1)
+    if TILE is None:
+        b=np.arange(b0,b0+2048)%n
+        idx=np.stack([np.full(2048,a),b],-1)
+    else:                                   # local index = ai * B + bi, as in vote_private_kernel's pair_index
+        A,B=TILE
+        ai=(a+np.arange(A))%n; bi=(b0+np.arange(B))%n
+        idx=np.stack([np.repeat(ai,B),np.tile(bi,A)],-1)
     tr=synth.trained_like_tr(pc,idx)
     mu,nu=tr[:,0],tr[:,1]
     nrot=np.minimum((nu.astype(np.float64)/res*2*np.pi).astype(int),72)
@@ -51,7 +61,7 @@ groups=[]
 for a in range(0,12):
     idx,mu,nu,nrot=batch_candidates(a*37%n, (a*211)%n)
     c,x,y,ok=frames(idx,mu,nu)
-    for w in range(0,2048,32):
+    for w in range(0,len(idx),32):
         sl=slice(w,w+32)
         nm=nrot[sl].max()
         q=[]
