@@ -537,6 +537,26 @@ __global__ void __launch_bounds__(CPPF_BV_THREADS, CPPF_BV_MIN_BLOCKS) backvote_
 // positions of the sub-sampled survivors, one warp per sample: sample j is survivor r_j = (off + j * stride) mod count
 // (the same bijection as rot_hist_kernel), found as the r_j-th set byte of the mask -- block by binary search over the
 // exclusive block offsets, then the warp scans the block 512 bytes at a time (popc of 0/1 bytes + warp prefix)
+// Sub-sample of the survivors (nocs/inference.py:277-281 shuffles them and keeps 10 000): sample j is survivor
+// r_j = (off + j * stride) mod count with stride an odd number next to count / golden ratio that is coprime with count --
+// a bijection of [0, count) whose first m terms are spread evenly over the whole survivor list for every m (a Kronecker
+// sequence).  A fixed prime stride is not: once count exceeds it, the samples fall into count / stride short runs of
+// adjacent survivors, i.e. into pairs anchored in a few patches of the cloud.
+__device__ __forceinline__ unsigned long long subsample_stride(unsigned long long count) {
+    if (count < 3ull) return 1ull;
+    unsigned long long s = (unsigned long long)((double)count * 0.6180339887498949) | 1ull;
+    while (true) {
+        unsigned long long a = count, b = s;
+        while (b != 0ull) {
+            const unsigned long long t = a % b;
+            a = b;
+            b = t;
+        }
+        if (a == 1ull) return s;
+        s += 2ull;
+    }
+}
+
 __global__ void __launch_bounds__(256) select_samples_kernel(const uint8_t* __restrict__ mask,
                                                              const long long* __restrict__ block_offsets, int n_blocks,
                                                              long long n_pairs, const long long* __restrict__ count_ptr,
@@ -545,9 +565,7 @@ __global__ void __launch_bounds__(256) select_samples_kernel(const uint8_t* __re
     const long long count = *count_ptr;
     const long long m = count < max_samples ? count : max_samples;
     const int lane = threadIdx.x & 31;
-    unsigned long long stride = 1000003ull;
-    if (count % 1000003ll == 0) stride = 999983ull;
-    if (m == count) stride = 1ull;
+    const unsigned long long stride = m == count ? 1ull : subsample_stride((unsigned long long)count);
     const unsigned long long off = m == count ? 0ull : offset_seed % (unsigned long long)(count > 0 ? count : 1);
     for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < m;
          j += (long long)gridDim.x * (blockDim.x >> 5)) {
@@ -666,10 +684,7 @@ __global__ void __launch_bounds__(kRotHistThreads) rot_hist_kernel(const RotHist
     const long long m = count < prm.max_samples ? count : prm.max_samples;
     const long long j0 = (long long)blockIdx.x * kRotHistPairs;
     if (j0 >= m) return;
-    // stride: a prime that does not divide count (so j -> (off + j*stride) mod count is a bijection)
-    unsigned long long stride = 1000003ull;
-    if (count % 1000003ll == 0) stride = 999983ull;
-    if (m == count) stride = 1ull;
+    const unsigned long long stride = m == count ? 1ull : subsample_stride((unsigned long long)count);
     const unsigned long long off = m == count ? 0ull : prm.offset_seed % (unsigned long long)count;
     int mono = 1;
     for (int s = threadIdx.x; s < prm.n_bins; s += blockDim.x) {

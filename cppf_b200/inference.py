@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import preprocess
-from .pipeline import PoseEstimator
+from .pipeline import NoSurvivorsError, PoseEstimator
 
 SYNSET_NAMES = ["BG", "bottle", "bowl", "camera", "can", "laptop", "mug"]          # nocs/inference.py:73-81
 
@@ -20,8 +20,9 @@ def estimate_image(depth, masks, class_ids: Sequence[int], estimators: Dict[str,
                    intrinsics=preprocess.NOCS_INTRINSICS, synset_names: Sequence[str] = SYNSET_NAMES, seed: int = 0,
                    jitter: bool = True, bboxes: Optional[np.ndarray] = None, bbox_mask: bool = False, orient_normals: bool = False):
     """depth [H,W] uint16 (mm) and masks [H,W,K] bool, numpy or CUDA tensors; class_ids [K].
-    -> dict(pred_RTs float32 [K,4,4], pred_scales float32 [K,3], n_points [K]) like the arrays the reference pickles
-    (nocs/inference.py:113-118, 336-345).  Instances with fewer points than knn keep the identity pose.
+    -> dict(pred_RTs float32 [K,4,4], pred_scales float32 [K,3], n_points [K], valid bool [K]) like the arrays the reference
+    pickles (nocs/inference.py:113-118, 336-345).  Instances with fewer points than knn, and instances for which no pair
+    voted for the winning centre, keep the identity pose and are flagged valid = False.
     All objects of the image are enqueued before the first pose record is read."""
     any_est = next(iter(estimators.values()))
     dev = any_est.device
@@ -31,6 +32,7 @@ def estimate_image(depth, masks, class_ids: Sequence[int], estimators: Dict[str,
     RTs = np.tile(np.eye(4, dtype=np.float32), (k, 1, 1))                       # :113-116
     scales = np.ones((k, 3), dtype=np.float32)                                  # :117
     n_points = np.zeros(k, np.int64)
+    valid = np.zeros(k, bool)
     pending = []
     for i in range(k):
         m = masks_d[:, :, i].clone()
@@ -54,6 +56,9 @@ def estimate_image(depth, masks, class_ids: Sequence[int], estimators: Dict[str,
         nrm = preprocess.estimate_normals(pc, cfg.knn, orient_normals)          # :142
         pending.append((i, est.estimate_fused(pc, nrm, seed=seed * 1000003 + i, sync=False)))      # :174-339
     for i, p in pending:
-        out = p.result() if hasattr(p, "result") else p
-        RTs[i], scales[i] = out["RT"], out["scales"]                            # :336-339
-    return {"pred_RTs": RTs, "pred_scales": scales, "n_points": n_points}
+        try:
+            out = p.result() if hasattr(p, "result") else p
+        except NoSurvivorsError:
+            continue
+        RTs[i], scales[i], valid[i] = out["RT"], out["scales"], True            # :336-339
+    return {"pred_RTs": RTs, "pred_scales": scales, "n_points": n_points, "valid": valid}

@@ -396,15 +396,15 @@ def pack_pe_weights(sd) -> np.ndarray:
 
 class PointEncoder(nn.Module):
     """Drop-in for reference ``models/model.py:34-77`` (num_layers=1 as at every call site,
-    nocs/inference.py:82).  O(N k) work; this round it is composed from torch CUDA ops on
-    the object's device (SURVEY.md section 8 row a5 / f1 schedules the fused kNN+SPRIN kernel next)."""
+    nocs/inference.py:82).  Runs as two sm_100a kernels (csrc/point_encoder.cu): ``cppf_knn`` (exact k nearest
+    neighbours without the N x N matrix) and ``cppf_point_encode`` (SPRIN convolution + LayerNorm + global max, one warp
+    per point).  The module only holds the parameters under the reference's state_dict keys; there is no eager path."""
 
     def __init__(self, k, spfcs, out_dim, num_layers=2, num_nbr_feats=2) -> None:
         super().__init__()
         if num_layers != 1:
             raise NotImplementedError("every reference call site uses num_layers=1 (nocs/inference.py:82)")
         self.k = k
-        self.use_fused = True           # False forces the torch-op composition (used by tests as a cross-check)
         self.spconvs = nn.ModuleList([SparseSO3Conv(32, num_nbr_feats, out_dim, *spfcs)])
         self.aggrs = nn.ModuleList([GlobalInfoProp(out_dim, out_dim // 4)])
 
@@ -460,29 +460,9 @@ class PointEncoder(nn.Module):
     def forward_nbrs(self, pc, pc_normal, nbrs_idx):
         """models/model.py:63-77.  pc,pc_normal [B,N,3], nbrs_idx [B,N,K] -> [B,N,out+out//4]."""
         _no_grad_only(pc, pc_normal)
-        if self.use_fused and pc.is_cuda and pc.shape[0] == 1 and self._fused_ok():
+        if pc.is_cuda and pc.shape[0] == 1 and self._fused_ok():
             return self.encode_fused(pc[0], pc_normal[0], nbrs_idx[0])[None]
-        with torch.no_grad():       # generic shapes (other spfcs / k > 64 / batches): composed from torch ops on the device
-            conv, aggr = self.spconvs[0], self.aggrs[0]
-            b_idx = torch.arange(pc.shape[0], device=pc.device)[:, None, None]
-            nb = pc[b_idx, nbrs_idx]                                             # [B,N,K,3] absolute coords
-            centre = pc.unsqueeze(-2)
-            nbr_feat = torch.cat([(nb - centre).norm(dim=-1, keepdim=True),
-                                  (pc_normal[b_idx, nbrs_idx] * pc_normal.unsqueeze(-2)).sum(-1, keepdim=True)], -1)
-            # rotation-invariant edge features (models/sprin.py:40-60)
-            mean = nb.mean(-2, keepdim=True)
-            l1, l2, l3 = mean - nb, nb - centre, centre - mean
-            n1, n2 = l1.norm(dim=-1, keepdim=True), l2.norm(dim=-1, keepdim=True)
-            n3 = l3.norm(dim=-1, keepdim=True).expand_as(n2)
-            ri = torch.cat([n1, n2, n3,
-                            (l1 * l2).sum(-1, keepdim=True) / (n1 * n2 + 1e-7),
-                            (l2 * l3).sum(-1, keepdim=True) / (n2 * n3 + 1e-7),
-                            (l3 * l1).sum(-1, keepdim=True) / (n3 * n1 + 1e-7)], -1)
-            kern = conv.kernel(ri)                                               # [B,N,K,rank]
-            contracted = torch.einsum("bnkr,bnki->bnri", kern, nbr_feat).flatten(-2)
-            out = conv.outnet(contracted)
-            if conv.layer_norm is not None:
-                out = conv.layer_norm(out)
-            tran = aggr.linear(out)
-            glob = tran.max(-2, keepdim=True)[0].expand(*out.shape[:-1], tran.shape[-1])
-            return torch.cat([out, glob], -1)
+        raise NotImplementedError(
+            "cppf_b200.PointEncoder runs only through its sm_100a kernel (csrc/point_encoder.cu): CUDA tensors, batch 1, "
+            "k <= 64, spfcs=[32,64,32,32], rank 32, out_dim 32 with LayerNorm -- the configuration of every reference call "
+            "site (nocs/inference.py:82).  There is no eager fallback.")

@@ -72,19 +72,26 @@ def release_workspaces():
     rowsplit._PAIRS_CACHE.clear()
 
 
-class PendingPose:
-    """A pose whose kernels are enqueued; .result() waits for its record and runs the host tail."""
+class NoSurvivorsError(RuntimeError):
+    """No pair voted for the winning centre (degenerate input): the reference's script would carry NaNs into the pose
+    (empty tensors through nocs/inference.py:236-335); every entry point here raises instead."""
 
-    def __init__(self, est, record_host, done, n_dirs, keep=(), staged=False):
+
+class PendingPose:
+    """A pose whose kernels are enqueued; .result() waits for its record and runs the host tail.  The vote-grid dims the
+    flat argmax is unravelled with travel WITH the pending pose (the staged path knows them when it enqueues, the one-call
+    path reads them from its own record), never through the estimator, so poses may be read in any order."""
+
+    def __init__(self, est, record_host, done, n_dirs, keep=(), staged=False, dims=None):
         self.est, self.record_host, self.done, self.n_dirs, self._keep, self.staged = est, record_host, done, n_dirs, keep, staged
+        self.dims = dims
 
     def result(self):
         self.done.synchronize()
         r = self.record_host.numpy()
-        if self.staged:
-            self._keep = ()
-            return self.est._pose_from_record(r, self.n_dirs)
         self._keep = ()
+        if self.staged:
+            return self.est._pose_from_record(r, self.n_dirs, self.dims)
         return self.est._pose_from_record16(r, self.n_dirs)
 
 
@@ -148,7 +155,7 @@ class PoseEstimator:
         nrm = torch.as_tensor(nrm_host).to(dev, non_blocking=True)
         if isinstance(pc_host, torch.Tensor) and pc_host.is_cuda:                   # cloud already resident in HBM
             corner = pc.min(0)[0]
-            dims = tuple(int(v) for v in (((pc.max(0)[0] - corner) / cfg.res).int() + 1).cpu())
+            dims = voting.grid_dims(pc, corner, cfg.res)
         else:
             corner_np, dims = vote_grid_geometry(np.asarray(pc_host), cfg.res)      # :194-195
             corner = torch.from_numpy(corner_np).to(dev, non_blocking=True)
@@ -188,7 +195,7 @@ class PoseEstimator:
         kept = kept[:n_kept]
         out = {"T": T_est, "n_survivors": n_kept, "grid_dims": dims, "argmax": flat}
         if n_kept == 0:
-            raise RuntimeError("no pair voted for the winning centre (degenerate input)")
+            raise NoSurvivorsError("no pair voted for the winning centre (degenerate input)")
 
         # ---- second pass on the survivors (:236-256): rotation / aux / scale heads
         R0 = 2 * B
@@ -257,18 +264,20 @@ class PoseEstimator:
 
 
     # ------------------------------------------------------------------ fused path
-    def _pose_from_record(self, rec, n_dirs):
+    def _pose_from_record(self, rec, n_dirs, dims):
         """Host tail of nocs/inference.py:305-339 from one small device->host record:
-        rec = [flat, best_up, (best_right), scale_sum x3, count, S_up, S_right, corner x3] (float64)."""
+        rec = [flat, best_up, (best_right), scale_sum x3, count, S_up, S_right, corner x3] (float64);
+        dims = the vote-grid dims of THIS object."""
         cfg = self.cfg
         flat = int(rec[0])
         bests = [int(rec[1 + j]) for j in range(n_dirs)]
         st = rec[1 + n_dirs:7 + n_dirs]
         corner = rec[7 + n_dirs:10 + n_dirs]
-        dims = self._last_dims
         cell = np.array(np.unravel_index(flat, dims))
         T = corner + cell * cfg.res                                                 # :209
-        cnt = max(st[3], 1.0)
+        if st[3] <= 0:
+            raise NoSurvivorsError("no pair voted for the winning centre (degenerate input)")
+        cnt = st[3]
         up = self.sphere_np[bests[0]] * (-1.0 if st[4] < 0 else 1.0)                # :299-302
         if cfg.regress_right:
             right = self.sphere_np[bests[1]] * (-1.0 if st[5] < 0 else 1.0)
@@ -287,7 +296,7 @@ class PoseEstimator:
         RT[:3, :3] = R * sn
         RT[:3, 3] = T
         return dict(RT=RT, scales=(pred_scale / sn).astype(np.float32), up=up, right=right, T_host=T, pred_scale=pred_scale,
-                    n_survivors=int(st[3]), argmax_flat=flat, best_bins=bests,
+                    n_survivors=int(st[3]), argmax_flat=flat, best_bins=bests, grid_dims=tuple(dims),
                     record=np.concatenate([[0.0, st[3]], pred_scale, R.reshape(-1), T]).astype(np.float32))
 
     # ------------------------------------------------------------------ one call per object
@@ -314,7 +323,7 @@ class PoseEstimator:
         global-reduction kernel of the staged path.  Costs one small device->host copy for a CUDA tensor."""
         if isinstance(pc_in, torch.Tensor) and pc_in.is_cuda:
             lo = pc_in.min(0)[0]
-            dims = tuple(int(v) for v in (((pc_in.max(0)[0] - lo) / self.cfg.res).int() + 1).cpu())
+            dims = voting.grid_dims(pc_in, lo, self.cfg.res)
         else:
             _, dims = vote_grid_geometry(np.asarray(pc_in), self.cfg.res)
         cells = dims[0] * dims[1] * dims[2]
@@ -389,9 +398,8 @@ class PoseEstimator:
     def _pose_from_record16(self, r, n_dirs):
         if r[15] != 0:
             raise RuntimeError("vote grid larger than the capacity given to cppf_pose_fused (status %d)" % int(r[15]))
-        self._last_dims = tuple(int(v) for v in r[12:15])
         old = np.concatenate([[r[0]], r[1:1 + n_dirs], r[3:9], r[9:12]])
-        return self._pose_from_record(old, n_dirs)
+        return self._pose_from_record(old, n_dirs, tuple(int(v) for v in r[12:15]))
 
     @torch.no_grad()
     def estimate_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, return_debug: bool = False,
@@ -418,11 +426,10 @@ class PoseEstimator:
         nrm = torch.as_tensor(nrm_in).to(dev, non_blocking=True)
         if isinstance(pc_in, torch.Tensor) and pc_in.is_cuda:
             corner = pc.min(0)[0]
-            dims = tuple(int(v) for v in (((pc.max(0)[0] - corner) / cfg.res).int() + 1).cpu())
+            dims = voting.grid_dims(pc, corner, cfg.res)
         else:
             corner_np, dims = vote_grid_geometry(np.asarray(pc_in), cfg.res)
             corner = torch.from_numpy(corner_np).to(dev, non_blocking=True)
-        self._last_dims = dims
         if idxs is None and cfg.n_pairs > 0:
             g = torch.Generator(device=dev).manual_seed(seed)
             idxs = torch.randint(0, n, (cfg.n_pairs, 2), generator=g, device=dev, dtype=torch.int32)
@@ -474,8 +481,8 @@ class PoseEstimator:
             host.copy_(rec_dev, non_blocking=True)
             done = torch.cuda.Event()
             done.record()
-            return PendingPose(self, host, done, nd, keep=(rec_dev,), staged=True)
-        out = self._pose_from_record(rec_dev.cpu().numpy(), nd)
+            return PendingPose(self, host, done, nd, keep=(rec_dev,), staged=True, dims=dims)
+        out = self._pose_from_record(rec_dev.cpu().numpy(), nd, dims)
         if return_debug:
             out.update(grid=grid, bins=bins, tail=tail, mask=mask, pos=pos, count=cnt, feat=feat, idxs=idxs, table=table)
         return out

@@ -67,9 +67,8 @@ def _steps(est, pc, nrm, seed, uniforms, inject_bins, rank, world, out):
     cfg, dev = est.cfg, est.device
     n = pc.shape[0]
     corner = pc.min(0)[0]
-    dims = tuple(int(v) for v in (((pc.max(0)[0] - corner) / cfg.res).int() + 1).cpu())     # nocs/inference.py:194-195
+    dims = voting.grid_dims(pc, corner, cfg.res)                                            # nocs/inference.py:194-195
     cells = dims[0] * dims[1] * dims[2]
-    est._last_dims = dims
     lo, hi = row_block(n, world, rank)
     idxs = _cached_block_pairs(n, lo, hi, dev)
     sl = slice(lo * n, hi * n)
@@ -118,7 +117,7 @@ def _steps(est, pc, nrm, seed, uniforms, inject_bins, rank, world, out):
     stats = fast.survivor_stats(pc, nrm, tail, idxs, pos, cnt, est.sphere, bests[0], bests[1] if cfg.regress_right else None)
     yield stats                                                     # exchange 3: survivor statistics
     rec = torch.cat([flat.double()] + [b.double() for b in bests] + [stats, corner.double()])
-    out.update(record=rec, n_dirs=n_dirs, grid=grid, bins=bins, mask=mask, rows=(lo, hi))
+    out.update(record=rec, n_dirs=n_dirs, grid=grid, bins=bins, mask=mask, rows=(lo, hi), dims=dims)
 
 
 def _prepare(est, pc_in, nrm_in):
@@ -141,7 +140,7 @@ def estimate_rowsplit(est, pc_in, nrm_in, seed: int = 0, uniforms=None, inject_b
     for t in _steps(est, pc, nrm, seed, uniforms, inject_bins, rank, world, out):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    pose = est._pose_from_record(out["record"].cpu().numpy(), out["n_dirs"])
+    pose = est._pose_from_record(out["record"].cpu().numpy(), out["n_dirs"], out["dims"])
     if return_debug:
         pose.update(grid=out["grid"], bins=out["bins"], mask=out["mask"], rows=out["rows"])
     return pose
@@ -174,7 +173,7 @@ def estimate_rowsplit_local(est, pc_in, nrm_in, world: int, seed: int = 0, unifo
     for r in recs[1:]:
         if not np.array_equal(r, recs[0]):
             raise RuntimeError("ranks disagree on the pose record")
-    pose = est._pose_from_record(recs[0], outs[0]["n_dirs"])
+    pose = est._pose_from_record(recs[0], outs[0]["n_dirs"], outs[0]["dims"])
     if return_debug:
         pose.update(grid=outs[0]["grid"], bins=torch.cat([o["bins"] for o in outs]), mask=torch.cat([o["mask"] for o in outs]))
     return pose

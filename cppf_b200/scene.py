@@ -72,10 +72,10 @@ def estimate_scene(point_encoder, ppf_encoder, pc, nrm, high_res_pc=None, high_r
         feat = point_encoder.encode_fused(high_res_pc, high_res_nrm)[subset]
     else:
         feat = point_encoder.encode_fused(pc, nrm)
-    preds = ppf_encoder.forward_with_idx(pc, nrm, feat, idxs)[0]                                   # [P,9]
+    preds = ppf_encoder.forward_with_idx(pc, nrm, feat, idxs)                                      # [P,9], unbatched like models/model.py:117-137
     preds_tr = preds[:, :2].contiguous()
     corner = pc.min(0)[0]                                                                          # cell 8
-    dims = tuple(int(v) for v in (((pc.max(0)[0] - corner) / res).int() + 1).cpu())
+    dims = voting.grid_dims(pc, corner, res)
     grid = torch.zeros(dims, dtype=torch.float32, device=dev)
     voting.ppf_vote(pc, preds_tr, idxs, grid, corner, res, num_rots, True)
     smoothed = gaussian_filter(grid, 1.0)                                                          # cell 9
@@ -96,7 +96,7 @@ def estimate_scene(point_encoder, ppf_encoder, pc, nrm, high_res_pc=None, high_r
         sel = sel[keep_pair].contiguous()
         if sel.shape[0] == 0:
             continue
-        pm = ppf_encoder.forward_with_idx(pc, nrm, feat, sel)[0]
+        pm = ppf_encoder.forward_with_idx(pc, nrm, feat, sel)
         rot = pm[:, 2].contiguous()
         sub = sel
         if sel.shape[0] > rot_subsample:

@@ -69,18 +69,15 @@ def gather_records(local_ids: Sequence[int], local_records: np.ndarray, n_total:
     block = block.to(dev)
     blocks = [torch.empty_like(block) for _ in range(world)]
     dist.all_gather(blocks, block, group=group)
-    seen = np.zeros(n_total, bool)
-    for b in blocks:
-        b = b.cpu().numpy()
-        for row in b:
-            i = int(row[0])
-            if i >= 0:
-                if seen[i]:
-                    raise RuntimeError(f"object {i} was processed by two ranks")
-                seen[i] = True
-                out[i] = row[1:]
-    if not seen.all():
-        raise RuntimeError(f"objects {np.nonzero(~seen)[0].tolist()} were processed by no rank")
+    rows = torch.cat(blocks).cpu().numpy()                       # one device->host copy of the [world * cap, 18] block
+    rows = rows[rows[:, 0] >= 0]
+    ids = rows[:, 0].astype(np.int64)
+    hits = np.bincount(ids, minlength=n_total)
+    if (hits > 1).any():
+        raise RuntimeError(f"objects {np.nonzero(hits > 1)[0].tolist()} were processed by two ranks")
+    if (hits[:n_total] == 0).any() or len(hits) > n_total:
+        raise RuntimeError(f"objects {np.nonzero(hits[:n_total] == 0)[0].tolist()} were processed by no rank")
+    out[ids] = rows[:, 1:]
     return out
 
 

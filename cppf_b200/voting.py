@@ -65,6 +65,14 @@ def _idx(x, device=None):
 
 
 # ------------------------------------------------------------------------- functional API
+def grid_dims(pc, corner, res):
+    """Vote-grid dims of a CUDA cloud, nocs/inference.py:195: ``int((max - min) / res) + 1`` per axis with a TRUE float32
+    division like NumPy's (and like geom_kernel on the device).  ``tensor / python_scalar`` on CUDA multiplies by the
+    rounded reciprocal instead, which can differ by one ulp and flip the truncation; a device-tensor divisor does not."""
+    ext = pc.max(0)[0] - corner
+    return tuple(int(v) for v in (torch.div(ext, torch.full_like(ext, float(res))).int() + 1).cpu())
+
+
 def ppf_vote(points, mu_nu, idxs, grid, corner, res, n_rots=72, adaptive=True, probs=None):
     """Centre voting (models/voting.py:8-66) accumulated into `grid` [gx,gy,gz] in place.
     idxs=None enumerates all N^2 ordered pairs."""

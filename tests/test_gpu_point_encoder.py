@@ -1,6 +1,6 @@
 """GPU parity of the fused point encoder (csrc/point_encoder.cu): exact kNN selection and the SPRIN
 convolution of models/model.py:46-77 + models/sprin.py:40-107, against fixtures minted from the
-reference modules (tests/golden/encoder_bottle.npz) and against the torch-op composition."""
+reference modules (tests/golden/encoder_bottle.npz) and against the oracle's restatement (oracle/ref_model.py)."""
 import os
 
 import numpy as np
@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from cppf_b200 import model, synth
+from oracle import ref_model
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -36,7 +37,7 @@ def test_fused_forward_nbrs_matches_reference_fixture():
 
 
 @pytest.mark.parametrize("n,k,seed", [(2048, 60, 0), (333, 20, 1), (100, 64, 2), (70, 33, 3)])
-def test_fused_encoder_equals_torch_composition(n, k, seed):
+def test_fused_encoder_equals_oracle_restatement(n, k, seed):
     torch.manual_seed(seed)
     pe = model.PointEncoder(k=k, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(DEV).eval()
     with torch.no_grad():
@@ -51,9 +52,9 @@ def test_fused_encoder_equals_torch_composition(n, k, seed):
     nbrs = pe.knn(pc)
     with torch.no_grad():
         fused = pe.forward_nbrs(pc[None], nrm[None], nbrs[None])[0]
-        pe.use_fused = False
-        ref = pe.forward_nbrs(pc[None], nrm[None], nbrs[None])[0]
-    np.testing.assert_allclose(fused.cpu().numpy(), ref.cpu().numpy(), rtol=2e-4, atol=5e-5)
+    sd = {kk: v.cpu() for kk, v in pe.state_dict().items()}
+    ref = ref_model.point_encode_nbrs(pc.cpu(), nrm.cpu(), nbrs.cpu(), sd)      # models/model.py:63-77 restated (oracle)
+    np.testing.assert_allclose(fused.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=5e-5)
     assert torch.equal(fused[:, 32:], fused[:1, 32:].expand(n, 8))              # the global-max columns are shared
 
 

@@ -74,7 +74,7 @@ class _GeometricHead(torch.nn.Module):
         out[:, 2] = ang
         out[:, 4] = torch.where(nrm[a][:, 1] * 0 + (pc[a] - c)[:, 1] > 0, 3.0, -3.0)
         out[:, 6:] = 0.0                                                      # exp(0) * scale_mean * 2
-        return out[None]
+        return out                                                            # [P,9] like the real forward_with_idx
 
 
 def test_estimate_scene_finds_both_objects():

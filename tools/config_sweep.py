@@ -64,7 +64,7 @@ if "4" in which:
     pcd, nd = torch.from_numpy(pc).to(dev), torch.from_numpy(nrm).to(dev)
     res = {}
     ms = timed(lambda: res.update(est.enqueue_fused(pcd, nd, seed=0).result()), 5)
-    out["config4_sunrgbd_like_dense_8192"] = {"ms_per_object": ms, "pairs_per_s": n * n / ms * 1e3, "grid_dims": list(est._last_dims),
+    out["config4_sunrgbd_like_dense_8192"] = {"ms_per_object": ms, "pairs_per_s": n * n / ms * 1e3, "grid_dims": list(res["grid_dims"]),
                                               "n_survivors": res["n_survivors"]}
     release_workspaces()
     torch.cuda.empty_cache()
@@ -88,7 +88,9 @@ if "3" in which:
         def batch():
             pend = [e.enqueue_fused(p, q, seed=s, inject_bins=injs[s], max_cells=1, routed_max_cells=64 ** 3)
                     for s, (e, (p, q)) in enumerate(zip(ests, dclouds))]
-            return [x.result() for x in pend]
+            last.update(pend[0].result())
+            return [x.result() for x in pend[1:]]
+        last = {}
         ms = timed(batch, 2)
         for e in ests:
             e.timing = timing
@@ -99,7 +101,7 @@ if "3" in which:
             e.timing = None
         L.cppf_timing_destroy(timing)
         out["config3_six_categories_64cube_dense_4096_" + tag] = {
-            "ms_per_batch": ms, "ms_per_object": ms / 6, "pairs_per_s": 6 * n * n / ms * 1e3, "grid_dims": list(ests[0]._last_dims),
+            "ms_per_batch": ms, "ms_per_object": ms / 6, "pairs_per_s": 6 * n * n / ms * 1e3, "grid_dims": list(last["grid_dims"]),
             "stage_ms_per_object": {nm: acc[i] / max(calls, 1) for i, nm in enumerate(names)}}
         del injs
 print(json.dumps(out))
