@@ -72,12 +72,16 @@ SIGNATURES = {
     "cppf_pose_args_bytes": (_i, []),
     "cppf_pose_workspace_bytes": (_i64, [_i, _i64, _i, _i, _i, _i, _i, _i64]),
     "cppf_pose_fused": (_i, [_p, _p]),
+    "cppf_pose_batch": (_i, [_p, _i, _i, _i, _p]),
     "cppf_timing_create": (_p, []),
     "cppf_timing_destroy": (None, [_p]),
     "cppf_timing_reserve": (_i, [_p, _i]),
     "cppf_timing_stages": (_i, []),
     "cppf_timing_stage_name": (C.c_char_p, [_i]),
     "cppf_timing_collect": (_i, [_p, _p]),
+    "cppf_vote_count": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p, _p]),
+    "cppf_peak_shared_atomics": (_i, [_i, _i, _i, _i, _i, _p, _p]),
+    "cppf_peak_global_red": (_i, [_i, _i, _i, _i, _p, _p]),
 }
 
 
@@ -89,7 +93,7 @@ class PoseArgs(C.Structure):
         ("uniforms", _p), ("inject_bins", _p), ("workspace", _p), ("record", _p), ("timing", _p),
         ("n_pairs", _i64), ("workspace_bytes", _i64), ("rot_subsample", _i64), ("seed", C.c_uint64),
         ("n_points", _i), ("idx_is_64", _i), ("knn", _i), ("n_rots", _i), ("adaptive", _i), ("regress_right", _i),
-        ("n_sphere", _i), ("inject_cols", _i), ("max_cells", _i), ("routed_max_cells", _i),
+        ("n_sphere", _i), ("inject_cols", _i), ("max_cells", _i), ("routed_max_cells", _i), ("sample_pairs", _i),
         ("res", _f), ("tol", _f), ("cos_thr", _f),
     ]
 

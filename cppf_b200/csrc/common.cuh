@@ -39,10 +39,27 @@ __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return {a.x - b.x, a.y - b
 __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 __device__ __forceinline__ f3 operator*(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 __device__ __forceinline__ f3 operator/(f3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
-__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// dot / length / cross / circle offset in the exact operation order nvcc 12.9 gives the reference's helper_math.cuh
+// expressions inside models/voting.py (read off the SASS of oracle/_ref/ref_{ppf_voting,backvote,rot_voting}.cubin, which
+// agree with each other): dot = fma(z, z, fma(x, x, y * y)); a cross component a.y * b.z - a.z * b.y = fma(a.y, b.z,
+// -(a.z * b.y)); cos * x + sin * y = fma(x, cos, y * sin).  Written with explicit intrinsics so that no other contraction
+// can be chosen here: decisions taken on these values (in / out of the grid, within tol of the centre) are bit-exact
+// with the reference kernels.
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y))); }
 __device__ __forceinline__ float len3(f3 a) { return sqrtf(dot3(a, a)); }
 __device__ __forceinline__ f3 cross3(f3 a, f3 b) {
-    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+    return {__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+            __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x))};
+}
+// c = a - ab * proj_len  (models/voting.py:23,89): one FFMA in the reference's SASS
+__device__ __forceinline__ f3 foot_point(f3 a, f3 ab, float mu) {
+    return {__fmaf_rn(mu, -ab.x, a.x), __fmaf_rn(mu, -ab.y, a.y), __fmaf_rn(mu, -ab.z, a.z)};
+}
+// x = co / (length(co) + 1e-7) * odist  (:28,94): the division is inside pair_frame, this is the single multiply
+__device__ __forceinline__ f3 scale3(f3 e, float s) { return {__fmul_rn(e.x, s), __fmul_rn(e.y, s), __fmul_rn(e.z, s)}; }
+// offset = cos(angle) * x + sin(angle) * y  (models/voting.py:34,100,141)
+__device__ __forceinline__ f3 circle_offset(f3 x, f3 y, float c, float s) {
+    return {__fmaf_rn(x.x, c, __fmul_rn(y.x, s)), __fmaf_rn(x.y, c, __fmul_rn(y.y, s)), __fmaf_rn(x.z, c, __fmul_rn(y.z, s))};
 }
 __device__ __forceinline__ f3 ld3(const float* __restrict__ p, int64_t i) {
     return {__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)};
@@ -89,17 +106,26 @@ __device__ __forceinline__ void pair_ab(const void* __restrict__ idx, int64_t p,
 // The double-precision islands of the CUDA-C strings (`1e-7` literals) are kept:
 // the degenerate test is a double compare, the normaliser a double sum rounded to float.
 __device__ __forceinline__ bool pair_frame(f3 a, f3 b, f3& ab, f3& ex) {
-    ab = a - b;
+    ab = {__fadd_rn(a.x, -b.x), __fadd_rn(a.y, -b.y), __fadd_rn(a.z, -b.z)};
     const float len = len3(ab);
     if ((double)len < 1e-7) return false;
-    ab = ab / (float)((double)len + 1e-7);
-    f3 co = {0.f, -ab.z, ab.y};
-    float lc = len3(co);
-    if ((double)lc < 1e-7) {
+    const float den = (float)((double)len + 1e-7);
+    ab = {__fdiv_rn(ab.x, den), __fdiv_rn(ab.y, den), __fdiv_rn(ab.z, den)};
+    // co = (0, -ab.z, ab.y); the reference evaluates length(co) twice and nvcc compiles the two differently: the
+    // degenerate test on sqrt(z*z + y*y) (two rounded products, one add), the normaliser on sqrt(fma(y, y, z*z))
+    const float yy = __fmul_rn(ab.y, ab.y);
+    const float lt = sqrtf(__fadd_rn(__fmul_rn(ab.z, ab.z), yy));
+    f3 co;
+    float lc2;
+    if ((double)lt < 1e-7) {
         co = {-ab.y, ab.x, 0.f};
-        lc = len3(co);
+        lc2 = __fmaf_rn(ab.x, ab.x, yy);
+    } else {
+        co = {0.f, -ab.z, ab.y};
+        lc2 = __fmaf_rn(ab.y, ab.y, __fmul_rn(ab.z, ab.z));
     }
-    ex = co / (float)((double)lc + 1e-7);
+    const float dc = (float)((double)sqrtf(lc2) + 1e-7);
+    ex = {__fdiv_rn(co.x, dc), __fdiv_rn(co.y, dc), __fdiv_rn(co.z, dc)};
     return true;
 }
 

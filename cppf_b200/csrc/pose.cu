@@ -16,6 +16,8 @@
 
 #include <math.h>
 
+#include <mutex>
+#include <thread>
 #include <vector>
 
 namespace cppf {
@@ -111,6 +113,17 @@ __global__ void __launch_bounds__(256) inject_bins_kernel(uint8_t* __restrict__ 
     }
 }
 
+// nocs/inference.py:177: point_idxs = np.random.randint(0, N, (P, 2)) -- drawn on the device: pair p takes two words of
+// Philox4x32-10(counter = (p, 0, 0x70616972 "pair", 0), key = seed), each mapped to [0, N) by a multiply-shift.
+__global__ void __launch_bounds__(256) sample_pairs_kernel(int2* __restrict__ idx, long long n_pairs, int n_points,
+                                                           unsigned long long seed) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (long long)gridDim.x * blockDim.x) {
+        const uint4 w = philox4x32_10(make_uint4((uint32_t)p, (uint32_t)((unsigned long long)p >> 32), 0x70616972u, 0u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        idx[p] = make_int2((int)__umulhi(w.x, (uint32_t)n_points), (int)__umulhi(w.y, (uint32_t)n_points));
+    }
+}
+
 // record[16] (double): 0 argmax flat | 1 best up bin | 2 best right bin (-1) | 3..5 sum log-scale | 6 survivors |
 //                      7 S_up | 8 S_right | 9..11 corner | 12..14 grid dims | 15 status
 __global__ void pack_record_kernel(const Geom* geom, const long long* flat, const long long* best, const double* stats,
@@ -158,11 +171,12 @@ struct Workspace {
     long long* count;
     unsigned char* pool;
     size_t pool_bytes;
+    int2* idx_gen;              // pairs drawn on the device (sample_pairs): [n_pairs] when the object is not dense
     size_t bytes;
 };
 
 static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells, int n_rots,
-                       int n_sphere, int64_t rot_subsample) {
+                       int n_sphere, int64_t rot_subsample, bool dense) {
     const int cap_cells = max_cells > routed_max_cells ? max_cells : routed_max_cells;
     Carver c{reinterpret_cast<unsigned char*>(base)};
     Workspace w;
@@ -186,6 +200,7 @@ static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int m
     w.count = c.take<long long>(1);
     w.pool_bytes = routed_max_cells > 0 ? (size_t)routed_pool_bytes(n_pairs, n_rots) : 0;
     w.pool = c.take<unsigned char>(w.pool_bytes);
+    w.idx_gen = c.take<int2>(dense ? 0 : (size_t)n_pairs);
     w.bytes = (c.off + 255) & ~(size_t)255;
     return w;
 }
@@ -217,8 +232,9 @@ extern "C" int cppf_pose_args_bytes(void) { return (int)sizeof(cppf_pose_args); 
 
 extern "C" int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells,
                                              int n_rots, int n_sphere, int64_t rot_subsample) {
-    if (n_pairs <= 0) n_pairs = (int64_t)n_points * n_points;
-    return (int64_t)carve(nullptr, n_points, n_pairs, knn, max_cells, routed_max_cells, n_rots, n_sphere, rot_subsample).bytes;
+    const bool dense = n_pairs <= 0 || n_pairs == (int64_t)n_points * n_points;
+    if (dense) n_pairs = (int64_t)n_points * n_points;
+    return (int64_t)carve(nullptr, n_points, n_pairs, knn, max_cells, routed_max_cells, n_rots, n_sphere, rot_subsample, dense).bytes;
 }
 
 extern "C" void* cppf_timing_create(void) { return new Timing(); }
@@ -264,12 +280,18 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (a == nullptr || a->struct_bytes != sizeof(cppf_pose_args)) return (int)cudaErrorInvalidValue;
     const int n = a->n_points;
-    const int64_t n_pairs = a->idx ? a->n_pairs : (int64_t)n * n;
+    const bool sampled = a->sample_pairs != 0;
+    if (sampled && a->idx != nullptr) return (int)cudaErrorInvalidValue;
+    const bool dense = a->idx == nullptr && !sampled;
+    const int64_t n_pairs = dense ? (int64_t)n * n : a->n_pairs;
     if (n <= 0 || n_pairs <= 0 || a->knn <= 0 || a->knn > 64 || a->knn > n) return (int)cudaErrorInvalidValue;
     if (a->max_cells <= 0 || a->max_cells > cppf_vote_private_max_cells()) return (int)cudaErrorInvalidValue;
     if (a->n_sphere <= 0 || a->record == nullptr || a->workspace == nullptr) return (int)cudaErrorInvalidValue;
     if (a->routed_max_cells < 0 || a->routed_max_cells > kMaxSlabs * slab_cap_cells()) return (int)cudaErrorInvalidValue;
-    const Workspace w = carve(a->workspace, n, n_pairs, a->knn, a->max_cells, a->routed_max_cells, a->n_rots, a->n_sphere, a->rot_subsample);
+    const Workspace w = carve(a->workspace, n, n_pairs, a->knn, a->max_cells, a->routed_max_cells, a->n_rots, a->n_sphere,
+                              a->rot_subsample, dense);
+    const void* idx = sampled ? (const void*)w.idx_gen : a->idx;
+    const int idx_is_64 = sampled ? 0 : a->idx_is_64;
     const int cap_cells = a->max_cells > a->routed_max_cells ? a->max_cells : a->routed_max_cells;
     if ((int64_t)w.bytes > a->workspace_bytes) return (int)cudaErrorInvalidValue;
     Timing* tm = reinterpret_cast<Timing*>(a->timing);
@@ -286,6 +308,11 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     } while (0)
 
     CPPF_TRY(mark());
+    if (sampled) {                                                              // nocs/inference.py:177
+        sample_pairs_kernel<<<(int)((n_pairs + 1023) / 1024 < 2048 ? (n_pairs + 1023) / 1024 : 2048), 256, 0, stream>>>(
+            w.idx_gen, (long long)n_pairs, n, (unsigned long long)a->seed);
+        CPPF_LAUNCH_CHECK();
+    }
     geom_kernel<<<1, 1024, 0, stream>>>(a->pc, n, a->res, a->max_cells, a->routed_max_cells, (int)slab_cap_cells(),
                                         w.geom);
     CPPF_LAUNCH_CHECK();
@@ -298,7 +325,7 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     CPPF_TRY(mark());
     const int n_dirs = a->regress_right ? 2 : 1;
     const int heads = 1 | 2 | 8 | (a->regress_right ? 4 : 0);
-    CPPF_TRY(cppf_encode_sample_tc(a->pc, a->nrm, w.table, a->tc_blob, a->idx, a->idx_is_64, n, n_pairs, a->uniforms, a->seed,
+    CPPF_TRY(cppf_encode_sample_tc(a->pc, a->nrm, w.table, a->tc_blob, idx, idx_is_64, n, n_pairs, a->uniforms, a->seed,
                                    heads, w.bins, w.tail, nullptr, stream));
     if (a->inject_bins != nullptr && a->inject_cols > 0) {
         inject_bins_kernel<<<sm_count() * 8, 256, 0, stream>>>(w.bins, a->inject_bins, a->inject_cols, (long long)n_pairs);
@@ -306,18 +333,18 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     }
     CPPF_TRY(mark());
     CPPF_RETURN_IF(cudaMemsetAsync(w.grid, 0, (size_t)cap_cells * 4, stream));
-    CPPF_TRY(vote_fast_launch(a->pc, nullptr, w.bins, a->lut, a->idx, a->idx_is_64, w.grid, w.acc, nullptr, a->res, n, n_pairs,
+    CPPF_TRY(vote_fast_launch(a->pc, nullptr, w.bins, a->lut, idx, idx_is_64, w.grid, w.acc, nullptr, a->res, n, n_pairs,
                               a->n_rots, 0, 0, 0, a->adaptive, w.geom, a->max_cells, stream));
     if (a->routed_max_cells > 0) {      // grids of up to 8 shared-memory slabs: the kernels return at once unless geom->mode == 1
         CPPF_RETURN_IF(cudaMemsetAsync(w.acc, 0, (size_t)cap_cells * 8, stream));
-        CPPF_TRY(vote_routed_launch(a->pc, nullptr, w.bins, a->lut, a->idx, a->idx_is_64, w.acc, w.pool, (int64_t)w.pool_bytes,
+        CPPF_TRY(vote_routed_launch(a->pc, nullptr, w.bins, a->lut, idx, idx_is_64, w.acc, w.pool, (int64_t)w.pool_bytes,
                                     nullptr, a->res, n, n_pairs, a->n_rots, 0, 0, 0, a->adaptive, w.geom, stream));
         CPPF_TRY(vote_finalize_launch(w.acc, w.grid, cap_cells, w.geom, 1, stream));
     }
     CPPF_TRY(mark());
     CPPF_TRY(grid_argmax_launch(w.grid, cap_cells, &w.geom->cells, reinterpret_cast<int64_t*>(w.flat), nullptr, stream));
     CPPF_TRY(mark());
-    CPPF_TRY(backvote_bins_launch(a->pc, w.bins, a->lut, a->idx, a->idx_is_64, w.mask, nullptr,
+    CPPF_TRY(backvote_bins_launch(a->pc, w.bins, a->lut, idx, idx_is_64, w.mask, nullptr,
                                   reinterpret_cast<const int64_t*>(w.flat), a->res, a->tol, n, n_pairs, a->n_rots, 0, 0, 0,
                                   w.geom, stream));
     CPPF_TRY(mark());
@@ -327,7 +354,7 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     CPPF_RETURN_IF(cudaMemsetAsync(w.counts, 0, (size_t)a->n_sphere * 2 * sizeof(float), stream));
     const int64_t max_samples = a->rot_subsample > 0 ? a->rot_subsample : n_pairs;
     for (int j = 0; j < n_dirs; ++j) {
-        CPPF_TRY(cppf_rot_hist_mask(a->pc, w.bins, a->lut, a->idx, a->idx_is_64, w.mask,
+        CPPF_TRY(cppf_rot_hist_mask(a->pc, w.bins, a->lut, idx, idx_is_64, w.mask,
                                     reinterpret_cast<const int64_t*>(w.compact_scratch), n_pairs,
                                     reinterpret_cast<const int64_t*>(w.count), a->sphere, w.counts + (size_t)j * a->n_sphere, n,
                                     a->n_rots, a->n_sphere, j, max_samples < n_pairs ? max_samples : n_pairs,
@@ -336,7 +363,7 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
                                     reinterpret_cast<int64_t*>(w.best + j), nullptr, stream));
     }
     CPPF_TRY(mark());
-    CPPF_TRY(cppf_survivor_stats_mask(a->pc, a->nrm, w.tail, a->idx, a->idx_is_64, w.mask, a->sphere,
+    CPPF_TRY(cppf_survivor_stats_mask(a->pc, a->nrm, w.tail, idx, idx_is_64, w.mask, a->sphere,
                                       reinterpret_cast<const int64_t*>(w.best),
                                       n_dirs > 1 ? reinterpret_cast<const int64_t*>(w.best + 1) : nullptr, w.stats, n, n_pairs,
                                       stream));
@@ -345,4 +372,82 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     CPPF_TRY(mark());
 #undef CPPF_TRY
     return 0;
+}
+
+// ---- the object loop as one call -------------------------------------------------------------------------------
+namespace {
+struct BatchPool {
+    std::mutex mu;                       // one cppf_pose_batch at a time per device
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> done;
+    cudaEvent_t fork = nullptr;
+};
+BatchPool g_pools[64];
+
+int pool_reserve(BatchPool& p, int n_streams) {
+    if (p.fork == nullptr) CPPF_RETURN_IF(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    while ((int)p.streams.size() < n_streams) {
+        cudaStream_t s;
+        cudaEvent_t e;
+        CPPF_RETURN_IF(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CPPF_RETURN_IF(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p.streams.push_back(s);
+        p.done.push_back(e);
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int cppf_pose_batch(const cppf_pose_args* args, int n_objects, int n_streams, int n_threads, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_objects < 0 || (n_objects > 0 && args == nullptr) || n_streams < 1 || n_streams > 16 || n_threads < 1 ||
+        n_threads > n_streams)
+        return (int)cudaErrorInvalidValue;
+    if (n_objects == 0) return 0;
+    for (int i = 0; i < n_objects; ++i)
+        if (args[i].struct_bytes != sizeof(cppf_pose_args) || args[i].timing != nullptr) return (int)cudaErrorInvalidValue;
+    int dev = 0;
+    CPPF_RETURN_IF(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    BatchPool& pool = g_pools[dev];
+    std::lock_guard<std::mutex> lock(pool.mu);
+    if (n_streams > n_objects) n_streams = n_objects;
+    if (n_threads > n_streams) n_threads = n_streams;
+    const int r = pool_reserve(pool, n_streams);
+    if (r != 0) return r;
+    // fork: every worker stream starts after what the caller enqueued on `stream`
+    CPPF_RETURN_IF(cudaEventRecord(pool.fork, stream));
+    for (int s = 0; s < n_streams; ++s) CPPF_RETURN_IF(cudaStreamWaitEvent(pool.streams[s], pool.fork, 0));
+    std::vector<int> errs((size_t)n_threads, 0);
+    auto work = [&](int t) {
+        if (cudaSetDevice(dev) != cudaSuccess) {
+            errs[t] = (int)cudaErrorInvalidDevice;
+            return;
+        }
+        // thread t owns worker streams t, t + T, ...; the objects of a stream are enqueued in order
+        for (int i = 0; i < n_objects && errs[t] == 0; ++i) {
+            const int s = i % n_streams;
+            if (s % n_threads != t) continue;
+            errs[t] = cppf_pose_fused(&args[i], pool.streams[s]);
+        }
+    };
+    if (n_threads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve((size_t)n_threads - 1);
+        for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    // join: `stream` continues after every worker stream (also after an error: whatever was enqueued is waited for)
+    int err = 0;
+    for (int s = 0; s < n_streams; ++s) {
+        const cudaError_t e1 = cudaEventRecord(pool.done[s], pool.streams[s]);
+        const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(stream, pool.done[s], 0) : e1;
+        if (e2 != cudaSuccess && err == 0) err = (int)e2;
+    }
+    for (int t = 0; t < n_threads; ++t)
+        if (errs[t] != 0) return errs[t];
+    return err;
 }

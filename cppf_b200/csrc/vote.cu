@@ -111,9 +111,9 @@ __global__ void __launch_bounds__(256) ppf_vote_kernel(const VoteParams prm) {
         const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
         f3 ab, ex;
         if (!pair_frame(a, b, ab, ex)) continue;                           // :21
-        const f3 c = a - ab * mn.x;                                        // :23
+        const f3 c = foot_point(a, ab, mn.x);                                        // :23
         const float prob = prm.probs ? fmaxf(__ldg(prm.probs + ia), __ldg(prm.probs + ib)) : 1.f;   // :25
-        const f3 x = ex * mn.y;                                            // :28
+        const f3 x = scale3(ex, mn.y);                                            // :28
         const f3 y = cross3(x, ab);                                        // :29
         int n = prm.n_rots;
         if (prm.adaptive) n = adaptive_rots(mn.y, prm.res, prm.n_rots);    // :31
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) ppf_vote_kernel(const VoteParams prm) {
                 ca = cosf(ang);
                 sa = sinf(ang);
             }
-            const f3 off = x * ca + y * sa;                                // :34
+            const f3 off = circle_offset(x, y, ca, sa);                                // :34
             const f3 g = {(c.x + off.x - cx) / prm.res, (c.y + off.y - cy) / prm.res,
                           (c.z + off.z - cz) / prm.res};                   // :35
             if (g.x < prm.lo || g.y < prm.lo || g.z < prm.lo || g.x >= prm.hx || g.y >= prm.hy || g.z >= prm.hz)
@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(256) backvote_kernel(const BackvoteParams prm)
         f3 res_off = {0.f, 0.f, 0.f};
         const bool live = pair_frame(a, b, ab, ex);                        // :87 degenerate rows are not written
         if (live) {
-            const f3 c = a - ab * mn.x;
-            const f3 x = ex * mn.y;
+            const f3 c = foot_point(a, ab, mn.x);
+            const f3 x = scale3(ex, mn.y);
             const f3 y = cross3(x, ab);
             const int n = adaptive_rots(mn.y, prm.res, prm.n_rots);        // :97 always adaptive
             const float2* tab = TABLE ? s_tab + (n > 0 ? n * (n - 1) / 2 : 0) : nullptr;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) backvote_kernel(const BackvoteParams prm)
                     ca = cosf(ang);
                     sa = sinf(ang);
                 }
-                const f3 off = x * ca + y * sa;
+                const f3 off = circle_offset(x, y, ca, sa);
                 const f3 pc = c + off;                                     // :101
                 const f3 dlt = {pc.x - tx, pc.y - ty, pc.z - tz};
                 if (len3(dlt) > prm.tol) continue;                         // :102
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(128) rot_vote_kernel(const float* __restrict__
         }
         const f3 ab = {fr[0], fr[1], fr[2]}, x = {fr[3], fr[4], fr[5]}, y = {fr[6], fr[7], fr[8]};
         const float tn = fr[9];
-        const f3 off = x * ca + y * sa;                                    // :141
+        const f3 off = circle_offset(x, y, ca, sa);                                    // :141
         const f3 axis = tn > 0.f ? ab : f3{-ab.x, -ab.y, -ab.z};
         f3 up = off * tn + axis;                                           // :142
         up = up / (float)((double)len3(up) + 1e-7);                        // :143

@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
                 const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
                 f3 ab, ex;
                 if (pair_frame(a, b, ab, ex)) {                                // voting.py:21
-                    c = a - ab * mu;                                           // :23
-                    x = ex * nu;                                               // :28
+                    c = foot_point(a, ab, mu);                                           // :23
+                    x = scale3(ex, nu);                                               // :28
                     y = cross3(x, ab);                                         // :29
                 } else {
                     n = 0;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
 #else
                 const float2 cs = tab[i];
 #endif
-                const f3 off = x * cs.x + y * cs.y;                            // :34
+                const f3 off = circle_offset(x, y, cs.x, cs.y);                            // :34
                 const float dx = c.x + off.x - cx, dy = c.y + off.y - cy, dz = c.z + off.z - cz;   // :35 before `/ res`
                 // conservative: every candidate the exact test of phase 2 accepts passes here
                 const bool inb = i < n && dx >= dlx && dy >= prm.dlo && dz >= prm.dlo && dx < dhx && dy < dhy && dz < dhz;
@@ -439,8 +439,8 @@ __global__ void __launch_bounds__(CPPF_BV_THREADS, CPPF_BV_MIN_BLOCKS) backvote_
         f3 ab, ex;
         bool hit = false;
         if (pair_frame(a, b, ab, ex)) {
-            const f3 c = a - ab * mu;
-            const f3 x = ex * nu;
+            const f3 c = foot_point(a, ab, mu);
+            const f3 x = scale3(ex, nu);
             const f3 y = cross3(x, ab);
             const int n = s_nlut[bn.y & 31];                                   // :97
             const float2* tab = s_tab + (n > 0 ? n * (n - 1) / 2 : 0);
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(CPPF_BV_THREADS, CPPF_BV_MIN_BLOCKS) backvote_
                         break;
                     }
                 }
-                const f3 off = x * cs.x + y * cs.y;
+                const f3 off = circle_offset(x, y, cs.x, cs.y);
                 const f3 pc = c + off;
                 const f3 dlt = {pc.x - tx, pc.y - ty, pc.z - tz};
                 if (len3(dlt) > prm.tol) continue;                             // :102
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(kRotHistThreads) rot_hist_kernel(const RotHist
             const float2 cs = __ldg(tab + i);
             const f3 ab = {fr[0], fr[1], fr[2]}, x = {fr[3], fr[4], fr[5]}, y = {fr[6], fr[7], fr[8]};
             const float tn = fr[9];
-            const f3 o = x * cs.x + y * cs.y;
+            const f3 o = circle_offset(x, y, cs.x, cs.y);
             const f3 axis = tn > 0.f ? ab : f3{-ab.x, -ab.y, -ab.z};
             up = o * tn + axis;
             up = up / (float)((double)len3(up) + 1e-7);

@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(kRouteThreads, 1) route_kernel(const RoutePara
                 const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
                 f3 ab, ex;
                 if (pair_frame(a, b, ab, ex)) {                                // voting.py:21
-                    c = a - ab * mu;                                           // :23
-                    x = ex * nu;                                               // :28
+                    c = foot_point(a, ab, mu);                                           // :23
+                    x = scale3(ex, nu);                                               // :28
                     y = cross3(x, ab);                                         // :29
                 } else {
                     n = 0;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kRouteThreads, 1) route_kernel(const RoutePara
             const int n_max = __reduce_max_sync(0xffffffffu, n);
             for (int i = 0; i < n_max; ++i) {
                 const float2 cs = tab[i];
-                const f3 off = x * cs.x + y * cs.y;                            // :34
+                const f3 off = circle_offset(x, y, cs.x, cs.y);                            // :34
                 const float dx = c.x + off.x - cx, dy = c.y + off.y - cy, dz = c.z + off.z - cz;
                 const bool inb = i < n && dx >= prm.dlo && dy >= prm.dlo && dz >= prm.dlo && dx < dhx && dy < dhy && dz < dhz;
                 const unsigned m = __ballot_sync(0xffffffffu, inb);

@@ -190,9 +190,12 @@ class PoseEstimator:
         # ---- back-vote filter + compaction (:216-231)
         _, mask = voting.backvote(pc, mu_nu, idxs, dims, corner, cfg.res, centre, 3 * cfg.res, cfg.num_rots,
                                   want_offsets=False)
-        kept, cnt, _ = voting.compact_pairs(mask, idxs, n)
+        kept, cnt, pos = voting.compact_pairs(mask, idxs, n, want_pos=True)
         n_kept = int(cnt.item())                                                    # the one host sync
-        kept = kept[:n_kept]
+        kept, pos = kept[:n_kept], pos[:n_kept]
+
+        def rows(t):            # injected per-pair noise is indexed by the ORIGINAL pair row: survivors take their rows
+            return None if t is None else torch.as_tensor(t).to(dev)[pos].contiguous()
         out = {"T": T_est, "n_survivors": n_kept, "grid_dims": dims, "argmax": flat}
         if n_kept == 0:
             raise NoSurvivorsError("no pair voted for the winning centre (degenerate input)")
@@ -207,12 +210,15 @@ class PoseEstimator:
         for j, (col, aux, tag) in enumerate([(0, preds_up_aux, "up"), (RB, preds_right_aux, "right")]):
             if j == 1 and not cfg.regress_right:                                    # :260-261
                 continue
-            rot = voting.sample_bins(heads, col, RB, q=noise.get(f"q_{tag}"), u=noise.get(f"u_{tag}"), seed=seed,
+            rot = voting.sample_bins(heads, col, RB, q=rows(noise.get(f"q_{tag}")), u=rows(noise.get(f"u_{tag}")), seed=seed,
                                      stream_id=2 + j, div=RB - 1, mul_a=float(np.float32(np.pi)))     # :250-256
             sub = kept
             if cfg.rot_subsample and n_kept > cfg.rot_subsample:                    # :277-281
-                g = torch.Generator(device=dev).manual_seed(seed + 17 + j)
-                sel = torch.randperm(n_kept, generator=g, device=dev)[:cfg.rot_subsample]
+                if noise.get("sub_key") is not None:        # injected shuffle: the survivors with the smallest keys
+                    sel = torch.argsort(rows(noise["sub_key"]), stable=True)[:cfg.rot_subsample]
+                else:
+                    g = torch.Generator(device=dev).manual_seed(seed + 17 + j)
+                    sel = torch.randperm(n_kept, generator=g, device=dev)[:cfg.rot_subsample]
                 sub, rot_sub = kept[sel].contiguous(), rot[sel].contiguous()
             else:
                 rot_sub = rot

@@ -288,6 +288,9 @@ typedef struct cppf_pose_args {
     int max_cells;               /* capacity of the shared-memory vote grid: <= cppf_vote_private_max_cells() */
     int routed_max_cells;        /* 0, or the capacity for larger grids voted through routed x-slabs
                                     (cppf_vote_routed): <= 8 * 56320 */
+    int sample_pairs;            /* 1 (with idx == NULL): draw the n_pairs random point pairs of nocs/inference.py:177 on the
+                                    device (Philox keyed by seed, uniform over [0, n_points)^2) instead of enumerating all
+                                    n_points^2 pairs */
     float res;
     float tol;                   /* back-vote tolerance, float32(3 * res) at nocs/inference.py:226 */
     float cos_thr;               /* float32(cos(angle_prec)) at :283 */
@@ -297,6 +300,17 @@ int cppf_pose_args_bytes(void);            /* sizeof(cppf_pose_args) as compiled
 int64_t cppf_pose_workspace_bytes(int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells, int n_rots,
                                   int n_sphere, int64_t rot_subsample);
 int cppf_pose_fused(const cppf_pose_args* args, void* stream);
+
+/* The object loop of nocs/inference.py:120-129 (sunrgbd/inference.py:115) as ONE call: args[0..n_objects) are enqueued
+ * like n_objects cppf_pose_fused calls, object i on internal worker stream (i % n_streams), the worker streams forked from
+ * and joined back into `stream` with events (work enqueued on `stream` before the call is visible to every object; work
+ * enqueued after it sees every record).  Small objects (the reference's P = 100 000 regime fills ~1.3 waves of the GPU per
+ * kernel) overlap across the worker streams, and the ~25 launches per object are issued by n_threads host threads, so
+ * neither the GPU nor the launching thread is the per-object bottleneck.
+ * Objects that share a worker stream may share a workspace; objects on different worker streams must not.  Records are
+ * identical to the per-object calls (same kernels, same arguments).  args[i].timing must be NULL.
+ * n_streams in [1, 16], n_threads in [1, n_streams].  Returns the first error. */
+int cppf_pose_batch(const cppf_pose_args* args, int n_objects, int n_streams, int n_threads, void* stream);
 
 /* Stage timing for cppf_pose_fused: CUDA events recorded on the launching stream around every stage.
  * cppf_timing_collect adds the elapsed milliseconds per stage of every call recorded since the last collect
@@ -358,6 +372,24 @@ int cppf_gaussian3d(const float* grid, float* out, float* tmp, int gx, int gy, i
                     void* stream);
 int cppf_scene_proposals(float* grid, int gx, int gy, int gz, float thresh, int margin, float rel_stop, int max_props,
                          float* h_out, void* scratch, void* stream);
+
+/* ==== measurement aids (bench.py's roofline block; never on the pose path) =====================================
+ * cppf_vote_count: the ALGORITHMIC work of one centre-vote launch over these inputs, counted on the device with the
+ * reference's own acceptance test (models/voting.py:21-39).  out3 (device, 3 x uint64): [0] rotation steps walked
+ * (sum over non-degenerate pairs of adaptive_n_rots, :31-32), [1] candidates that pass the in-bounds test (:36-39) --
+ * 8 x this is the number of trilinear atomic adds (:56-63) the reference issues and every vote kernel here performs --
+ * [2] non-degenerate pairs (:21).  Exactly one of mu_nu / bins (+lut) is given; idx == NULL enumerates all N^2 pairs.
+ * cppf_peak_shared_atomics: G atomic adds / s this GPU sustains (best of `reps` timed launches, CUDA events on `stream`,
+ * synchronises) on a [gx,gy,gz] u32 grid in shared memory, one 1024-thread CTA per SM, nothing else in the loop:
+ * conflict_free = 0: 32 lanes x the 8-corner splat of a uniformly random base cell each (the bank behaviour of an
+ * unsorted vote); 1: lane l always in bank l (the hardware roof, one wavefront per instruction).
+ * cppf_peak_global_red: the same 8-corner pattern as fp32 reductions on a grid in global memory (the reference's own
+ * atomicAdd, models/voting.py:56-63). */
+int cppf_vote_count(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, const void* idx,
+                    int idx_is_64, const float* corner, float res, int n_points, int64_t n_pairs, int n_rots, int gx,
+                    int gy, int gz, int adaptive, uint64_t* out3, void* stream);
+int cppf_peak_shared_atomics(int gx, int gy, int gz, int conflict_free, int reps, double* g_atomics_per_s, void* stream);
+int cppf_peak_global_red(int gx, int gy, int gz, int reps, double* g_atomics_per_s, void* stream);
 
 #ifdef __cplusplus
 }

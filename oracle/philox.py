@@ -37,6 +37,14 @@ def pair_uniforms(seed, n_pairs):
     return np.stack([u01(x) for x in w], -1)
 
 
+def pair_uniforms_at(seed, pair_index):
+    """pair_uniforms for an arbitrary set of pair indices (int64 array) -- the counter IS the pair index."""
+    p = np.asarray(pair_index).astype(np.uint64)
+    w = philox4x32_10((p & np.uint64(0xFFFFFFFF)).astype(np.uint32), (p >> np.uint64(32)).astype(np.uint32), 0, 0,
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return np.stack([u01(x) for x in w], -1)
+
+
 def row_uniforms(seed, n_rows, stream_id):
     """uniforms of cppf_sample_bins mode 2: counter (row_lo, row_hi, stream_id, 0)."""
     p = np.arange(n_rows, dtype=np.uint64)

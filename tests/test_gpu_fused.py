@@ -8,6 +8,7 @@ import torch
 from cppf_b200 import fast, model, synth, voting
 from cppf_b200.pipeline import PoseConfig, PoseEstimator
 from oracle import clib, philox, ref_model
+from parity_util import assert_masks_equal_up_to_rounding
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -92,6 +93,74 @@ def test_encode_sample_dense_philox_and_head_mask(impl):
     assert none_tail is None and torch.equal(b_tr[:, :2], b_inj[:, :2]) and not b_tr[:, 2:].any()
 
 
+@pytest.mark.parametrize("n", [96, 128, 300, 1024, 4096])
+def test_dense_tc_encoder_matches_indexed_and_oracle_at_every_tile_shape(n):
+    """The BENCHMARKED instantiation -- encode_sample_tc_kernel<dense> with row-aligned 128-pair tiles, the a-side table row
+    through the ones-operand MMA, tiles_per_row = ceil(n / 128) (1 ragged tile at 96, 1 full at 128, 2 full + 1 ragged at
+    300, 8 at 1024, 32 at the headline N = 4096) -- against (i) the indexed instantiation on the same pairs and uniforms and
+    (ii) the oracle's fp32 layer-by-layer MLP + sequential inverse-CDF draw, on a random subset of <= 200 000 pairs.
+    Bars: bins equal except at a CDF edge within fp32 rounding (counted, off by at most one bin); tail logits rtol 1e-4."""
+    seed = 987654321
+    m, pc, nrm, feat = _setup(n, 11)
+    with torch.no_grad():
+        table = _table(m, feat, "tc")
+        b_dense, t_dense = fast.encode_sample(m, _t(pc), _t(nrm), table, None, heads=15, seed=seed, impl="tc")
+    n_pairs = n * n
+    rng = np.random.default_rng(n)
+    sub = np.sort(rng.choice(n_pairs, size=min(n_pairs, 200_000), replace=False)).astype(np.int64)
+    # always include the corners of the tiling: first / last pair of a row, tile boundaries, the diagonal, the last row
+    special = np.array([0, n - 1, n, n_pairs - 1, n_pairs - n, (n // 2) * n + n // 2] +
+                       [r * n + c for r in (0, n // 3, n - 1) for c in (127, 128, 129, n - 2) if 0 <= c < n], np.int64)
+    sub = np.unique(np.concatenate([sub, special]))
+    idx = np.stack([sub // n, sub % n], -1)
+    u = philox.pair_uniforms_at(seed, sub)
+    with torch.no_grad():
+        b_idx, t_idx = fast.encode_sample(m, _t(pc), _t(nrm), table, _t(idx, torch.int64), heads=15, uniforms=_t(u), impl="tc")
+    bd = b_dense.cpu().numpy()[sub].astype(np.int64)
+    bi = b_idx.cpu().numpy().astype(np.int64)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    logits = ref_model.ppf_encode_idx(torch.from_numpy(pc), torch.from_numpy(nrm), feat, idx, sd)
+    tu = torch.from_numpy(u)
+    allowed = max(2, len(sub) // 5000)
+    for h, (c0, nb) in enumerate([(0, 32), (32, 32), (64, 36), (100, 36)]):
+        ref = ref_model.sample_bins_cdf(logits[:, c0:c0 + nb], tu[:, h], exp2=True).numpy()
+        for name, other in (("indexed kernel", bi[:, h]), ("oracle", ref)):
+            d = bd[:, h] - other
+            mism = int((d != 0).sum())
+            print(f"[dense tc n={n}] head {h} vs {name}: {mism} of {len(sub)} draws differ")
+            assert mism <= allowed, f"n={n} head {h}: {mism} of {len(sub)} dense draws differ from the {name}"
+            assert int(np.abs(d).max()) <= 1
+    tail_d = t_dense.cpu().numpy()[:, sub].T
+    np.testing.assert_allclose(tail_d, logits[:, 136:].numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(tail_d, t_idx.cpu().numpy().T, rtol=1e-5, atol=2e-6)
+
+
+def test_backvote_bins_bit_equal_to_reference_kernel_dense_1024():
+    """All 1 048 576 ordered pairs of an N = 1024 bottle under the trained-like vote load: the survivor mask of the
+    bins-driven back-vote kernel (dense enumeration, arc window, fast accept) is BIT-EQUAL to the mask the reference's own
+    `backvote` kernel (models/voting.py:74-112, built for sm_100a from the reference string) leaves on the same GPU."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("reference cubins / cuda-python not present")
+    cfg, pc, idxs, tr, corner, dims = _vote_case(1024, 0, 8, dense=True)
+    lut = fast.decode_lut(cfg["vote_range"])
+    b_mu = torch.argmin((torch.from_numpy(tr[:, 0:1]) - lut[None, :32]).abs(), -1)
+    b_nu = torch.argmin((torch.from_numpy(tr[:, 1:2]) - lut[None, 32:64]).abs(), -1)
+    bins = torch.stack([b_mu, b_nu, b_mu * 0, b_mu * 0], -1).to(torch.uint8).to(DEV)
+    grid = torch.zeros(dims, device=DEV)
+    fast.vote_fast(_t(pc), None, grid, _t(corner), cfg["res"], bins=bins, lut=lut.to(DEV))
+    flat = voting.grid_argmax(grid)
+    mask = fast.backvote_bins(_t(pc), bins, lut.to(DEV), None, dims, _t(corner), flat, cfg["res"], 3 * cfg["res"])
+    _, centre = ref_model.centre_from_grid(grid.cpu().numpy(), corner, cfg["res"])
+    ref_off = ref_gpu.backvote(_t(pc), _t(tr), torch.zeros(idxs.shape[0], 3, device=DEV), _t(idxs, torch.int32), _t(corner),
+                               cfg["res"], 72, dims, _t(centre.astype(np.float32)), 3 * cfg["res"])
+    ref_mask = (ref_off != 0).any(-1)
+    assert 0.01 < ref_mask.float().mean().item() < 0.9
+    n_diff = int((mask.bool() != ref_mask).sum().item())
+    print(f"[backvote_bins dense 1024 vs reference cubin] differing bits: {n_diff} of {idxs.shape[0]}")
+    assert n_diff == 0
+
+
 def _table(m, feat, impl):
     return m.tc_preproject(feat.to(DEV)) if impl == "tc" else m.preproject(feat.to(DEV))
 
@@ -171,8 +240,17 @@ def test_backvote_bins_matches_oracle():
                               3 * cfg["res"])
     _, centre = ref_model.centre_from_grid(grid.cpu().numpy(), corner, cfg["res"])
     ref = clib.backvote(pc, tr, idxs.astype(np.int32), dims, corner, cfg["res"], centre.astype(np.float32), 3 * cfg["res"])
-    agree = (mask.cpu().numpy().astype(bool) == np.any(ref != 0, -1)).mean()
-    assert agree > 0.999
+    # the bins-driven kernel (analytic arc window + fast accept) against the plain-C oracle (gcc + libm): bit-equal except
+    # for candidates on the tolerance sphere within float32 rounding (counted and proven)
+    assert_masks_equal_up_to_rounding(mask.cpu().numpy().astype(bool), np.any(ref != 0, -1), pc, tr, idxs, dims, corner,
+                                      cfg["res"], centre.astype(np.float32), np.float32(3 * cfg["res"]),
+                                      "backvote_bins vs C oracle", 4)
+    # ... and bit-equal to the reference's own kernel on this GPU, where its cubin travelled
+    from oracle import ref_gpu
+    if ref_gpu.available():
+        ref_off = ref_gpu.backvote(_t(pc), _t(tr), torch.zeros(idxs.shape[0], 3, device=DEV), _t(idxs, torch.int32), _t(corner),
+                                   cfg["res"], 72, dims, _t(centre.astype(np.float32)), 3 * cfg["res"])
+        np.testing.assert_array_equal(mask.bool().cpu().numpy(), (ref_off != 0).any(-1).cpu().numpy())
 
 
 def test_rot_hist_equals_unfused_and_stats_match_numpy():
