@@ -36,14 +36,29 @@ if ROOT not in sys.path:
 
 METRIC = "point_pairs_per_sec"
 UNIT = "pairs/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch and the utilisation of the resource that binds each kernel,
-# from the committed `ncu --set full` capture of this pipeline (profiles/r1f_kernels_ncu.md), N=4096 dense
-TRAFFIC_NCU = {"encode_sample": 3.3728e6 + 345.649152e6, "vote": 67.36128e6 + 0.84736e6,
-               "backvote": 67.252736e6 + 3.7312e6, "stats": 285.441792e6 + 7.912192e6}
-BINDING_NCU = {"encode_sample": {"issue_slots_busy": 0.456, "tensor_pipe_active": 0.438, "warps_per_sm": 16},
-               "vote": {"shared_memory_wavefronts_of_peak": 0.738, "issue_slots_busy": 0.772,
-                        "wavefronts_per_ATOMS": 3.64},
-               "backvote": {"issue_slots_busy": 0.778}, "stats": {"dram_read_tbs": 2.88}}
+
+
+def ncu_constants():
+    """Counters that only a profiler can give (DRAM bytes per launch, pipe utilisations), from profiles/ncu_constants.json.
+    Every entry names the capture it came from and the sha256 of the kernel's source file at capture time; an entry whose
+    source has changed since is DROPPED (reported as null), never printed stale."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "ncu_constants.json")
+    out, stale = {}, []
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return out, ["profiles/ncu_constants.json missing"]
+    for name, ent in table.get("kernels", {}).items():
+        try:
+            cur = hashlib.sha256(open(os.path.join(ROOT, ent["source"]), "rb").read()).hexdigest()
+        except Exception:
+            cur = None
+        if cur == ent.get("source_sha256"):
+            out[name] = ent
+        else:
+            stale.append(f"{name}: {ent.get('source')} changed since {ent.get('capture')}")
+    return out, stale
 
 
 def parse():
@@ -134,71 +149,165 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU reference path
-def cpu_reference_step(pc, nrm, sd_pe, sd_ppf, idxs, cfg, sphere, seed):
-    """The reference's own per-object path on the CPU for a bounded pair sample: oracle
-    restatement of the torch modules (reference models/model.py, run by torch CPU with all
-    threads) + the reference's CUDA-C voting strings compiled for the CPU with OpenMP
-    (oracle/_ref/libref_voting_cpu.so; falls back to the plain-C port if it did not travel)."""
-    from oracle import clib, ref_model
-    impl = "ref_cpu" if clib.have_ref_cpu() else "oracle"
-    n = pc.shape[0]
-    tpc, tn = torch.from_numpy(pc), torch.from_numpy(nrm)
-    dist = torch.cdist(tpc[None], tpc[None])[0]
-    feat = ref_model.point_encode(tpc, tn, dist, sd_pe, cfg["knn"])
-    logits = ref_model.ppf_encode_idx(tpc, tn, feat, idxs, sd_ppf)
-    B = cfg["tr_num_bins"]
-    g = torch.Generator().manual_seed(seed)
-    pr = torch.softmax(logits[:, :2 * B].reshape(-1, 2, B), -1)
-    bins = torch.cat([torch.multinomial(pr[:, 0], 1, generator=g), torch.multinomial(pr[:, 1], 1, generator=g)], -1)
-    tr = ref_model.decode_tr(bins[:, 0], bins[:, 1], B, cfg["vote_range"]).numpy()
-    lo, hi = pc.min(0), pc.max(0)
-    dims = ((hi - lo) / cfg["res"]).astype(np.int32) + 1
-    idx32 = idxs.astype(np.int32)
-    grid = clib.ppf_voting(pc, tr, np.ones(n, np.float32), idx32, dims, lo, cfg["res"], 72, True, impl=impl)
-    flat, centre = ref_model.centre_from_grid(grid, lo, cfg["res"])
-    oc = clib.backvote(pc, tr, idx32, dims, lo, cfg["res"], centre.astype(np.float32), 3 * cfg["res"], 72, impl=impl)
-    kept = idxs[np.any(oc != 0, -1)]
-    if len(kept):
-        l2 = ref_model.ppf_encode_idx(tpc, tn, feat, kept, sd_ppf)
-        up = torch.multinomial(torch.softmax(l2[:, 2 * B:2 * B + cfg["rot_num_bins"]], -1), 1, generator=g)[:, 0]
-        rot = ref_model.decode_rot(up, cfg["rot_num_bins"]).numpy().astype(np.float32)
-        sub = np.random.default_rng(seed).permutation(len(kept))[:10000]
-        cand = clib.rot_voting(pc, rot[sub], kept[sub].astype(np.int32), 72, impl=impl)
-        counts = ((torch.from_numpy(cand.reshape(-1, 3)) @ torch.from_numpy(sphere.T.astype(np.float32))) >
-                  float(np.cos(1.5 / 180 * np.pi))).sum(0)
-        best = sphere[int(torch.argmax(counts))]
-        ref_model.aux_sign(pc, nrm, kept, best, l2[:, -5].numpy())
-    return int(flat), impl
-
-
 def run_cpu_reference(args, steps, warmup, sample_pairs):
+    """The reference's own per-object path on the host cores, timed on a bounded pair sample of the SAME object:
+    oracle/ref_pipeline.estimate = nocs/inference.py:174-339 restated (torch CPU with all threads for the network -- a PORT
+    of models/model.py, pinned to it by the golden fixtures -- and the reference's own CUDA-C voting strings compiled for the
+    CPU with OpenMP, oracle/_ref/libref_voting_cpu.so, or the plain-C port if that library did not travel).
+
+    The per-OBJECT cost (kNN + SPRIN point encoder, O(N k); the orientation vote on its 10 000-survivor sub-sample,
+    nocs/inference.py:277-284) and the per-PAIR cost (pair MLP, sampling, votes, back-vote, second pass) are timed separately, so that the value can be stated like for like with the GPU arm, which amortises the per-object cost over
+    all N^2 pairs of the object:  value = N^2 / (fixed + N^2 * per_pair).  The raw pairs/s of the sample is reported too."""
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core, both in torch and in
     # the OpenMP voting library (which reads the variable when it is first loaded)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from cppf_b200 import model, synth
-    from oracle import ref_model
+    from oracle import clib, ref_model, ref_pipeline
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = synth.BOTTLE
+    cfg = dict(synth.BOTTLE)
     torch.manual_seed(0)
     sd_pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).state_dict()
     sd_ppf = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141).state_dict()
     sphere = ref_model.fibonacci_sphere(480)
     n = args.n_points
-    times, impl = [], "oracle"
+    vote_impl = "ref_cpu" if clib.have_ref_cpu() else "oracle"
+    tot, fixed, per_pair = [], [], []
     for s in range(warmup + steps):
         pc, nrm = synth.synth_bottle(n, s)
         idxs = synth.sample_pairs(n, sample_pairs, s)
+        if args.votes == "trained_like":
+            # the vote load of the GPU arm: the first-pass draws are replaced by the geometric targets (SURVEY.md 8d i)
+            tl = synth.trained_like_tr(pc, idxs)
+            lut_mu = (np.arange(32, dtype=np.float32) / np.float32(31) * np.float32(0.5) - np.float32(0.25))
+            lut_nu = np.arange(32, dtype=np.float32) / np.float32(31) * np.float32(0.25)
+            q_mu = np.full((sample_pairs, 32), 1e30, np.float32)
+            q_nu = np.full((sample_pairs, 32), 1e30, np.float32)
+            q_mu[np.arange(sample_pairs), np.argmin(np.abs(tl[:, :1] - lut_mu[None]), -1)] = 1e-30      # the race is decided
+            q_nu[np.arange(sample_pairs), np.argmin(np.abs(tl[:, 1:] - lut_nu[None]), -1)] = 1e-30
+            noise = {"q_mu": q_mu, "q_nu": q_nu}
+        else:
+            noise = None
+        tm = {}
         t0 = time.perf_counter()
-        _, impl = cpu_reference_step(pc, nrm, sd_pe, sd_ppf, idxs, cfg, sphere, s)
+        ref_pipeline.estimate(pc, nrm, sd_pe, sd_ppf, idxs, cfg, noise=noise, seed=s, sphere=sphere, impl=vote_impl,
+                              cdist_knn=True, timings=tm)
         dt = time.perf_counter() - t0
         if s >= warmup:
-            times.append(dt)
-    total = sum(times)
-    return {"value": sample_pairs * len(times) / total, "ms_per_step": 1e3 * total / len(times), "impl": impl,
-            "cores": torch.get_num_threads(),
-            "sample": f"{sample_pairs} random pairs of the N={n} object per step ({len(times)} steps): point encoder + "
-                      "pair MLP (torch CPU, all threads) + multinomial + vote/back-vote/rot-vote "
-                      f"({'reference CUDA-C strings built for CPU, OpenMP' if impl == 'ref_cpu' else 'plain-C oracle port'})"}
+            tot.append(dt)
+            if tm["orientation_is_fixed"]:          # the 10 000-survivor sub-sample costs the same for any P
+                fixed.append(tm["point_encoder"] + tm["orientation"])
+                per_pair.append(tm["pairs"] / sample_pairs)
+            else:
+                fixed.append(tm["point_encoder"])
+                per_pair.append((tm["pairs"] + tm["orientation"]) / sample_pairs)
+    fx, pp = float(np.mean(fixed)), float(np.mean(per_pair))
+    n2 = float(n) * n
+    return {"value": n2 / (fx + n2 * pp), "value_on_sample": sample_pairs * len(tot) / sum(tot),
+            "ms_per_step": 1e3 * sum(tot) / len(tot), "vote_kind": "reference" if vote_impl == "ref_cpu" else "port",
+            "mlp_kind": "port", "fixed_cost_ms": 1e3 * fx, "per_pair_ms": 1e3 * pp, "cores": torch.get_num_threads(),
+            "sample": f"{sample_pairs} random pairs of the N={n} object per step ({len(tot)} steps), votes={args.votes}: "
+                      "oracle/ref_pipeline.estimate = nocs/inference.py:174-339 restated -- cdist + topk + SPRIN and the pair "
+                      "MLP as a torch-CPU port of models/model.py (all threads), multinomial, vote / back-vote / rot-vote "
+                      f"({'the reference CUDA-C strings built for the CPU with OpenMP' if vote_impl == 'ref_cpu' else 'plain-C port'}). "
+                      f"value = N^2 / (fixed_cost + N^2 * per_pair): the per-object stages (point encoder + orientation vote on "
+                      f"its 10 000-survivor sub-sample, {1e3 * fx:.1f} ms) amortised over all N^2 pairs like the GPU arm; "
+                      "value_on_sample = raw pairs/s of the sample"}
+
+
+def cpu_baseline_block(r):
+    # kind "port": the network half is a port of models/model.py (the reference modules cannot travel to the GPU box);
+    # the voting half is the reference's own CUDA-C compiled for the CPU whenever oracle/_ref travelled (vote_kind)
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "mlp_kind": r["mlp_kind"],
+            "vote_kind": r["vote_kind"], "fixed_cost_ms": r["fixed_cost_ms"], "per_pair_ms": r["per_pair_ms"],
+            "value_on_sample": r["value_on_sample"], "sample": r["sample"]}
+
+
+# ------------------------------------------------------------------------------ GPU reference arm
+def gpu_reference_arm(dev, clouds, inject, est, pe, ppf, stage_names, L, timing, args):
+    """BASELINE config 2, "vs reference CuPy": the reference's OWN kernels on this GPU (models/voting.py's CUDA-C strings
+    built for sm_100a, launched with the reference's launch shapes) + the reference's torch modules on torch-CUDA, in the
+    order of nocs/inference.py:174-339 (oracle/ref_gpu_pipeline.py), next to this library on the same inputs:
+      (i) the reference's regime, P = 100 000 sampled pairs;  (ii) the dense N^2 workload of this bench, chunked to fit.
+    Per-stage CUDA-event times and the end-to-end time per object, both sides."""
+    from cppf_b200 import synth
+    from cppf_b200.pipeline import PoseConfig, PoseEstimator
+    try:
+        from oracle import ref_gpu, ref_gpu_pipeline
+        if not ref_gpu.available():
+            return {"unavailable": "oracle/_ref cubins or cuda-python not present on this box"}
+    except Exception as e:                                   # pragma: no cover
+        return {"unavailable": repr(e)}
+    n = args.n_points
+    cfg = dict(synth.BOTTLE)
+    sd_pe = {k: v.detach() for k, v in pe.state_dict().items()}
+    sd_ppf = {k: v.detach() for k, v in ppf.state_dict().items()}
+    sphere = est.sphere
+    pc = torch.from_numpy(clouds[0][0]).to(dev)
+    nrm = torch.from_numpy(clouds[0][1]).to(dev)
+    out = {}
+
+    def ours_stages(e, **kw):
+        L.cppf_timing_collect(timing, (C.c_float * len(stage_names))())
+        e.timing = timing
+        t = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e.enqueue_fused(pc, nrm, seed=0, **kw).result()
+            t.append((time.perf_counter() - t0) * 1e3)
+        acc = (C.c_float * len(stage_names))()
+        calls = L.cppf_timing_collect(timing, acc)
+        e.timing = None
+        return {nm: acc[i] / max(calls, 1) for i, nm in enumerate(stage_names)}, min(t)
+
+    def table(ref, ours, ours_wall):
+        rs = ref["stage_ms"]
+        rows = {"point_encoder": (rs.get("point_encoder", 0.0), ours["point_encoder"] + ours["geometry"]),
+                "encode": (rs.get("encode", 0.0) + rs.get("encode2", 0.0), ours["preproject"] + ours["encode_sample"]),
+                "vote": (rs.get("vote", 0.0), ours["vote"]),
+                "argmax": (rs.get("argmax", 0.0), ours["argmax"]),
+                "backvote": (rs.get("backvote", 0.0), ours["backvote"] + ours["compact"]),
+                "rot_vote+sphere": (rs.get("rot_vote", 0.0), ours["rot_hist"]),
+                "aux_sign+stats": (rs.get("aux_sign", 0.0), ours["stats"])}
+        tab = {k: {"reference_ms": a, "ours_ms": b, "speedup": (a / b if b > 0 else None)} for k, (a, b) in rows.items()}
+        r_tot, o_tot = sum(a for a, _ in rows.values()), sum(b for _, b in rows.values())
+        return {"stages": tab, "reference_gpu_ms_per_object": r_tot, "ours_gpu_ms_per_object": o_tot,
+                "gpu_speedup": r_tot / o_tot, "reference_wall_ms_per_object": ref["wall_ms"], "ours_wall_ms_per_object": ours_wall,
+                "reference_objects_per_sec": 1e3 / ref["wall_ms"], "ours_objects_per_sec": 1e3 / ours_wall,
+                "reference_survivors": ref["n_survivors"]}
+
+    # (i) P = 100 000 sampled pairs, the network's own votes on both sides
+    p = 100000
+    idx = torch.from_numpy(synth.sample_pairs(n, p, 0).astype(np.int32)).to(dev)
+    ref = None
+    for _ in range(3):                                        # first call loads the cubins / warms cuBLAS
+        r = ref_gpu_pipeline.estimate(pc, nrm, sd_pe, sd_ppf, idx, cfg, sphere, seed=0)
+        if ref is None or r["wall_ms"] < ref["wall_ms"]:
+            ref = r
+    est_s = PoseEstimator(pe, ppf, PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=p)), dev)
+    o_st, o_wall = ours_stages(est_s, idxs=idx)
+    out["sampled_100k"] = table(ref, o_st, o_wall)
+    # (ii) dense N^2 pairs with the trained-like vote load of the headline number
+    inj = inject[0]
+    if inj is not None:
+        lut = est.lut
+        b = inj.long()
+        tr = torch.stack([lut[b[:, 0]], lut[32 + b[:, 1]]], -1).contiguous()
+        ii = torch.arange(n, device=dev, dtype=torch.int32)
+        idx_d = torch.stack([ii[:, None].expand(n, n), ii[None, :].expand(n, n)], -1).reshape(-1, 2).contiguous()
+        ref = None
+        for _ in range(2):
+            r = ref_gpu_pipeline.estimate(pc, nrm, sd_pe, sd_ppf, idx_d, cfg, sphere, seed=0, inject_tr=tr)
+            if ref is None or r["wall_ms"] < ref["wall_ms"]:
+                ref = r
+        del idx_d, tr
+        o_st, o_wall = ours_stages(est, inject_bins=inj)
+        out["dense_n2_trained_like"] = table(ref, o_st, o_wall)
+    out["note"] = ("reference = models/voting.py kernel strings compiled for sm_100a (oracle/_ref/*.cubin) with the reference's "
+                   "launch shapes + the reference modules restated on torch-CUDA (cuBLAS SGEMM, ATen), host round trips as in "
+                   "nocs/inference.py; ours = cppf_pose_fused.  Same cloud, same weights, same pairs.")
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------ main
@@ -216,8 +325,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgj,
-                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"],
-                                 "kind": "reference" if r["impl"] == "ref_cpu" else "port", "sample": r["sample"]},
+                "cpu_baseline": cpu_baseline_block(r),
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -345,50 +453,133 @@ def main():
         ms_net, _, _, _ = run("hbm", votes_injected=False)
     sampled = None
     if args.path == "fused" and not args.no_variants:
-        # the reference's own inference regime (nocs/inference.py:177): 100 000 random pairs per object, from pinned host
-        # clouds; one cppf_pose_fused call per object, all objects of the run enqueued back to back.  The kernels of one
-        # such object are short (0.5 ms in ~25 launches), so objects are also dealt round-robin to a few CUDA streams.
+        # The reference's own inference regime (nocs/inference.py:120-129,177): 100 000 random pairs per object, clouds in
+        # host memory.  The whole object loop is ONE library call (cppf_pose_batch through pipeline.enqueue_batch): one
+        # pinned block + one H2D for all clouds, pairs drawn on the device, objects fanned out over worker streams (one
+        # object fills ~1.3 waves per kernel), launches issued by several host threads, one D2H for all records.
+        from cppf_b200.pipeline import enqueue_batch
         est_s = PoseEstimator(pe, ppf, PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=100000)), dev)
         n_s = 240
-
+        items = [(est_s, clouds[s_ % n_obj][0], clouds[s_ % n_obj][1], s_) for s_ in range(n_s)]
+        enqueue_batch(items[:16]).results(on_error="none")
+        barrier()
+        sweep = {}
+        best = None
+        for n_str, n_thr in ((1, 1), (2, 2), (4, 4), (8, 4)):
+            reps, host = [], []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                a0.record()
+                pend = enqueue_batch(items, n_streams=n_str, n_threads=n_thr)
+                host.append((time.perf_counter() - t0) * 1e6 / n_s)
+                pend.records17()                       # the host tail of every object, column-wise
+                a1.record()
+                barrier()
+                reps.append(a0.elapsed_time(a1))
+            sweep[f"streams{n_str}_threads{n_thr}"] = {"objects_per_sec": n_s / (statistics.median(reps) * 1e-3),
+                                                        "host_enqueue_us_per_object": statistics.median(host)}
+            if best is None or statistics.median(reps) < best[0]:
+                best = (statistics.median(reps), reps, statistics.median(host), n_str, n_thr)
+        ms_1, reps, host_us, n_str, n_thr = best
+        # per-object calls on one stream (round 1's path) for comparison, and the stage breakdown of one object
         def enq(s_):
             return est_s.enqueue_fused(pinned[s_ % n_obj][0], pinned[s_ % n_obj][1], seed=s_, max_cells=cells[s_ % n_obj])
         for s_ in range(3):
             enq(s_).result()
         barrier()
-        host_us = []
-        for s_ in range(20):            # host cost of one enqueue with an idle GPU
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            q = enq(s_)
-            host_us.append((time.perf_counter() - t0) * 1e6)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        pend = [enq(s_) for s_ in range(n_s)]
+        for q in pend:
             q.result()
+        a1.record()
         barrier()
-        reps = []
-        for _ in range(3):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            pend = [enq(s_) for s_ in range(n_s)]
-            for q in pend:
-                q.result()
-            a1.record()
-            barrier()
-            reps.append(a0.elapsed_time(a1))
-        ms_1 = statistics.median(reps)
+        ms_loop = a0.elapsed_time(a1)
         stage_s = {}
         if timing:                      # stage breakdown from a separate short run (event records slow short objects down)
             L.cppf_timing_collect(timing, (C.c_float * len(stage_names))())
             est_s.timing = timing
             for s_ in range(20):
-                est_s.enqueue_fused(pinned[s_ % n_obj][0], pinned[s_ % n_obj][1], seed=s_, max_cells=cells[s_ % n_obj]).result()
+                enq(s_).result()
             acc = (C.c_float * len(stage_names))()
             calls = L.cppf_timing_collect(timing, acc)
             est_s.timing = None
             stage_s = {nm: round(acc[i] / max(calls, 1), 4) for i, nm in enumerate(stage_names)}
         sampled = {"objects_per_sec_per_gpu": n_s / (ms_1 * 1e-3), "pairs_per_sec_per_gpu": n_s * 100000 / (ms_1 * 1e-3),
-                   "ms_per_object": ms_1 / n_s, "ms_per_object_repeats": [r / n_s for r in reps], "host_enqueue_us_per_object": statistics.median(host_us), "stage_ms": stage_s,
-                   "pairs_per_object": 100000,
-                   "note": "reference regime: P = 100 000 sampled pairs (nocs/inference.py:177), host clouds in, pose records out"}
+                   "ms_per_object": ms_1 / n_s, "ms_per_object_repeats": [r / n_s for r in reps],
+                   "host_enqueue_us_per_object": host_us, "n_streams": n_str, "n_threads": n_thr, "sweep": sweep,
+                   "per_object_calls_one_stream": {"objects_per_sec": n_s / (ms_loop * 1e-3), "ms_per_object": ms_loop / n_s},
+                   "stage_ms": stage_s, "pairs_per_object": 100000, "objects_per_batch": n_s,
+                   "note": "reference regime: P = 100 000 sampled pairs (nocs/inference.py:177), host clouds in, pose records "
+                           "out, the object loop (nocs/inference.py:120-129) as ONE cppf_pose_batch call; timed region = "
+                           "packing + H2D + all kernels + D2H + host tail of all objects"}
+    trained = None
+    ckpt = os.path.join(ROOT, "tests", "golden", "trained_bottle.npz")
+    if args.path == "fused" and not args.no_variants and os.path.exists(ckpt):
+        # the same dense workload with the TRAINED checkpoint (oracle/train_synth_bottle.py: the reference modules trained on
+        # this synthetic bottle) and NO bin injection: the votes are the network's own
+        d = np.load(ckpt)
+        pe_t = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32)
+        ppf_t = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=141)
+        pe_t.load_state_dict({k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("pe/")})
+        ppf_t.load_state_dict({k[4:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("ppf/")})
+        est_t = PoseEstimator(pe_t.to(dev).eval(), ppf_t.to(dev).eval(), pcfg, dev)
+        res_t = [(torch.from_numpy(p).to(dev), torch.from_numpy(q).to(dev)) for p, q in clouds[:8]]
+        for s_ in range(2):
+            est_t.enqueue_fused(res_t[s_][0], res_t[s_][1], seed=s_, max_cells=cells[s_]).result()
+        if timing:
+            L.cppf_timing_collect(timing, (C.c_float * len(stage_names))())
+            est_t.timing = timing
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        pend = [est_t.enqueue_fused(res_t[s_][0], res_t[s_][1], seed=s_, max_cells=cells[s_]) for s_ in range(8)]
+        poses = [q.result() for q in pend]
+        a1.record()
+        barrier()
+        ms_t = a0.elapsed_time(a1) / 8
+        stage_t = {}
+        if timing:
+            acc = (C.c_float * len(stage_names))()
+            calls = L.cppf_timing_collect(timing, acc)
+            est_t.timing = None
+            stage_t = {nm: round(acc[i] / max(calls, 1), 4) for i, nm in enumerate(stage_names)}
+        err_T = float(np.mean([np.linalg.norm(q["T_host"]) for q in poses]))          # the bottles are centred at the origin
+        trained = {"value": pairs_per_obj / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t, "stage_ms": stage_t,
+                   "mean_survivors": float(np.mean([q["n_survivors"] for q in poses])),
+                   "mean_centre_error_m": err_T, "mean_abs_up_y": float(np.mean([abs(q["up"][1]) for q in poses])),
+                   "note": "dense N^2 pairs, weights = tests/golden/trained_bottle.npz (the reference modules trained on the "
+                           "synthetic bottle), votes = the network's own draws (no injection); the poses are checked: centre "
+                           "error in metres (res = 4e-3), |up . y| (the bottles stand along y)"}
+    # ---- algorithmic work of the vote launch and the same-run peaks, measured (untimed)
+    vote_work = None
+    if rank == 0 and args.path == "fused":
+        pcd = torch.from_numpy(clouds[args.warmup][0]).to(dev)
+        corner_np, dims = synth.vote_grid_geometry(clouds[args.warmup][0], synth.BOTTLE["res"])
+        cnt = torch.zeros(3, dtype=torch.int64, device=dev)
+        sp = torch.cuda.current_stream(dev).cuda_stream
+        inj = inject[args.warmup]
+        if inj is not None:
+            bins4 = torch.zeros((pairs_per_obj, 4), dtype=torch.uint8, device=dev)
+            bins4[:, :inj.shape[1]] = inj
+            _lib.check(L.cppf_vote_count(pcd.data_ptr(), None, bins4.data_ptr(), est.lut.data_ptr(), None, 0,
+                                         torch.from_numpy(corner_np).to(dev).data_ptr(), float(synth.BOTTLE["res"]), n,
+                                         pairs_per_obj, 72, dims[0], dims[1], dims[2], 1, cnt.data_ptr(), sp), "cppf_vote_count")
+            c = cnt.cpu().numpy()
+            pk = (C.c_double * 3)()
+            _lib.check(L.cppf_peak_shared_atomics(dims[0], dims[1], dims[2], 0, 5, C.byref(pk, 0), sp), "peak")
+            _lib.check(L.cppf_peak_shared_atomics(dims[0], dims[1], dims[2], 1, 5, C.byref(pk, 8), sp), "peak")
+            _lib.check(L.cppf_peak_global_red(dims[0], dims[1], dims[2], 3, C.byref(pk, 16), sp), "peak")
+            vote_work = {"rotation_steps": int(c[0]), "in_bounds_candidates": int(c[1]), "live_pairs": int(c[2]),
+                         "atomics": int(c[1]) * 8, "grid_dims": list(dims),
+                         "peak_shared_random_bank_gatoms": pk[0], "peak_shared_conflict_free_gatoms": pk[1],
+                         "peak_global_fp32_red_gatoms": pk[2]}
+            del bins4
+    gpu_ref = None
+    if rank == 0 and args.path == "fused" and not args.no_variants:
+        gpu_ref = gpu_reference_arm(dev, clouds, inject, est, pe, ppf, stage_names, L, timing, args)
     total_pairs = world * args.steps * pairs_per_obj
     value = total_pairs / (ms_hbm * 1e-3)
     e2e = total_pairs / (ms_e2e * 1e-3)
@@ -402,29 +593,27 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))      # kernels are timed inside a long step
         peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+        ncu, ncu_stale = ncu_constants()
         kern = dict(timers)
         # Algorithmic work per launch.  Dense pairs are enumerated in-kernel (no index read).
         #   encode_sample : 24 B/pair written (4 bin bytes + 5 tail floats); 23 968 FLOP/pair canonical pair MLP
         #                   (models/model.py:12-23,87; 13.9 k executed after the per-point pre-projection of layer 0)
-        #   vote          : 4 B/pair read (bins); ~180 shared-memory atomics/pair under the trained-like load
+        #   vote          : 4 B/pair read (bins); atomics = 8 x in-bounds candidates, COUNTED in this run (cppf_vote_count)
         #   twopass       : first-pass encode writes 64 fp32 logits/pair, vote reads 8 B (mu,nu)/pair
         algo_bytes = {"encode_sample": pairs_per_obj * 24, "vote": pairs_per_obj * 4, "backvote": pairs_per_obj * 5,
                       "stats": pairs_per_obj * 24,
                       "ppf_encode_pass1": pairs_per_obj * 64 * 4, "ppf_vote": pairs_per_obj * 8}
         algo_flops = {"encode_sample": pairs_per_obj * 23968.0, "ppf_encode_pass1": pairs_per_obj * (23968.0 - 2 * 16 * 77)}
-        binding = {"encode_sample": "SIMT epilogues between the tcgen05 MMA steps (3xTF32 chain; issue slots 46 %, tensor pipe 44 %)" if args.encoder == "tc"
-                                    else "fp32 FMA pipe",
-                   "vote": "shared-memory pipe (74 % of peak wavefronts, 3.6 bank/same-cell replays per ATOMS) and issue slots (77 %)",
-                   "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput", "stats": "HBM gather (2.9 TB/s)",
+        binding = {"encode_sample": "SIMT epilogues between the tcgen05 MMA steps (3xTF32 chain)" if args.encoder == "tc" else "fp32 FMA pipe",
+                   "vote": "shared-memory atomic pipe (random-bank replays) and issue slots",
+                   "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput", "stats": "HBM gather",
                    "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "FP32/issue (two-sweep kNN select + one-warp-per-point SPRIN MLP)"}
         detail = {}
         for k, v in kern.items():
             t = v["avg_ms"] * 1e-3
             d = {"avg_ms": v["avg_ms"], "binding_resource": binding.get(k)}
-            if k in BINDING_NCU:
-                d["binding_utilisation_ncu"] = BINDING_NCU[k]
-            if k in TRAFFIC_NCU:
-                d["dram_bytes_per_launch_ncu"] = TRAFFIC_NCU[k]
+            if k in ncu:                 # profiler-only counters, with the capture and source hash they belong to
+                d["ncu"] = {kk: vv for kk, vv in ncu[k].items() if kk != "source_sha256"}
             if k in algo_bytes:
                 d["hbm"] = {"achieved": algo_bytes[k] / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": algo_bytes[k] / t / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": algo_bytes[k]}
@@ -436,34 +625,47 @@ def main():
                                "algorithmic_flops_per_launch": algo_flops[k],
                                "note": "canonical fp32 pair-MLP FLOPs against the measured dense bf16 peak; the kernel runs "
                                        "tf32 (half the bf16 rate) in 3 passes for fp32-grade logits"}
-            if k == "vote" and args.votes == "trained_like" and args.path == "fused" and args.n_points == 4096:
-                # the vote phase is measured in atomics/s against a same-box microbenchmark
-                # (tools/atomics_bench.cu -> profiles/r1_atomics_microbench.json); the count per launch is ncu's
-                # predicated-on thread count of the ATOMS instructions of this workload (profiles/r1f_kernels_ncu.md)
-                n_atom = 3.0246e9
-                d["atomics"] = {"per_launch_ncu": n_atom, "achieved": n_atom / t / 1e9, "unit": "G atomics/s",
-                                "peak_shared_u32_trilinear_pattern_microbench": 2813.4, "frac": n_atom / t / 1e9 / 2813.4,
-                                "global_fp32_red_microbench": {"uniform_71KB": 93.9, "concentrated_71KB": 16.4},
-                                "note": "shared-memory u32 atomics of the privatised grid; the microbenchmark peak is the bare "
-                                        "8-corner splat pattern with nothing else in the loop"}
+            if k == "vote" and vote_work is not None:
+                # the vote phase in atomics/s.  Count and peaks are measured in THIS run: cppf_vote_count
+                # walks the same bins with the reference's acceptance test; cppf_peak_* time the bare patterns.
+                n_atom = float(vote_work["atomics"])
+                d["atomics"] = {"per_launch": n_atom, "per_pair": n_atom / pairs_per_obj, "achieved": n_atom / t / 1e9,
+                                "unit": "G atomics/s", "peak_random_bank": vote_work["peak_shared_random_bank_gatoms"],
+                                "frac": n_atom / t / 1e9 / vote_work["peak_shared_random_bank_gatoms"],
+                                "peak_conflict_free": vote_work["peak_shared_conflict_free_gatoms"],
+                                "frac_of_conflict_free": n_atom / t / 1e9 / vote_work["peak_shared_conflict_free_gatoms"],
+                                "global_fp32_red_same_grid": vote_work["peak_global_fp32_red_gatoms"],
+                                "work": vote_work,
+                                "note": "peak_random_bank: 32 lanes x the 8-corner splat of a random cell each, nothing else in "
+                                        "the loop (what any unsorted scatter into shared memory can reach); "
+                                        "peak_conflict_free: lane l in bank l (the hardware roof); all measured in this process"}
             detail[k] = d
         roof = None
-        timed = [k for k in kern if k in algo_bytes]
-        if timed:
-            dom = max(timed, key=lambda k: kern[k]["avg_ms"])
-            use_tensor = dom in algo_flops and args.encoder == "tc"
-            src = detail[dom]["tensor" if use_tensor else "hbm"]
-            roof = {"kernel": dom, "bound": "tensor" if use_tensor else "hbm", "achieved": src["achieved"], "peak": src["peak"],
-                    "unit": src["unit"], "frac": src["frac"], "traffic": TRAFFIC_NCU.get(dom), "peak_source": peak_src,
-                    "avg_launch_ms": kern[dom]["avg_ms"], "binding_resource": binding.get(dom),
-                    "note": "dominant kernel by live CUDA-event time; none of this path's kernels is HBM-bound "
-                            "(logits never reach HBM) -- see roofline_detail for every kernel against the resource "
-                            "that binds it"}
+        if "vote" in detail and "atomics" in detail["vote"] and kern["vote"]["avg_ms"] >= max(v["avg_ms"] for v in kern.values()):
+            at = detail["vote"]["atomics"]
+            roof = {"kernel": "vote", "bound": "smem_atomics", "achieved": at["achieved"], "peak": at["peak_random_bank"],
+                    "unit": "G atomics/s", "frac": at["frac"], "traffic": (ncu.get("vote") or {}).get("dram_bytes_per_launch"),
+                    "peak_source": "cppf_peak_shared_atomics, same process (random-bank 8-corner pattern on the same grid)",
+                    "peak_conflict_free": at["peak_conflict_free"], "frac_of_conflict_free": at["frac_of_conflict_free"],
+                    "algorithmic_atomics_per_launch": at["per_launch"], "avg_launch_ms": kern["vote"]["avg_ms"],
+                    "hbm_frac_for_the_record": detail["vote"]["hbm"]["frac"],
+                    "note": "dominant kernel by live CUDA-event time.  It accumulates into a grid privatised in shared memory: "
+                            "its HBM traffic is 4 B/pair (hbm_frac_for_the_record) and says nothing; the resource it uses is "
+                            "the shared-memory atomic pipe, so achieved / peak are in atomics/s (SURVEY.md 8d), count and "
+                            "peak both measured in this run"}
+        else:
+            timed = [k for k in kern if k in algo_bytes]
+            if timed:
+                dom = max(timed, key=lambda k: kern[k]["avg_ms"])
+                use_tensor = dom in algo_flops and args.encoder == "tc"
+                src = detail[dom]["tensor" if use_tensor else "hbm"]
+                roof = {"kernel": dom, "bound": "tensor" if use_tensor else "hbm", "achieved": src["achieved"],
+                        "peak": src["peak"], "unit": src["unit"], "frac": src["frac"],
+                        "traffic": (ncu.get(dom) or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                        "avg_launch_ms": kern[dom]["avg_ms"], "binding_resource": binding.get(dom)}
         cpu = None
         if not args.no_cpu_baseline:
-            r = run_cpu_reference(args, 2, 1, args.cpu_sample_pairs)
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"],
-                   "kind": "reference" if r["impl"] == "ref_cpu" else "port", "sample": r["sample"]}
+            cpu = cpu_baseline_block(run_cpu_reference(args, 2, 1, args.cpu_sample_pairs))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_hbm / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": cfgj,
@@ -471,13 +673,17 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "objects_per_sec": world * args.steps / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_detail": detail, "kernels": kern,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "ncu_constants_dropped_as_stale": ncu_stale}
         if ms_net is not None:
             line["variant_network_votes"] = {"value": total_pairs / (ms_net * 1e-3), "unit": UNIT,
                                              "ms_per_step": ms_net / args.steps,
                                              "note": "no bin injection: votes from the random-init network's own samples"}
+        if trained is not None:
+            line["variant_trained_network"] = trained
         if sampled is not None:
             line["variant_sampled_100k"] = sampled
+        if gpu_ref is not None:
+            line["vs_gpu_reference"] = gpu_ref
         print(json.dumps(line))
     if dist_on:
         dist.destroy_process_group()

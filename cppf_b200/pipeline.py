@@ -341,11 +341,13 @@ class PoseEstimator:
 
     @torch.no_grad()
     def enqueue_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, inject_bins=None, max_cells=None,
-                      routed_max_cells=0, record_host=None):
+                      routed_max_cells=0, record_host=None, device_pairs: bool = False):
         """Enqueue the whole per-object path (cppf_pose_fused) on the current stream and return a PendingPose;
         nothing here waits for the GPU when max_cells is given.  pc_in / nrm_in: float32 [N,3], host (numpy or
         pinned torch) or CUDA.  max_cells / routed_max_cells: capacity of the vote grid in the shared-memory kernel /
-        in the routed-slab kernel (see grid_capacity; default: derived from the cloud's bounding box)."""
+        in the routed-slab kernel (see grid_capacity; default: derived from the cloud's bounding box).
+        device_pairs: draw the cfg.n_pairs random pairs of nocs/inference.py:177 inside the library (Philox keyed by
+        `seed`) instead of with torch.randint -- the pairs cppf_pose_batch / enqueue_batch use."""
         cfg, dev = self.cfg, self.device
         L = _lib.lib()
         n = pc_in.shape[0]
@@ -359,20 +361,24 @@ class PoseEstimator:
                                "configuration; use estimate_fused(staged=True)")
         pc = torch.as_tensor(pc_in).to(dev, torch.float32, non_blocking=True).contiguous()
         nrm = torch.as_tensor(nrm_in).to(dev, torch.float32, non_blocking=True).contiguous()
-        if idxs is None and cfg.n_pairs > 0:                                        # nocs/inference.py:177
+        sample_dev = bool(device_pairs and idxs is None and cfg.n_pairs > 0)
+        if sample_dev:
+            pass
+        elif idxs is None and cfg.n_pairs > 0:                                      # nocs/inference.py:177
             if self._gen is None:
                 self._gen = torch.Generator(device=dev)
             idxs = torch.randint(0, n, (cfg.n_pairs, 2), generator=self._gen.manual_seed(seed), device=dev, dtype=torch.int32)
         elif idxs is not None:
             idxs = torch.as_tensor(idxs).to(dev).contiguous()
             assert idxs.dtype in (torch.int32, torch.int64)
-        n_pairs = n * n if idxs is None else idxs.shape[0]
+        n_pairs = cfg.n_pairs if sample_dev else (n * n if idxs is None else idxs.shape[0])
         if uniforms is not None:
             assert uniforms.shape == (n_pairs, 4) and uniforms.is_contiguous() and uniforms.dtype == torch.float32
         if inject_bins is not None:
             assert inject_bins.dtype == torch.uint8 and inject_bins.is_contiguous() and inject_bins.shape[0] == n_pairs
         ws = self._workspace(n, n_pairs, int(max_cells), int(routed_max_cells))
         rec = torch.empty(16, dtype=torch.float64, device=dev)
+        a_sample = int(sample_dev)
         a = _lib.PoseArgs()
         a.struct_bytes = C.sizeof(_lib.PoseArgs)
         a.pc, a.nrm = pc.data_ptr(), nrm.data_ptr()
@@ -387,7 +393,7 @@ class PoseEstimator:
         a.n_points, a.idx_is_64 = n, int(idxs is not None and idxs.dtype == torch.int64)
         a.knn, a.n_rots, a.adaptive, a.regress_right = cfg.knn, cfg.num_rots, int(cfg.adaptive_voting), int(cfg.regress_right)
         a.n_sphere, a.inject_cols = self.sphere.shape[0], (inject_bins.shape[1] if inject_bins is not None else 0)
-        a.max_cells, a.routed_max_cells = int(max_cells), int(routed_max_cells)
+        a.max_cells, a.routed_max_cells, a.sample_pairs = int(max_cells), int(routed_max_cells), a_sample
         a.res, a.tol, a.cos_thr = float(cfg.res), float(3 * cfg.res), self.cos_thr
         with torch.cuda.device(dev):
             _lib.check(L.cppf_pose_fused(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "cppf_pose_fused")
@@ -406,6 +412,41 @@ class PoseEstimator:
             raise RuntimeError("vote grid larger than the capacity given to cppf_pose_fused (status %d)" % int(r[15]))
         old = np.concatenate([[r[0]], r[1:1 + n_dirs], r[3:9], r[9:12]])
         return self._pose_from_record(old, n_dirs, tuple(int(v) for v in r[12:15]))
+
+    def _records17_from_records16(self, r):
+        """[m,16] pose records of this category -> [m,17] float32 gather records (sunrgbd/inference.py:287:
+        class_id, score = survivor count, scale x3, R x9 row-major, T x3), column-wise: the host tail of
+        nocs/inference.py:305-339 for a whole batch.  Rows without survivors / over capacity get score 0 and identity R."""
+        cfg = self.cfg
+        m = r.shape[0]
+        ok = (r[:, 15] == 0) & (r[:, 6] > 0)
+        gy, gz = np.maximum(r[:, 13], 1).astype(np.int64), np.maximum(r[:, 14], 1).astype(np.int64)
+        flat = r[:, 0].astype(np.int64)
+        cell = np.stack([flat // (gy * gz), (flat % (gy * gz)) // gz, flat % gz], -1)
+        T = r[:, 9:12] + cell * cfg.res                                             # :209
+        up = self.sphere_np[np.clip(r[:, 1].astype(np.int64), 0, len(self.sphere_np) - 1)] * np.where(r[:, 7] < 0, -1.0, 1.0)[:, None]
+        if cfg.regress_right:
+            right = self.sphere_np[np.clip(r[:, 2].astype(np.int64), 0, len(self.sphere_np) - 1)] * np.where(r[:, 8] < 0, -1.0, 1.0)[:, None]
+            right = right - (up * right).sum(-1, keepdims=True) * up
+        else:
+            right = np.stack([np.zeros(m), -up[:, 2], up[:, 1]], -1)
+        right = right / (np.linalg.norm(right, axis=-1, keepdims=True) + 1e-9)
+        bad = np.linalg.norm(right, axis=-1) < 1e-7
+        if bad.any():
+            alt = np.stack([up[:, 1], -up[:, 0], np.zeros(m)], -1)
+            right[bad] = alt[bad] / (np.linalg.norm(alt[bad], axis=-1, keepdims=True) + 1e-9)
+        if cfg.z_right:
+            R = np.stack([np.cross(up, right), up, right], -1)
+        else:
+            R = np.stack([right, up, np.cross(right, up)], -1)
+        cnt = np.where(ok, r[:, 6], 1.0)
+        scale = np.exp((r[:, 3:6] / cnt[:, None]).astype(np.float32)) * np.asarray(cfg.scale_mean) * cfg.scale_mul     # :335
+        out = np.zeros((m, 17), np.float32)
+        out[:, 1] = np.where(ok, r[:, 6], 0.0)
+        out[:, 2:5] = scale
+        out[:, 5:14] = np.where(ok[:, None], R.reshape(m, 9), np.eye(3).reshape(1, 9))
+        out[:, 14:17] = T
+        return out
 
     @torch.no_grad()
     def estimate_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, return_debug: bool = False,
@@ -494,10 +535,181 @@ class PoseEstimator:
         return out
 
 
-def estimate_many(items, sync: bool = True):
+_ARGS_DTYPE = None
+
+
+def _args_dtype():
+    """numpy mirror of struct cppf_pose_args (include/cppf_b200.h), so that a whole batch of argument blocks is filled
+    column-wise; checked against the compiled layout."""
+    global _ARGS_DTYPE
+    if _ARGS_DTYPE is None:
+        ct = {C.c_int64: "<i8", C.c_uint64: "<u8", C.c_void_p: "<u8", C.c_int: "<i4", C.c_float: "<f4"}
+        dt = np.dtype({"names": [f for f, _ in _lib.PoseArgs._fields_],
+                       "formats": [ct[t] for _, t in _lib.PoseArgs._fields_],
+                       "offsets": [getattr(_lib.PoseArgs, f).offset for f, _ in _lib.PoseArgs._fields_],
+                       "itemsize": C.sizeof(_lib.PoseArgs)})
+        assert dt.itemsize == _lib.lib().cppf_pose_args_bytes()
+        _ARGS_DTYPE = dt
+    return _ARGS_DTYPE
+
+
+class PendingBatch:
+    """A batch enqueued by ONE cppf_pose_batch call; .results() waits for the [n,16] record block (one device->host copy)
+    and runs the host tail of nocs/inference.py:305-339 for every object."""
+
+    def __init__(self, ests, records_host, done, keep):
+        self.ests, self.records_host, self.done, self._keep = ests, records_host, done, keep
+
+    def results(self, on_error="raise"):
+        """-> list of pose dicts.  on_error="none": objects whose pose could not be formed (no survivors / grid over
+        capacity) yield None instead of raising."""
+        self.done.synchronize()
+        self._keep = ()
+        recs = self.records_host.numpy()
+        out = []
+        for est, r in zip(self.ests, recs):
+            try:
+                out.append(est._pose_from_record16(r, 2 if est.cfg.regress_right else 1))
+            except RuntimeError:
+                if on_error == "raise":
+                    raise
+                out.append(None)
+        return out
+
+    def records17(self):
+        """The gather records (sunrgbd/inference.py:287 layout) of the whole batch as one float32 [n,17] array, computed
+        column-wise (no per-object Python): what shard.gather_records sends."""
+        self.done.synchronize()
+        self._keep = ()
+        recs = self.records_host.numpy()
+        out = np.zeros((len(self.ests), 17), np.float32)
+        groups = {}
+        for i, e in enumerate(self.ests):
+            groups.setdefault(id(e), (e, []))[1].append(i)
+        for est, rows in groups.values():
+            rows = np.asarray(rows)
+            out[rows] = est._records17_from_records16(recs[rows])
+        return out
+
+
+@torch.no_grad()
+def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None):
+    """The object loop of nocs/inference.py:120-129 as ONE library call (cppf_pose_batch).
+    items = [(estimator, pc, normals, seed), ...]: float32 [N_i,3] clouds, host (numpy / pinned torch) or CUDA; objects may
+    belong to different categories (estimators).  Host clouds are packed into one pinned block and copied with ONE
+    host->device copy; the point pairs of nocs/inference.py:177 are drawn on the device (cfg.n_pairs > 0; 0 = all N^2
+    pairs); all records come back with ONE device->host copy.  -> PendingBatch."""
+    if not items:
+        raise ValueError("empty batch")
+    dev = items[0][0].device
+    L = _lib.lib()
+    n_obj = len(items)
+    n_streams = max(1, min(int(n_streams), 16, n_obj))
+    n_threads = max(1, min(int(n_threads), n_streams))
+    ns = np.array([it[1].shape[0] for it in items], np.int64)
+    # ---- clouds: one pinned staging block, one H2D (CUDA clouds are used in place)
+    on_dev = [isinstance(it[1], torch.Tensor) and it[1].is_cuda for it in items]
+    host_rows = int(sum(n for n, d in zip(ns, on_dev) if not d))
+    keep = []
+    ptr_pc, ptr_nrm = np.zeros(n_obj, np.uint64), np.zeros(n_obj, np.uint64)
+    if host_rows:
+        stage = torch.empty((2 * host_rows, 3), dtype=torch.float32, pin_memory=True)
+        sn = stage.numpy()
+        off = 0
+        offs = []
+        for (est, pc, nrm, _), d, n in zip(items, on_dev, ns):
+            if d:
+                offs.append(-1)
+                continue
+            sn[off:off + n] = pc.numpy() if isinstance(pc, torch.Tensor) else pc
+            sn[off + n:off + 2 * n] = nrm.numpy() if isinstance(nrm, torch.Tensor) else nrm
+            offs.append(off)
+            off += 2 * n
+        dstage = stage.to(dev, non_blocking=True)
+        keep += [stage, dstage]
+        base = dstage.data_ptr()
+        for i, (o, n) in enumerate(zip(offs, ns)):
+            if o >= 0:
+                ptr_pc[i], ptr_nrm[i] = base + 12 * o, base + 12 * (o + int(n))
+    for i, ((est, pc, nrm, _), d) in enumerate(zip(items, on_dev)):
+        if d:
+            pcd, nd = pc.to(torch.float32).contiguous(), nrm.to(torch.float32).contiguous()
+            keep += [pcd, nd]
+            ptr_pc[i], ptr_nrm[i] = pcd.data_ptr(), nd.data_ptr()
+    # ---- grid capacities (nocs/inference.py:194-195) and pair counts
+    caps = []
+    for (est, pc, nrm, _), d in zip(items, on_dev):
+        cap = est.grid_capacity(pc)
+        if cap is None:
+            raise RuntimeError("vote grid too large for cppf_pose_batch; use estimate_fused(staged=True) for this object")
+        if not est._onecall_ok():
+            raise RuntimeError("cppf_pose_batch needs the tcgen05 encoder and the reference PointEncoder / head configuration")
+        caps.append(cap)
+    caps = np.asarray(caps, np.int64)
+    pairs = np.array([(it[0].cfg.n_pairs if n_pairs is None else n_pairs) for it in items], np.int64)
+    dense = pairs <= 0
+    pairs = np.where(dense, ns * ns, pairs)
+    # ---- one workspace per worker stream, sized for the largest object it serves
+    ws = []
+    for s_ in range(n_streams):
+        rows = np.arange(s_, n_obj, n_streams)
+        nb = 0
+        for i in rows:
+            cfg = items[i][0].cfg
+            nb = max(nb, L.cppf_pose_workspace_bytes(int(ns[i]), 0 if dense[i] else int(pairs[i]), cfg.knn, int(caps[i, 0]),
+                                                     int(caps[i, 1]), cfg.num_rots, items[i][0].sphere.shape[0],
+                                                     int(cfg.rot_subsample or 0)))
+        slot = ("batch", dev.index or 0, s_)
+        w = _WORKSPACES.get(slot)
+        if w is None or w.numel() < nb:
+            _WORKSPACES[slot] = None
+            w = _WORKSPACES[slot] = torch.empty(nb, dtype=torch.uint8, device=dev)
+        ws.append(w)
+    rec = torch.empty((n_obj, 16), dtype=torch.float64, device=dev)
+    # ---- argument blocks, filled column-wise per category
+    a = np.zeros(n_obj, _args_dtype())
+    a["struct_bytes"] = a.dtype.itemsize
+    a["pc"], a["nrm"] = ptr_pc, ptr_nrm
+    a["n_points"], a["n_pairs"] = ns, pairs
+    a["sample_pairs"] = (~dense).astype(np.int32)
+    a["max_cells"], a["routed_max_cells"] = caps[:, 0], caps[:, 1]
+    a["seed"] = np.array([int(it[3]) for it in items], np.uint64)
+    a["record"] = rec.data_ptr() + 128 * np.arange(n_obj, dtype=np.uint64)
+    wsp = np.array([w.data_ptr() for w in ws], np.uint64)
+    wsb = np.array([w.numel() for w in ws], np.int64)
+    a["workspace"], a["workspace_bytes"] = wsp[np.arange(n_obj) % n_streams], wsb[np.arange(n_obj) % n_streams]
+    groups = {}
+    for i, it in enumerate(items):
+        groups.setdefault(id(it[0]), (it[0], []))[1].append(i)
+    for est, rows in groups.values():
+        cfg = est.cfg
+        rows = np.asarray(rows)
+        a["pe_blob"][rows], a["tc_blob"][rows] = est.pe.pe_blob(dev).data_ptr(), est.ppf.tc_blob(dev).data_ptr()
+        a["lut"][rows], a["sphere"][rows] = est.lut.data_ptr(), est.sphere.data_ptr()
+        a["rot_subsample"][rows] = int(cfg.rot_subsample or 0)
+        a["knn"][rows], a["n_rots"][rows] = cfg.knn, cfg.num_rots
+        a["adaptive"][rows], a["regress_right"][rows] = int(cfg.adaptive_voting), int(cfg.regress_right)
+        a["n_sphere"][rows] = est.sphere.shape[0]
+        a["res"][rows], a["tol"][rows], a["cos_thr"][rows] = float(cfg.res), float(3 * cfg.res), est.cos_thr
+    with torch.cuda.device(dev):
+        _lib.check(L.cppf_pose_batch(a.ctypes.data, n_obj, n_streams, n_threads, torch.cuda.current_stream(dev).cuda_stream),
+                   "cppf_pose_batch")
+    host = torch.empty((n_obj, 16), dtype=torch.float64, pin_memory=True)
+    host.copy_(rec, non_blocking=True)
+    done = torch.cuda.Event()
+    done.record()
+    return PendingBatch([it[0] for it in items], host, done, keep + [rec, a, ws])
+
+
+def estimate_many(items, sync: bool = True, batched: bool = True, n_streams: int = 4, n_threads: int = 4):
     """Batch of objects, possibly of different categories: items = [(estimator, pc, normals, seed), ...]
     (the reference loops over them one at a time and picks the category's weights, nocs/inference.py:120-129).
-    Every object is enqueued before the first record is read, so the GPU works through the batch without
-    waiting for the host.  Returns the list of pose dicts (or PendingPose objects with sync=False)."""
+    batched=True: ONE cppf_pose_batch call (objects overlap on worker streams; pairs drawn on the device).
+    batched=False: one cppf_pose_fused call per object on the current stream, pairs drawn by torch.randint.
+    Either way every object is enqueued before the first record is read.  Returns the list of pose dicts (sync=True),
+    or a PendingBatch / list of PendingPose."""
+    if batched and all(it[0]._onecall_ok() and it[0].grid_capacity(it[1]) is not None for it in items):
+        pend = enqueue_batch(items, n_streams=n_streams, n_threads=n_threads)
+        return pend.results() if sync else pend
     pend = [est.estimate_fused(pc, nrm, seed=seed, sync=False) for est, pc, nrm, seed in items]
     return [p.result() for p in pend] if sync else pend

@@ -45,7 +45,7 @@ def pair_mlp(x, sd):
 
 def ppf_encode_idx(pc, nrm, feat, idxs, sd):
     """models/model.py:117-137 forward_with_idx.  pc,nrm [N,3], feat [N,F], idxs [P,2] -> [P,out]."""
-    idxs = torch.as_tensor(np.asarray(idxs)).long()
+    idxs = idxs.long() if isinstance(idxs, torch.Tensor) else torch.as_tensor(np.asarray(idxs)).long().to(pc.device)
     ia, ib = idxs[:, 0], idxs[:, 1]
     d = pc[ia] - pc[ib]                                     # :120  a minus b
     dn = torch.norm(d, dim=-1)                              # :121

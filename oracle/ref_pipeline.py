@@ -19,6 +19,8 @@ Anything not injected is drawn from ``torch.Generator().manual_seed(seed)`` / ``
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 import torch
 
@@ -44,9 +46,13 @@ def exact_knn(pc: torch.Tensor, k: int) -> torch.Tensor:
 
 
 def estimate(pc, nrm, sd_pe, sd_ppf, idxs, cfg, noise=None, seed=0, sphere=None, impl=None, cdist_knn=False,
-             return_debug=False):
+             return_debug=False, timings=None):
     """pc, nrm float32 [N,3]; sd_*: state_dicts of the reference modules; idxs int [P,2] (:177); cfg: dict with the category
-    constants (config/category/*.yaml + config/config.yaml).  -> dict(RT, scales, T, flat, n_survivors, best_bins, ...)."""
+    constants (config/category/*.yaml + config/config.yaml).  -> dict(RT, scales, T, flat, n_survivors, best_bins, ...).
+    timings: optional dict that receives the wall-clock seconds of the per-OBJECT stages ("point_encoder": kNN + SPRIN,
+    O(N k); "orientation": :258-284 on the 10 000-survivor sub-sample, a constant once more than 10 000 pairs survive) and
+    of the per-PAIR stages ("pairs": everything else)."""
+    t_start = time.perf_counter()
     noise = noise or {}
     impl = impl or ("ref_cpu" if clib.have_ref_cpu() else "oracle")
     gen = torch.Generator().manual_seed(int(seed))
@@ -60,6 +66,7 @@ def estimate(pc, nrm, sd_pe, sd_ppf, idxs, cfg, noise=None, seed=0, sphere=None,
         feat = ref_model.point_encode(tpc, tn, dist, sd_pe, cfg["knn"])
     else:
         feat = ref_model.point_encode_nbrs(tpc, tn, exact_knn(tpc, cfg["knn"]), sd_pe)
+    t_pe = time.perf_counter()
     logits = ref_model.ppf_encode_idx(tpc, tn, feat, idxs, sd_ppf)
     # ---- :183-188 sample (mu, nu)
     b_mu = _race(logits[:, :B], noise.get("q_mu"), gen)
@@ -83,6 +90,9 @@ def estimate(pc, nrm, sd_pe, sd_ppf, idxs, cfg, noise=None, seed=0, sphere=None,
     if return_debug:
         out.update(grid=grid, tr=tr, mask=mask, feat=feat)
     if len(kept) == 0:
+        if timings is not None:
+            timings.update(point_encoder=t_pe - t_start, orientation=0.0, pairs=time.perf_counter() - t_pe,
+                           orientation_is_fixed=False)
         return out
     # ---- :236-256 second encoder pass on the survivors
     l2 = ref_model.ppf_encode_idx(tpc, tn, feat, kept, sd_ppf)
@@ -90,6 +100,7 @@ def estimate(pc, nrm, sd_pe, sd_ppf, idxs, cfg, noise=None, seed=0, sphere=None,
     sphere = ref_model.fibonacci_sphere(int(4 * np.pi / (cfg.get("angle_prec", 1.5) / 180 * np.pi))) if sphere is None else sphere
     thr = np.cos(cfg.get("angle_prec", 1.5) / 180 * np.pi)
     dirs, bests = [], []
+    t_orient = 0.0
     for j, (c0, aux_col, tag) in enumerate([(2 * B, -5, "up"), (2 * B + RB, -4, "right")]):
         if j == 1 and not cfg.get("regress_right", False):                            # :260-261
             continue
@@ -105,10 +116,12 @@ def estimate(pc, nrm, sd_pe, sd_ppf, idxs, cfg, noise=None, seed=0, sphere=None,
                 sel = np.argsort(np.asarray(key)[pos], kind="stable")[:m]
         else:
             sel = np.arange(len(kept))
+        t_o = time.perf_counter()
         cand = clib.rot_voting(pc, rot[sel], kept[sel].astype(np.int32), n_rots, impl=impl)        # :265-275
         counts = ((torch.from_numpy(cand.reshape(-1, 3)) @ torch.from_numpy(sphere.T.astype(np.float32))) >
                   float(np.float32(thr))).sum(0).numpy()                              # :282-283
         best = int(np.argmax(counts))                                                 # :284
+        t_orient += time.perf_counter() - t_o
         final, _, _ = ref_model.aux_sign(pc, nrm, kept, sphere[best], l2[:, aux_col].numpy())      # :286-302
         dirs.append(final)
         bests.append(best)
@@ -119,4 +132,8 @@ def estimate(pc, nrm, sd_pe, sd_ppf, idxs, cfg, noise=None, seed=0, sphere=None,
                                          z_right=cfg.get("z_right", False), regress_right=cfg.get("regress_right", False),
                                          scale_mul=cfg.get("scale_mul", 2.0))
     out.update(RT=RT, scales=scales, up=dirs[0], best_bins=bests, log_scale=log_scale)
+    if timings is not None:
+        timings.update(point_encoder=t_pe - t_start, orientation=t_orient, pairs=time.perf_counter() - t_pe - t_orient,
+                       orientation_is_fixed=bool(int(cfg.get("rot_subsample", 10000) or 0) and
+                                                 len(kept) > int(cfg.get("rot_subsample", 10000) or 0)))
     return out

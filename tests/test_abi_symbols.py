@@ -75,3 +75,12 @@ def test_dropin_package_shadows_the_reference_module_paths():
             "print('ok')\n") % (root, os.path.join(root, "dropin"))
     out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_numpy_mirror_of_pose_args_matches_the_compiled_layout():
+    """enqueue_batch fills a whole batch of cppf_pose_args column-wise through a numpy structured dtype."""
+    from cppf_b200 import pipeline
+    dt = pipeline._args_dtype()
+    assert dt.itemsize == _lib.lib().cppf_pose_args_bytes()
+    assert dt.names == tuple(f for f, _ in _lib.PoseArgs._fields_)
+    assert dt.fields["sample_pairs"][1] == _lib.PoseArgs.sample_pairs.offset

@@ -68,14 +68,16 @@ def test_state_dict_keys_match_reference_checkpoints():
         assert tuple(v.shape) == d["pe/" + k].shape
 
 
-def test_point_encoder_host_composition_matches_reference():
+def test_point_encoder_has_no_eager_path():
+    """The product PointEncoder runs only through its sm_100a kernel: CPU tensors (or a batch, or an unsupported
+    configuration) raise -- the torch-op composition lives in the oracle (oracle/ref_model.py:point_encode_nbrs, pinned to
+    the reference module by test_oracle_golden.py::test_point_encoder_matches_reference)."""
+    import pytest
     d = load_golden("encoder_bottle.npz")
     pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).eval()
     pe.load_state_dict(split_state(d, "pe/"))
-    with torch.no_grad():
-        f = pe.forward_nbrs(torch.from_numpy(d["pc"])[None], torch.from_numpy(d["nrm"])[None],
-                            torch.from_numpy(d["nbrs"])[None])
-    np.testing.assert_allclose(f[0].numpy(), d["feat_nbrs"], rtol=1e-4, atol=1e-5)
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        pe.forward_nbrs(torch.from_numpy(d["pc"])[None], torch.from_numpy(d["nrm"])[None], torch.from_numpy(d["nbrs"])[None])
 
 
 def test_unsupported_architecture_fails_loudly():
