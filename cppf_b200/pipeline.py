@@ -450,7 +450,8 @@ class PoseEstimator:
 
     @torch.no_grad()
     def estimate_fused(self, pc_in, nrm_in, seed: int = 0, idxs=None, uniforms=None, return_debug: bool = False,
-                       sync: bool = True, inject_bins=None, staged: bool = False, max_cells=None, routed_max_cells=0):
+                       sync: bool = True, inject_bins=None, staged: bool = False, max_cells=None, routed_max_cells=0,
+                       device_pairs: bool = False):
         """Same pose as `estimate`, through the fused kernels: logits, (mu,nu) floats and rotation
         candidates never reach HBM; a single 128-byte record comes back to the host.  By default the whole
         object is ONE library call (cppf_pose_fused); staged=True / return_debug=True run it kernel by kernel
@@ -459,7 +460,7 @@ class PoseEstimator:
             cap = (max_cells, routed_max_cells) if max_cells is not None else self.grid_capacity(pc_in)
             if cap is not None:
                 pend = self.enqueue_fused(pc_in, nrm_in, seed=seed, idxs=idxs, uniforms=uniforms, inject_bins=inject_bins,
-                                          max_cells=cap[0], routed_max_cells=cap[1])
+                                          max_cells=cap[0], routed_max_cells=cap[1], device_pairs=device_pairs)
                 return pend.result() if sync else pend
         return self._estimate_fused_staged(pc_in, nrm_in, seed=seed, idxs=idxs, uniforms=uniforms, return_debug=return_debug,
                                            sync=sync, inject_bins=inject_bins)

@@ -21,14 +21,14 @@ def _est(seed, cfg):
 
 def test_config3_categories_batched_on_64_cube_grids():
     """Six weight sets ("categories", nocs/inference.py:127-129) on clouds whose vote grid is exactly 64^3:
-    too large for one SM's shared memory, so the vote runs on the global-reduction kernel; the batch API must
+    too large for one SM's shared memory, so the vote runs on the routed-slab kernel; the batch API (cppf_pose_batch) must
     return what the per-object calls return, from host and from device-resident clouds."""
     cfg = PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=40000, rot_subsample=2000))
     ests = [_est(s, cfg) for s in range(3)]
     clouds = [synth.synth_cylinder_grid64(1024, s) for s in range(3)]
     for p, _ in clouds:
         assert synth.vote_grid_geometry(p, cfg.res)[1] == (64, 64, 64)
-    single = [e.estimate_fused(p, q, seed=s) for s, (e, (p, q)) in enumerate(zip(ests, clouds))]
+    single = [e.estimate_fused(p, q, seed=s, device_pairs=True) for s, (e, (p, q)) in enumerate(zip(ests, clouds))]
     many_host = estimate_many([(e, p, q, s) for s, (e, (p, q)) in enumerate(zip(ests, clouds))])
     many_dev = estimate_many([(e, torch.from_numpy(p).to(DEV), torch.from_numpy(q).to(DEV), s)
                               for s, (e, (p, q)) in enumerate(zip(ests, clouds))])
@@ -113,16 +113,19 @@ def test_full_size_vote_properties_n4096_dense():
 
 def test_degenerate_and_empty_inputs():
     """Edge cases of the reference kernels (models/voting.py:21: pairs with |ab| < 1e-7 are dropped silently): a pair list
-    made only of (a, a) pairs votes nothing, keeps no survivor and still yields a finite record; zero pairs are a no-op."""
+    made only of (a, a) pairs votes nothing and keeps no survivor -- every entry point then raises NoSurvivorsError (the
+    reference's script would carry NaNs into the pose); zero pairs are a no-op."""
     from cppf_b200 import fast, voting
+    from cppf_b200.pipeline import NoSurvivorsError
     cfg = PoseConfig.from_dict(dict(synth.BOTTLE, n_pairs=5000))
     est = _est(0, cfg)
     pc, nrm = synth.synth_bottle(300, 2)
     same = np.repeat(np.arange(300, dtype=np.int32)[:, None], 2, 1)
     for staged in (False, True):
-        out = est.estimate_fused(pc, nrm, seed=0, idxs=same, staged=staged)
-        assert out["n_survivors"] == 0 and out["argmax_flat"] == 0
-        assert np.isfinite(out["RT"]).all() and np.isfinite(out["scales"]).all()
+        with pytest.raises(NoSurvivorsError):
+            est.estimate_fused(pc, nrm, seed=0, idxs=same, staged=staged)
+    with pytest.raises(NoSurvivorsError):
+        est.estimate(pc, nrm, seed=0, idxs=same)
     corner, dims = synth.vote_grid_geometry(pc, cfg.res)
     grid = torch.zeros(dims, device=DEV)
     empty_idx = torch.zeros((0, 2), dtype=torch.int32, device=DEV)

@@ -132,7 +132,7 @@ def test_dense_tc_encoder_matches_indexed_and_oracle_at_every_tile_shape(n):
             assert int(np.abs(d).max()) <= 1
     tail_d = t_dense.cpu().numpy()[:, sub].T
     np.testing.assert_allclose(tail_d, logits[:, 136:].numpy(), rtol=1e-4, atol=2e-5)
-    np.testing.assert_allclose(tail_d, t_idx.cpu().numpy().T, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(tail_d, t_idx.cpu().numpy().T, rtol=1e-5, atol=1e-5)     # a-side row via MMA vs FADD: 3xTF32 grade
 
 
 def test_backvote_bins_bit_equal_to_reference_kernel_dense_1024():
@@ -150,15 +150,21 @@ def test_backvote_bins_bit_equal_to_reference_kernel_dense_1024():
     grid = torch.zeros(dims, device=DEV)
     fast.vote_fast(_t(pc), None, grid, _t(corner), cfg["res"], bins=bins, lut=lut.to(DEV))
     flat = voting.grid_argmax(grid)
-    mask = fast.backvote_bins(_t(pc), bins, lut.to(DEV), None, dims, _t(corner), flat, cfg["res"], 3 * cfg["res"])
-    _, centre = ref_model.centre_from_grid(grid.cpu().numpy(), corner, cfg["res"])
-    ref_off = ref_gpu.backvote(_t(pc), _t(tr), torch.zeros(idxs.shape[0], 3, device=DEV), _t(idxs, torch.int32), _t(corner),
-                               cfg["res"], 72, dims, _t(centre.astype(np.float32)), 3 * cfg["res"])
-    ref_mask = (ref_off != 0).any(-1)
-    assert 0.01 < ref_mask.float().mean().item() < 0.9
-    n_diff = int((mask.bool() != ref_mask).sum().item())
-    print(f"[backvote_bins dense 1024 vs reference cubin] differing bits: {n_diff} of {idxs.shape[0]}")
-    assert n_diff == 0
+    gyz = dims[1] * dims[2]
+    # the winning cell (nearly every trained-like pair survives) and two cells away from it (a selective mask)
+    for shift in (0, 4 * gyz + 3 * dims[2] + 2, -(3 * gyz) - 5 * dims[2]):
+        f2 = (flat + shift).clamp(0, dims[0] * gyz - 1)
+        mask = fast.backvote_bins(_t(pc), bins, lut.to(DEV), None, dims, _t(corner), f2, cfg["res"], 3 * cfg["res"])
+        cell = np.array(np.unravel_index(int(f2.item()), dims))
+        centre = (np.asarray(corner, np.float64) + cell * cfg["res"]).astype(np.float32)          # nocs/inference.py:209,226
+        ref_off = ref_gpu.backvote(_t(pc), _t(tr), torch.zeros(idxs.shape[0], 3, device=DEV), _t(idxs, torch.int32), _t(corner),
+                                   cfg["res"], 72, dims, _t(centre), 3 * cfg["res"])
+        ref_mask = (ref_off != 0).any(-1)
+        n_diff = int((mask.bool() != ref_mask).sum().item())
+        print(f"[backvote_bins dense 1024 vs reference cubin, cell {cell.tolist()}] survivors {int(ref_mask.sum())} of "
+              f"{idxs.shape[0]}, differing bits: {n_diff}")
+        assert int(ref_mask.sum()) > 1000
+        assert n_diff == 0
 
 
 def _table(m, feat, impl):
@@ -186,9 +192,21 @@ def test_vote_fast_matches_oracle_and_is_deterministic(adaptive):
         grids.append(g)
     assert torch.equal(grids[0], grids[1])                                  # integer accumulation: run-to-run identical
     got = grids[0].cpu().numpy()
-    # weights are rounded to 2^-14 per corner: |err| <= 2^-15 * contributions
-    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=5e-3)
+    # weights are rounded to 2^-14 per corner: |err| <= 2^-15 * contributions.  Against the float64 C oracle a candidate
+    # whose grid coordinate sits within float32 rounding of an acceptance bound (models/voting.py:36-39) may be accepted
+    # by one side only: at most a few cells may differ, each by less than one vote
+    bad = ~np.isclose(got, ref, rtol=1e-4, atol=5e-3)
+    print(f"[vote_fast adaptive={adaptive} vs float64 C oracle] cells outside tolerance: {int(bad.sum())} of {bad.size}")
+    assert bad.sum() <= 8 and (np.abs(got - ref)[bad] < 1.0).all()
     assert int(voting.grid_argmax(grids[0]).item()) == int(np.argmax(ref))
+    from oracle import ref_gpu
+    if ref_gpu.available():
+        # ... and against the reference's own kernel on this GPU (same float32 arithmetic, contraction spelled out in
+        # csrc/common.cuh) every cell agrees: the two accept exactly the same candidates
+        rg = ref_gpu.ppf_voting(_t(pc), _t(tr), torch.ones(len(pc), device=DEV), _t(idxs, torch.int32), torch.zeros(dims, device=DEV),
+                                _t(corner), cfg["res"], 72, adaptive).cpu().numpy()
+        np.testing.assert_allclose(got, rg, rtol=1e-4, atol=5e-3)
+        assert int(np.argmax(got)) == int(np.argmax(rg))
     slow = torch.zeros(dims, device=DEV)
     voting.ppf_vote(_t(pc), _t(tr), _t(idxs, torch.int32), slow, _t(corner), cfg["res"], 72, adaptive)
     assert int(voting.grid_argmax(slow).item()) == int(np.argmax(ref))
