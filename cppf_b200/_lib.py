@@ -57,7 +57,7 @@ SIGNATURES = {
     "cppf_vote_routed": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _i64, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),
     "cppf_vote_slabs_supported": (_i, [_i, _i, _i]),
     "cppf_vote_slabs": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),
-    "cppf_backvote_bins": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _f, _f, _i, _i64, _i, _i, _i, _i, _p]),
+    "cppf_backvote_bins": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _f, _f, C.c_double, _i, _i64, _i, _i, _i, _i, _p]),
     "cppf_rot_hist": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i64, C.c_uint64, _f, _p]),
     "cppf_survivor_stats": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i64, _p]),
     "cppf_backproject_scratch_bytes": (_i64, [_i, _i]),
@@ -91,7 +91,7 @@ class PoseArgs(C.Structure):
         ("struct_bytes", _i64),
         ("pc", _p), ("nrm", _p), ("idx", _p), ("pe_blob", _p), ("tc_blob", _p), ("lut", _p), ("sphere", _p),
         ("uniforms", _p), ("inject_bins", _p), ("workspace", _p), ("record", _p), ("timing", _p),
-        ("n_pairs", _i64), ("workspace_bytes", _i64), ("rot_subsample", _i64), ("seed", C.c_uint64),
+        ("n_pairs", _i64), ("workspace_bytes", _i64), ("rot_subsample", _i64), ("seed", C.c_uint64), ("res_host", C.c_double),
         ("n_points", _i), ("idx_is_64", _i), ("knn", _i), ("n_rots", _i), ("adaptive", _i), ("regress_right", _i),
         ("n_sphere", _i), ("inject_cols", _i), ("max_cells", _i), ("routed_max_cells", _i), ("sample_pairs", _i),
         ("res", _f), ("tol", _f), ("cos_thr", _f),

@@ -133,6 +133,15 @@ __device__ __forceinline__ void issue_bias(uint32_t tmem_d, uint32_t ones, uint3
     mma_tf32(tmem_d, kdesc(ones, kAPlane), kdesc(v, N * 16), idesc, 0u);
 }
 
+// one lane of a converged warp (elect.sync): the thread that issues tcgen05.mma / commit for its group
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
@@ -188,6 +197,9 @@ __device__ __forceinline__ void tmem_ld32_second(uint32_t (&r)[32]) {
 #endif
 #ifndef CPPF_TC_LD_PIPE
 #define CPPF_TC_LD_PIPE 2    // TMEM -> register loads of the step epilogues split in two, the second in flight while the first is consumed
+#endif
+#ifndef CPPF_TC_PREFETCH
+#define CPPF_TC_PREFETCH 1   // dense mode: point data of the next tile is loaded one tile ahead (see the tile loop)
 #endif
 #ifndef CPPF_TC_TB_LDCG
 #define CPPF_TC_TB_LDCG 1    // table rows bypass L1 (ld.global.cg): with 224 KB of shared memory the L1 is too small to keep them
@@ -303,8 +315,13 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     __shared__ __align__(8) uint64_t s_bar[kGroups];
     __shared__ uint32_t s_tmem;
     float* sblob = reinterpret_cast<float*>(smem);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int g = tid >> 7, tg = tid & 127;             // group, row within the tile
+    const int tid = threadIdx.x;
+    // warp index through a lane-0 broadcast: the compiler then knows that everything derived from it (group, operand and
+    // TMEM addresses, descriptors) is warp-uniform and keeps it in uniform registers -- tcgen05.mma takes its operands from
+    // there, and with per-thread values every MMA was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~13
+    // instructions per MMA on the critical path of the group's leader warp)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int g = warp >> 2, tg = tid & 127;            // group, row within the tile
     unsigned char* s_ones = smem + kSmemFloats * 4;
     unsigned char* s_ta = s_ones + kOnesBytes + g * kTaBytes;                 // this group's a-side row operand (dense mode)
     unsigned char* a_hi = s_ones + kOnesBytes + kGroups * kTaBytes + g * kGroupBytes;
@@ -336,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     const uint32_t sA = smem_u32(a_hi), sAl = sA + kABytes;
     const uint32_t sW = smem_u32(sblob);
     const uint32_t sOnes = smem_u32(s_ones), sTa = smem_u32(s_ta);
-    const bool leader = tg == 0;
+    const bool lead_warp = (warp & 3) == 0;              // warp-uniform; one elected lane of it issues the MMAs
     uint32_t phase = 0;
 
 // publish this group's A operand, let the leader issue `ISSUE`, wait until the accumulators are complete
@@ -345,11 +362,13 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                        \
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                    \
         asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");                                          \
-        if (leader) {                                                                                       \
+        if (lead_warp) {                                                                                    \
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                 \
-            ISSUE;                                                                                          \
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) \
-                         : "memory");                                                                       \
+            if (elect_one()) {                                                                              \
+                ISSUE;                                                                                      \
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) \
+                             : "memory");                                                                   \
+            }                                                                                               \
         }                                                                                                   \
         __syncwarp();                                                                                       \
         mbar_wait(bar, phase);                                                                              \
@@ -361,10 +380,14 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     // is a row constant of the tile and enters through the ones-operand MMA instead of 96 FADDs per pair
     const int tiles_per_row = (prm.n_points + kTile - 1) / kTile;
     const long long n_tiles = DENSE ? (long long)prm.n_points * tiles_per_row : (prm.n_pairs + kTile - 1) / kTile;
-    for (long long tile = (long long)blockIdx.x * kGroups + g; tile < n_tiles; tile += (long long)gridDim.x * kGroups) {
-        long long p;
-        bool valid;
-        int a = 0, b = 0;
+    // The point data of a tile is fetched ONE TILE AHEAD (dense mode: both points' xyz + normal and this
+    // thread's chunk of the a-side table row), so that the L2 round trip at the head of a tile -- an SM configured
+    // with 224 KB of shared memory has next to no L1 -- overlaps the previous tile instead of the MMA chain's critical path.
+    const long long t_stride = (long long)gridDim.x * kGroups;
+    const long long ts = prm.n_points;
+    auto coords = [&](long long tile, long long& p, bool& valid, int& a, int& b) {
+        a = 0;
+        b = 0;
         if (DENSE) {
             a = (int)(tile / tiles_per_row);
             b = (int)(tile - (long long)a * tiles_per_row) * kTile + tg;
@@ -376,8 +399,35 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
             valid = p < prm.n_pairs;
             if (valid) pair_ab<IDX64>(prm.idx, p, prm.n_points, a, b);
         }
+    };
+    long long n_p = 0;
+    bool n_valid = false;
+    int n_a = 0, n_b = 0;
+    f3 n_pa = {0.f, 0.f, 0.f}, n_pb = n_pa, n_na = n_pa, n_nb = n_pa;
+    float4 n_ta = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](long long tile) {
+        coords(tile, n_p, n_valid, n_a, n_b);
+#if CPPF_TC_PREFETCH
+        if (DENSE) {
+            n_pa = ld3(prm.pc, n_a); n_pb = ld3(prm.pc, n_b); n_na = ld3(prm.nrm, n_a); n_nb = ld3(prm.nrm, n_b);
+            if (tg < 24) n_ta = __ldg(reinterpret_cast<const float4*>(prm.table) + n_a + tg * ts);
+        }
+#endif
+    };
+    long long tile = (long long)blockIdx.x * kGroups + g;
+    if (DENSE && tile < n_tiles) fetch(tile);
+    for (; tile < n_tiles; tile += t_stride) {
+        if (!DENSE) fetch(tile);                // indexed pairs: no look-ahead (the ta rows already fill the register file)
+        const long long p = n_p;
+        const bool valid = n_valid;
+        const int a = n_a, b = n_b;
         float ppf[4];
-        ppf_of(ld3(prm.pc, a), ld3(prm.pc, b), ld3(prm.nrm, a), ld3(prm.nrm, b), ppf);
+#if CPPF_TC_PREFETCH
+        if (DENSE) ppf_of(n_pa, n_pb, n_na, n_nb, ppf);
+        else
+#endif
+            ppf_of(ld3(prm.pc, a), ld3(prm.pc, b), ld3(prm.nrm, a), ld3(prm.nrm, b), ppf);
+        const float4 ta_row = n_ta;
         float4 u4;
         if (prm.uniforms != nullptr) {
             u4 = valid ? __ldg(reinterpret_cast<const float4*>(prm.uniforms) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -390,7 +440,6 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
         // (consecutive b in dense mode) read 512 contiguous bytes per load and the a side is a broadcast
         const float4* TA = reinterpret_cast<const float4*>(prm.table) + a;
         const float4* TB = reinterpret_cast<const float4*>(prm.table) + (long long)(kTabCols / 8) * prm.n_points + b;
-        const long long ts = prm.n_points;
         float4 ta[8], tb[8];
         float x[32];
 
@@ -399,7 +448,11 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
         st_chunk(a_hi, 1, tg, 0.f, 0.f, 0.f, 0.f);
         if (DENSE) {
             if (tg < 24) {                     // rows 4 tg .. 4 tg + 3 of the [96 x 8] operand: k = 0 <- hi, k = 4 <- lo
+#if CPPF_TC_PREFETCH
+                const float4 v = ta_row;
+#else
                 const float4 v = __ldg(TA + tg * ts);
+#endif
                 const float vs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -413,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
                 ta[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 tb[q] = ld_tab(TB + q * ts);
             }
+            if (tile + t_stride < n_tiles) fetch(tile + t_stride);          // next tile's point data: consumed one tile later
             CPPF_TC_STEP((issue_bias<96>(tm, sOnes, sTa), issue3<96, 8, true>(tm, sA, sAl, sW + kOffWp * 4)));
         } else {
 #pragma unroll

@@ -29,7 +29,7 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
 int backvote_bins_launch(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
                          uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
                          int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, const Geom* geom,
-                         cudaStream_t stream);
+                         cudaStream_t stream, double res_host);
 int vote_finalize_launch(const unsigned long long* acc, float* grid, int cells, const Geom* geom, int only_mode,
                          cudaStream_t stream);
 int64_t routed_pool_bytes(int64_t n_pairs, int n_rots);
@@ -346,7 +346,7 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     CPPF_TRY(mark());
     CPPF_TRY(backvote_bins_launch(a->pc, w.bins, a->lut, idx, idx_is_64, w.mask, nullptr,
                                   reinterpret_cast<const int64_t*>(w.flat), a->res, a->tol, n, n_pairs, a->n_rots, 0, 0, 0,
-                                  w.geom, stream));
+                                  w.geom, stream, a->res_host));
     CPPF_TRY(mark());
     // survivors stay addressed through the mask: per-block counts + scan instead of a materialised list (:230-231)
     CPPF_TRY(cppf_compact_count(w.mask, n_pairs, reinterpret_cast<int64_t*>(w.count), w.compact_scratch, stream));

@@ -42,17 +42,49 @@ __device__ __forceinline__ float div_by(float a, float b, float y) {
 }
 
 // trilinear splat of one in-bounds candidate at grid coordinates g -- models/voting.py:40-63 with
-// prob == 1 (nocs/inference.py:201).  Each corner weight is rounded ONCE to 2^-14: the last product is an
-// FFMA onto 2^23, whose low mantissa bits are then the rounded fixed-point weight (no F2I on the XU pipe).
+// prob == 1 (nocs/inference.py:201).  Each corner weight is rounded ONCE to 2^-14 units and leaves the multiplier
+// already AS AN INTEGER: the x-y factor carries 2^-60 and the z factor 2^-75 (exact power-of-two scalings of normal
+// floats), so the last product w_xy * w_z * 2^(14 - 149) lands in the denormal range, where an FMUL rounds the exact
+// product to a multiple of 2^-149 (round-half-even) and the bit pattern of the result IS that multiple.  No F2I, no
+// magic-number FFMA + subtraction: one FMUL per corner (fp32 denormals run at full rate in the FMA pipe; this
+// translation unit must not be built with -ftz=true).  Bit-identical to round-half-even(w_xy * w_z * 2^14).
+#ifndef CPPF_SPLAT_DENORM
+#define CPPF_SPLAT_DENORM 1
+#endif
+#ifndef CPPF_SPLAT_I2F
+#define CPPF_SPLAT_I2F 1
+#endif
 __device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float gxf, float gyf, float gzf, int gyz, int gz) {
     const int fx = (int)gxf, fy = (int)gyf, fz = (int)gzf;                     // :40
+#if CPPF_SPLAT_I2F
+    // in-bounds coordinates are >= 0.01, so truncation is the floor of :42 and the integer converts back exactly: one
+    // conversion on the XU pipe per axis (F2I) instead of two (F2I + FRND)
+    const float rx = gxf - (float)fx, ry = gyf - (float)fy, rz = gzf - (float)fz;
+#else
     const float rx = gxf - floorf(gxf), ry = gyf - floorf(gyf), rz = gzf - floorf(gzf);
+#endif
+    unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
+#if CPPF_SPLAT_DENORM
+    constexpr float kSx = 8.67361737988403547e-19f;                            // 2^-60
+    constexpr float kSz = 2.64697796016968855e-23f;                            // 2^-75
+    const float wx0 = fmaf(-rx, kSx, kSx), wx1 = rx * kSx;                      // (1 - rx) 2^-60, rx 2^-60: exact
+    const float wy0 = 1.f - ry;
+    const float z0 = fmaf(-rz, kSz, kSz), z1 = rz * kSz;                        // (1 - rz) 2^-75, rz 2^-75: exact
+    const float w00 = wx0 * wy0, w01 = wx0 * ry, w10 = wx1 * wy0, w11 = wx1 * ry;
+    atomicAdd(cell, __float_as_uint(w00 * z0));
+    atomicAdd(cell + 1, __float_as_uint(w00 * z1));
+    atomicAdd(cell + gz, __float_as_uint(w01 * z0));
+    atomicAdd(cell + gz + 1, __float_as_uint(w01 * z1));
+    atomicAdd(cell + gyz, __float_as_uint(w10 * z0));
+    atomicAdd(cell + gyz + 1, __float_as_uint(w10 * z1));
+    atomicAdd(cell + gyz + gz, __float_as_uint(w11 * z0));
+    atomicAdd(cell + gyz + gz + 1, __float_as_uint(w11 * z1));
+#else
     const float wx0 = 1.f - rx, wy0 = 1.f - ry;
     const float z1 = rz * kFixScale, z0 = (1.f - rz) * kFixScale;
     const float w00 = wx0 * wy0, w01 = wx0 * ry, w10 = rx * wy0, w11 = rx * ry;
     constexpr float kMagic = 8388608.f;                                        // 2^23
     constexpr unsigned kMagicBits = 0x4B000000u;
-    unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
     atomicAdd(cell, __float_as_uint(fmaf(w00, z0, kMagic)) - kMagicBits);
     atomicAdd(cell + 1, __float_as_uint(fmaf(w00, z1, kMagic)) - kMagicBits);
     atomicAdd(cell + gz, __float_as_uint(fmaf(w01, z0, kMagic)) - kMagicBits);
@@ -61,6 +93,7 @@ __device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float
     atomicAdd(cell + gyz + 1, __float_as_uint(fmaf(w10, z1, kMagic)) - kMagicBits);
     atomicAdd(cell + gyz + gz, __float_as_uint(fmaf(w11, z0, kMagic)) - kMagicBits);
     atomicAdd(cell + gyz + gz + 1, __float_as_uint(fmaf(w11, z1, kMagic)) - kMagicBits);
+#endif
 }
 
 __device__ __forceinline__ void st_shared_f4(unsigned addr, float x, float y, float z) {

@@ -375,6 +375,8 @@ struct BackvotePParams {
     long long n_pairs;
     int n_rots, gx, gy, gz;
     const Geom* geom;                // optional: device-side geometry overrides corner / dims / bounds
+    double res_host;                 // the resolution as the DOUBLE the host multiplies the winning cell with (nocs/inference.py:209:
+                                     // `corners[0] + cand * cfg.res`, a Python float); (double)(float)res differs from it in the 9th digit
 };
 
 #ifndef CPPF_BV_THREADS
@@ -422,9 +424,9 @@ __global__ void __launch_bounds__(CPPF_BV_THREADS, CPPF_BV_MIN_BLOCKS) backvote_
     const long long flat = *prm.argmax_flat;
     const int gyz = gy * gz;
     const int ix = (int)(flat / gyz), iy = (int)((flat % gyz) / gz), iz = (int)(flat % gz);
-    const float tx = (float)((double)cx + (double)ix * (double)prm.res);
-    const float ty = (float)((double)cy + (double)iy * (double)prm.res);
-    const float tz = (float)((double)cz + (double)iz * (double)prm.res);
+    const float tx = (float)((double)cx + (double)ix * prm.res_host);
+    const float ty = (float)((double)cy + (double)iy * prm.res_host);
+    const float tz = (float)((double)cz + (double)iz * prm.res_host);
     // is the tolerance ball around the winning cell at least one cell away from every face of the grid?
     const int gxi = prm.geom != nullptr ? prm.geom->gx : prm.gx;
     const int marg = (int)(prm.tol * prm.inv_res) + 2;
@@ -1000,7 +1002,7 @@ int vote_finalize_launch(const unsigned long long* acc, float* grid, int cells, 
 int backvote_bins_launch(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
                          uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
                          int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, const Geom* geom,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, double res_host) {
     if (n_pairs <= 0) return 0;
     if (n_rots > kMaxRotsP || n_rots <= 0) return (int)cudaErrorInvalidValue;
     if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
@@ -1009,7 +1011,7 @@ int backvote_bins_launch(const float* points, const uint8_t* bins, const float* 
     if (terr) return terr;
     BackvotePParams prm{rot_tab, points, bins, lut, idx, out_mask, corner, reinterpret_cast<const long long*>(argmax_flat), res,
                         (float)(1.0 / (double)res), tol, (float)(gx - 1), (float)(gy - 1), (float)(gz - 1), n_points,
-                        (long long)n_pairs, n_rots, gx, gy, gz, geom};
+                        (long long)n_pairs, n_rots, gx, gy, gz, geom, res_host > 0.0 ? res_host : (double)res};
     long long blocks = (n_pairs + CPPF_BV_THREADS - 1) / CPPF_BV_THREADS;
     const long long cap = (long long)sm_count() * CPPF_BV_BLOCKS_PER_SM;
     if (blocks > cap) blocks = cap;
@@ -1052,10 +1054,10 @@ extern "C" int cppf_vote_slabs(const float* points, const float* mu_nu, const ui
 
 extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, const float* lut, const void* idx,
                                   int idx_is_64, uint8_t* out_mask, const float* corner, const int64_t* argmax_flat,
-                                  float res, float tol, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz,
-                                  void* stream_) {
+                                  float res, float tol, double res_host, int n_points, int64_t n_pairs, int n_rots, int gx,
+                                  int gy, int gz, void* stream_) {
     return backvote_bins_launch(points, bins, lut, idx, idx_is_64, out_mask, corner, argmax_flat, res, tol, n_points, n_pairs,
-                                n_rots, gx, gy, gz, nullptr, (cudaStream_t)stream_);
+                                n_rots, gx, gy, gz, nullptr, (cudaStream_t)stream_, res_host);
 }
 
 namespace cppf {

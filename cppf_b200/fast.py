@@ -141,7 +141,7 @@ def backvote_bins(points, bins, lut, idxs, dims, corner, argmax_flat, res, tol, 
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().cppf_backvote_bins(
             points.data_ptr(), bins.data_ptr(), lut.data_ptr(), ip, is64, mask.data_ptr(), corner.data_ptr(),
-            argmax_flat.data_ptr(), float(res), float(tol), n, n_pairs, int(n_rots), int(dims[0]), int(dims[1]),
+            argmax_flat.data_ptr(), float(res), float(tol), float(res), n, n_pairs, int(n_rots), int(dims[0]), int(dims[1]),
             int(dims[2]), _sp(dev)), "cppf_backvote_bins")
     return mask
 

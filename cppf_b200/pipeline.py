@@ -394,7 +394,7 @@ class PoseEstimator:
         a.knn, a.n_rots, a.adaptive, a.regress_right = cfg.knn, cfg.num_rots, int(cfg.adaptive_voting), int(cfg.regress_right)
         a.n_sphere, a.inject_cols = self.sphere.shape[0], (inject_bins.shape[1] if inject_bins is not None else 0)
         a.max_cells, a.routed_max_cells, a.sample_pairs = int(max_cells), int(routed_max_cells), a_sample
-        a.res, a.tol, a.cos_thr = float(cfg.res), float(3 * cfg.res), self.cos_thr
+        a.res, a.tol, a.cos_thr, a.res_host = float(cfg.res), float(3 * cfg.res), self.cos_thr, float(cfg.res)
         with torch.cuda.device(dev):
             _lib.check(L.cppf_pose_fused(C.byref(a), torch.cuda.current_stream(dev).cuda_stream), "cppf_pose_fused")
         if record_host is None:         # a slot of a pinned ring (a fresh pinned allocation per object costs a cudaHostAlloc)
@@ -544,7 +544,7 @@ def _args_dtype():
     column-wise; checked against the compiled layout."""
     global _ARGS_DTYPE
     if _ARGS_DTYPE is None:
-        ct = {C.c_int64: "<i8", C.c_uint64: "<u8", C.c_void_p: "<u8", C.c_int: "<i4", C.c_float: "<f4"}
+        ct = {C.c_int64: "<i8", C.c_uint64: "<u8", C.c_void_p: "<u8", C.c_int: "<i4", C.c_float: "<f4", C.c_double: "<f8"}
         dt = np.dtype({"names": [f for f, _ in _lib.PoseArgs._fields_],
                        "formats": [ct[t] for _, t in _lib.PoseArgs._fields_],
                        "offsets": [getattr(_lib.PoseArgs, f).offset for f, _ in _lib.PoseArgs._fields_],
@@ -692,6 +692,7 @@ def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None):
         a["adaptive"][rows], a["regress_right"][rows] = int(cfg.adaptive_voting), int(cfg.regress_right)
         a["n_sphere"][rows] = est.sphere.shape[0]
         a["res"][rows], a["tol"][rows], a["cos_thr"][rows] = float(cfg.res), float(3 * cfg.res), est.cos_thr
+        a["res_host"][rows] = float(cfg.res)
     with torch.cuda.device(dev):
         _lib.check(L.cppf_pose_batch(a.ctypes.data, n_obj, n_streams, n_threads, torch.cuda.current_stream(dev).cuda_stream),
                    "cppf_pose_batch")

@@ -215,11 +215,13 @@ int cppf_vote_slabs(const float* points, const float* mu_nu, const uint8_t* bins
                     int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, void* stream);
 
 /* models/voting.py:74-112 + nocs/inference.py:207-211,229-230 from bins: the winning cell is
- * read from device memory (*argmax_flat), centre = corner + cell*res as at :209; out_mask[p] =
- * any(out_offsets[p] != 0). */
+ * read from device memory (*argmax_flat), centre = float32(corner + cell * res_host) as at :209,:226 -- the host
+ * multiplies in float64 with the Python float `cfg.res`, so res_host is that DOUBLE (0: use (double)res; the two differ in
+ * the 9th digit, which moves the float32 centre by one ulp for some cells and flips candidates on the tolerance sphere);
+ * `res` is the float32 the kernels divide by (cp.float32(cfg.res) at :225).  out_mask[p] = any(out_offsets[p] != 0). */
 int cppf_backvote_bins(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
                        uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
-                       int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, void* stream);
+                       double res_host, int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, void* stream);
 
 /* models/voting.py:119-147 + nocs/inference.py:276-284 fused: orientation candidates of a
  * sub-sample (without replacement, <= max_samples) of the survivors pos[0:*count] are counted
@@ -277,6 +279,8 @@ typedef struct cppf_pose_args {
     int64_t workspace_bytes;
     int64_t rot_subsample;       /* nocs/inference.py:279-281 (10000); 0 = every survivor */
     uint64_t seed;
+    double res_host;             /* cfg.res as the float64 the host multiplies the winning cell with (nocs/inference.py:209);
+                                    0 = (double)res */
     int n_points;
     int idx_is_64;
     int knn;                     /* config/config.yaml:21 (60) */

@@ -151,8 +151,8 @@ def test_backvote_bins_bit_equal_to_reference_kernel_dense_1024():
     fast.vote_fast(_t(pc), None, grid, _t(corner), cfg["res"], bins=bins, lut=lut.to(DEV))
     flat = voting.grid_argmax(grid)
     gyz = dims[1] * dims[2]
-    # the winning cell (nearly every trained-like pair survives) and two cells away from it (a selective mask)
-    for shift in (0, 4 * gyz + 3 * dims[2] + 2, -(3 * gyz) - 5 * dims[2]):
+    # the winning cell (nearly every trained-like pair survives) and four cells away from it (selective masks)
+    for shift in (0, 4 * gyz + 3 * dims[2] + 2, -(3 * gyz) - 5 * dims[2], 2 * gyz - 7 * dims[2] + 1, 5):
         f2 = (flat + shift).clamp(0, dims[0] * gyz - 1)
         mask = fast.backvote_bins(_t(pc), bins, lut.to(DEV), None, dims, _t(corner), f2, cfg["res"], 3 * cfg["res"])
         cell = np.array(np.unravel_index(int(f2.item()), dims))

@@ -40,3 +40,27 @@ def test_eight_corner_weights_sum_to_one_within_the_roundings():
             total += _fixed(wxy, z)
     assert np.abs(total - 16384).max() <= 4           # eight half-unit roundings + the float32 products
     assert abs(float(total.mean()) - 16384.0) < 0.01  # unbiased
+
+
+def test_denormal_product_carries_the_same_integer_in_its_bit_pattern():
+    """The shipped formulation (csrc/vote_common.cuh, CPPF_SPLAT_DENORM): the x-y factor scaled by 2^-60 and the z factor by
+    2^-75 (exact), so that their float32 product is a denormal whose BIT PATTERN is round-half-even(w * z * 2^14) -- the
+    same integer as the magic-number FFMA, without the subtraction."""
+    rng = np.random.default_rng(2)
+    n = 2_000_000
+    r = rng.random((n, 3), dtype=F)
+    w = ((F(1) - r[:, 0]) * r[:, 1]).astype(F)                    # a product of two of (r, 1 - r)
+    zf = np.where(rng.random(n) < 0.5, r[:, 2], (F(1) - r[:, 2]).astype(F)).astype(F)
+    ws = (w * F(2.0 ** -60)).astype(F)                            # exact: normal range
+    zs = (zf * F(2.0 ** -75)).astype(F)
+    assert np.array_equal(ws.astype(np.float64), w.astype(np.float64) * 2.0 ** -60)
+    assert np.array_equal(zs.astype(np.float64), zf.astype(np.float64) * 2.0 ** -75)
+    prod = (ws * zs).astype(F)                                    # float32 multiply: one rounding, into the denormals
+    got = prod.view(np.uint32).astype(np.int64)
+    want = _fixed(w, (zf * F(16384.0)).astype(F))
+    assert np.array_equal(got, want)
+    # edge values: weight 0, weight 1, exact ties
+    e_w = np.array([0.0, 1.0, 1.0, 0.5, 0.25, 3 * 2.0 ** -15, 2.0 ** -15], F)
+    e_z = np.array([1.0, 1.0, 0.0, 2.0 ** -14, 2.0 ** -13, 1.0, 1.0], F)
+    e = ((e_w * F(2.0 ** -60)).astype(F) * (e_z * F(2.0 ** -75)).astype(F)).astype(F).view(np.uint32).astype(np.int64)
+    assert e.tolist() == [0, 16384, 0, 0, 0, 2, 0]               # half-even: 0.5 -> 0, 0.5 -> 0, 1.5 -> 2, 0.5 -> 0
