@@ -54,7 +54,11 @@ __device__ __forceinline__ float div_by(float a, float b, float y) {
 #ifndef CPPF_SPLAT_I2F
 #define CPPF_SPLAT_I2F 1
 #endif
-__device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float gxf, float gyf, float gzf, int gyz, int gz) {
+__device__ __forceinline__ void red_shared_u32(unsigned saddr, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+// grid_saddr: 32-bit shared-window address of the grid (cvta once per kernel, not per splat)
+__device__ __forceinline__ void splat_fixed(unsigned grid_saddr, float gxf, float gyf, float gzf, int gyz, int gz) {
     const int fx = (int)gxf, fy = (int)gyf, fz = (int)gzf;                     // :40
 #if CPPF_SPLAT_I2F
     // in-bounds coordinates are >= 0.01, so truncation is the floor of :42 and the integer converts back exactly: one
@@ -63,7 +67,8 @@ __device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float
 #else
     const float rx = gxf - floorf(gxf), ry = gyf - floorf(gyf), rz = gzf - floorf(gzf);
 #endif
-    unsigned* cell = s_grid + fx * gyz + fy * gz + fz;
+    const unsigned cell = grid_saddr + 4u * (unsigned)(fx * gyz + fy * gz + fz);
+    const unsigned sy = 4u * (unsigned)gz, sx = 4u * (unsigned)gyz;
 #if CPPF_SPLAT_DENORM
     constexpr float kSx = 8.67361737988403547e-19f;                            // 2^-60
     constexpr float kSz = 2.64697796016968855e-23f;                            // 2^-75
@@ -71,28 +76,28 @@ __device__ __forceinline__ void splat_fixed(unsigned* __restrict__ s_grid, float
     const float wy0 = 1.f - ry;
     const float z0 = fmaf(-rz, kSz, kSz), z1 = rz * kSz;                        // (1 - rz) 2^-75, rz 2^-75: exact
     const float w00 = wx0 * wy0, w01 = wx0 * ry, w10 = wx1 * wy0, w11 = wx1 * ry;
-    atomicAdd(cell, __float_as_uint(w00 * z0));
-    atomicAdd(cell + 1, __float_as_uint(w00 * z1));
-    atomicAdd(cell + gz, __float_as_uint(w01 * z0));
-    atomicAdd(cell + gz + 1, __float_as_uint(w01 * z1));
-    atomicAdd(cell + gyz, __float_as_uint(w10 * z0));
-    atomicAdd(cell + gyz + 1, __float_as_uint(w10 * z1));
-    atomicAdd(cell + gyz + gz, __float_as_uint(w11 * z0));
-    atomicAdd(cell + gyz + gz + 1, __float_as_uint(w11 * z1));
+    red_shared_u32(cell, __float_as_uint(w00 * z0));
+    red_shared_u32(cell + 4u, __float_as_uint(w00 * z1));
+    red_shared_u32(cell + sy, __float_as_uint(w01 * z0));
+    red_shared_u32(cell + sy + 4u, __float_as_uint(w01 * z1));
+    red_shared_u32(cell + sx, __float_as_uint(w10 * z0));
+    red_shared_u32(cell + sx + 4u, __float_as_uint(w10 * z1));
+    red_shared_u32(cell + sx + sy, __float_as_uint(w11 * z0));
+    red_shared_u32(cell + sx + sy + 4u, __float_as_uint(w11 * z1));
 #else
     const float wx0 = 1.f - rx, wy0 = 1.f - ry;
     const float z1 = rz * kFixScale, z0 = (1.f - rz) * kFixScale;
     const float w00 = wx0 * wy0, w01 = wx0 * ry, w10 = rx * wy0, w11 = rx * ry;
     constexpr float kMagic = 8388608.f;                                        // 2^23
     constexpr unsigned kMagicBits = 0x4B000000u;
-    atomicAdd(cell, __float_as_uint(fmaf(w00, z0, kMagic)) - kMagicBits);
-    atomicAdd(cell + 1, __float_as_uint(fmaf(w00, z1, kMagic)) - kMagicBits);
-    atomicAdd(cell + gz, __float_as_uint(fmaf(w01, z0, kMagic)) - kMagicBits);
-    atomicAdd(cell + gz + 1, __float_as_uint(fmaf(w01, z1, kMagic)) - kMagicBits);
-    atomicAdd(cell + gyz, __float_as_uint(fmaf(w10, z0, kMagic)) - kMagicBits);
-    atomicAdd(cell + gyz + 1, __float_as_uint(fmaf(w10, z1, kMagic)) - kMagicBits);
-    atomicAdd(cell + gyz + gz, __float_as_uint(fmaf(w11, z0, kMagic)) - kMagicBits);
-    atomicAdd(cell + gyz + gz + 1, __float_as_uint(fmaf(w11, z1, kMagic)) - kMagicBits);
+    red_shared_u32(cell, __float_as_uint(fmaf(w00, z0, kMagic)) - kMagicBits);
+    red_shared_u32(cell + 4u, __float_as_uint(fmaf(w00, z1, kMagic)) - kMagicBits);
+    red_shared_u32(cell + sy, __float_as_uint(fmaf(w01, z0, kMagic)) - kMagicBits);
+    red_shared_u32(cell + sy + 4u, __float_as_uint(fmaf(w01, z1, kMagic)) - kMagicBits);
+    red_shared_u32(cell + sx, __float_as_uint(fmaf(w10, z0, kMagic)) - kMagicBits);
+    red_shared_u32(cell + sx + 4u, __float_as_uint(fmaf(w10, z1, kMagic)) - kMagicBits);
+    red_shared_u32(cell + sx + sy, __float_as_uint(fmaf(w11, z0, kMagic)) - kMagicBits);
+    red_shared_u32(cell + sx + sy + 4u, __float_as_uint(fmaf(w11, z1, kMagic)) - kMagicBits);
 #endif
 }
 

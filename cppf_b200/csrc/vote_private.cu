@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     const int gyz = gy * gzd, gz = gzd;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned* s_lane = s_grid + (lane & 1) * rep;
+    const unsigned s_lane = (unsigned)__cvta_generic_to_shared(s_grid + (lane & 1) * rep);   // this lane's replica
     const unsigned q_addr = (unsigned)__cvta_generic_to_shared(s_queue + (threadIdx.x >> 5) * kVoteQueue);
     const float cx = __ldg(corner), cy = __ldg(corner + 1), cz = __ldg(corner + 2);
     // A batch is 2048 consecutive entries of the pair list, or -- dense mode -- a 128 x 16 tile of the pair matrix
@@ -197,18 +197,21 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
                 rank[j] = atomicAdd(&s_hist[n], 1);
             }
         }
-        // ---- overflow guard on the votes of the previous batches (nobody is voting now)
-        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-            const unsigned v = s_grid[i];
-            if (v >= kFlushAt) {
-                atomicAdd(prm.acc + acc_off + i, (unsigned long long)v);
-                s_grid[i] = 0u;
-            }
-            if (rep) {
-                const unsigned w = s_grid[rep + i];
-                if (w >= kFlushAt) {
-                    atomicAdd(prm.acc + acc_off + i, (unsigned long long)w);
-                    s_grid[rep + i] = 0u;
+        // ---- overflow guard on the votes of the previous batches (nobody is voting now): four cells per load, the
+        // per-cell flush only where one of them has reached the threshold
+        for (int r = 0; r < (rep ? 2 : 1); ++r) {
+            unsigned* gr = s_grid + r * rep;
+            for (int i = 4 * threadIdx.x; i < cells; i += 4 * blockDim.x) {
+                if (i + 4 <= cells) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(gr + i);
+                    if (max(max(v.x, v.y), max(v.z, v.w)) < kFlushAt) continue;
+                }
+                for (int j = i; j < min(i + 4, cells); ++j) {
+                    const unsigned v = gr[j];
+                    if (v >= kFlushAt) {
+                        atomicAdd(prm.acc + acc_off + j, (unsigned long long)v);
+                        gr[j] = 0u;
+                    }
                 }
             }
         }

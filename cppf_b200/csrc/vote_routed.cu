@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
     const int x0 = slab * pps;
     const int x1 = min(gx, x0 + pps + 1);                          // + the overlap plane of the x+1 corners
     const int cells = (x1 - x0) * gyz;
+    const unsigned s_grid_addr = (unsigned)__cvta_generic_to_shared(s_grid);
     for (int i = threadIdx.x; i < cells; i += blockDim.x) s_grid[i] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        if (g[q].x == g[q].x) splat_fixed(s_grid, g[q].x - fx0, g[q].y, g[q].z, gyz, gz);   // NaN = padding
+                        if (g[q].x == g[q].x) splat_fixed(s_grid_addr, g[q].x - fx0, g[q].y, g[q].z, gyz, gz);   // NaN = padding
 #pragma unroll
                     for (int q = 0; q < 4; ++q) g[q] = nx[q];
                 }
