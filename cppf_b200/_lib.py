@@ -79,6 +79,11 @@ SIGNATURES = {
     "cppf_timing_stages": (_i, []),
     "cppf_timing_stage_name": (C.c_char_p, [_i]),
     "cppf_timing_collect": (_i, [_p, _p]),
+    "cppf_encode_sample_tc_rows": (_i, [_p, _p, _p, _p, _p, _i, _i, _i64, _i, _p, C.c_uint64, _i, _p, _p, _p, _p]),
+    "cppf_vote_fast_rows": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p]),
+    "cppf_backvote_bins_rows": (_i, [_p, _p, _p, _i, _p, _p, _p, _f, _f, C.c_double, _i, _i64, _i, _i, _i, _i, _p]),
+    "cppf_rot_hist_rows": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i64, C.c_uint64, _f, _p]),
+    "cppf_survivor_stats_rows": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i64, _p]),
     "cppf_vote_count": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _i, _i64, _i, _i, _i, _i, _i, _p, _p]),
     "cppf_peak_shared_atomics": (_i, [_i, _i, _i, _i, _i, _p, _p]),
     "cppf_peak_global_red": (_i, [_i, _i, _i, _i, _p, _p]),

@@ -78,17 +78,19 @@ struct Geom {
     int planes_per_slab, n_slabs;   // mode 1
 };
 
-// (a, b) of pair p: from an int32/int64 index list, or row-major dense enumeration.
+// (a, b) of pair p: from an int32/int64 index list, or row-major dense enumeration.  row0: dense enumeration of a ROW
+// BLOCK of the pair matrix (one object split over several GPUs): pair p is (row0 + p / N, p % N).
 template <bool IDX64>
-__device__ __forceinline__ void pair_ab(const void* __restrict__ idx, int64_t p, int n_points, int& a, int& b) {
+__device__ __forceinline__ void pair_ab(const void* __restrict__ idx, int64_t p, int n_points, int& a, int& b, int row0 = 0) {
     if (idx == nullptr) {
         if (((uint64_t)p >> 32) == 0) {                 // N < 65 536: a 32-bit divide is a third of the 64-bit one
             const uint32_t q = (uint32_t)p / (uint32_t)n_points;
-            a = (int)q;
+            a = (int)q + row0;
             b = (int)((uint32_t)p - q * (uint32_t)n_points);
         } else {
-            a = (int)(p / n_points);
-            b = (int)(p - (int64_t)a * n_points);
+            const int64_t q = p / n_points;
+            a = (int)q + row0;
+            b = (int)(p - q * n_points);
         }
     } else if (IDX64) {
         const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(idx) + p);

@@ -90,6 +90,7 @@ struct Params {
     int n_points;
     long long n_pairs;
     int heads;
+    int row0;                   // dense mode: first row of the block of the pair matrix this launch covers (n_pairs / n_points rows)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
     // dense mode: a tile is 128 consecutive points b of ONE point a (ragged at the end of a row), so that the a-side table row
     // is a row constant of the tile and enters through the ones-operand MMA instead of 96 FADDs per pair
     const int tiles_per_row = (prm.n_points + kTile - 1) / kTile;
-    const long long n_tiles = DENSE ? (long long)prm.n_points * tiles_per_row : (prm.n_pairs + kTile - 1) / kTile;
+    const long long n_tiles = DENSE ? (prm.n_pairs / prm.n_points) * tiles_per_row : (prm.n_pairs + kTile - 1) / kTile;
     // The point data of a tile is fetched ONE TILE AHEAD (dense mode: both points' xyz + normal and this
     // thread's chunk of the a-side table row), so that the L2 round trip at the head of a tile -- an SM configured
     // with 224 KB of shared memory has next to no L1 -- overlaps the previous tile instead of the MMA chain's critical path.
@@ -389,10 +390,11 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
         a = 0;
         b = 0;
         if (DENSE) {
-            a = (int)(tile / tiles_per_row);
-            b = (int)(tile - (long long)a * tiles_per_row) * kTile + tg;
+            const int r = (int)(tile / tiles_per_row);                            // row within the block
+            a = r + prm.row0;
+            b = (int)(tile - (long long)r * tiles_per_row) * kTile + tg;
             valid = b < prm.n_points;
-            p = (long long)a * prm.n_points + b;
+            p = (long long)r * prm.n_points + b;                                  // position in this launch's outputs
             if (!valid) b = 0;
         } else {
             p = tile * kTile + tg;
@@ -432,7 +434,9 @@ __global__ void __launch_bounds__(kThreads, 1) encode_sample_tc_kernel(const Par
         if (prm.uniforms != nullptr) {
             u4 = valid ? __ldg(reinterpret_cast<const float4*>(prm.uniforms) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
-            const uint4 w = philox4x32_10(make_uint4((uint32_t)p, (uint32_t)((unsigned long long)p >> 32), 0u, 0u),
+            // the counter is the pair's index in the WHOLE pair matrix, so a row block draws what the full launch draws
+            const long long pg = DENSE ? p + (long long)prm.row0 * prm.n_points : p;
+            const uint4 w = philox4x32_10(make_uint4((uint32_t)pg, (uint32_t)((unsigned long long)pg >> 32), 0u, 0u),
                                           make_uint2((uint32_t)prm.seed, (uint32_t)(prm.seed >> 32)));
             u4 = make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
         }
@@ -650,15 +654,25 @@ extern "C" int cppf_tc_preproject(const float* feat, const float* tc_blob, float
     return 0;
 }
 
-extern "C" int cppf_encode_sample_tc(const float* pc, const float* nrm, const float* table, const float* tc_blob,
-                                     const void* idx, int idx_is_64, int n_points, int64_t n_pairs, const float* uniforms,
-                                     uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_t, void* stream) {
+namespace cppf {
+// dense pairs (idx == NULL) cover rows [row0, row0 + n_pairs / n_points) of the pair matrix: all of it, or one block
+bool dense_rows_ok(const void* idx, int n_points, int64_t n_pairs, int row0) {
+    if (idx != nullptr) return row0 == 0;
+    if (n_points <= 0 || row0 < 0 || n_pairs % n_points != 0) return false;
+    return row0 + n_pairs / n_points <= n_points;
+}
+}  // namespace cppf
+
+extern "C" int cppf_encode_sample_tc_rows(const float* pc, const float* nrm, const float* table, const float* tc_blob,
+                                          const void* idx, int idx_is_64, int n_points, int64_t n_pairs, int row0,
+                                          const float* uniforms, uint64_t seed, int heads, uint8_t* bins, float* tail,
+                                          float* dbg_t, void* stream) {
     if (n_pairs <= 0) return 0;
-    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
+    if (!dense_rows_ok(idx, n_points, n_pairs, row0)) return (int)cudaErrorInvalidValue;
     if ((heads & 8) && tail == nullptr) return (int)cudaErrorInvalidValue;
-    tc::Params prm{pc, nrm, table, tc_blob, idx, uniforms, seed, bins, tail, dbg_t, n_points, (long long)n_pairs, heads};
+    tc::Params prm{pc, nrm, table, tc_blob, idx, uniforms, seed, bins, tail, dbg_t, n_points, (long long)n_pairs, heads, row0};
     const bool dense = idx == nullptr;
-    const long long n_tiles = dense ? (long long)n_points * ((n_points + tc::kTile - 1) / tc::kTile)
+    const long long n_tiles = dense ? (n_pairs / n_points) * ((n_points + tc::kTile - 1) / tc::kTile)
                                     : (n_pairs + tc::kTile - 1) / tc::kTile;
     long long ctas = (n_tiles + tc::kGroups - 1) / tc::kGroups;
     if (ctas > sm_count()) ctas = sm_count();
@@ -669,4 +683,12 @@ extern "C" int cppf_encode_sample_tc(const float* pc, const float* nrm, const fl
     kern<<<(int)ctas, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int cppf_encode_sample_tc(const float* pc, const float* nrm, const float* table, const float* tc_blob,
+                                     const void* idx, int idx_is_64, int n_points, int64_t n_pairs, const float* uniforms,
+                                     uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_t, void* stream) {
+    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
+    return cppf_encode_sample_tc_rows(pc, nrm, table, tc_blob, idx, idx_is_64, n_points, n_pairs, 0, uniforms, seed, heads, bins,
+                                      tail, dbg_t, stream);
 }

@@ -25,11 +25,11 @@ namespace cppf {
 int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, const void* idx,
                      int idx_is_64, float* grid, void* scratch, const float* corner, float res, int n_points,
                      int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, const Geom* geom, int max_cells,
-                     cudaStream_t stream, int slab_cells = 0, long long total_cells = 0);
+                     cudaStream_t stream, int slab_cells = 0, long long total_cells = 0, int row0 = 0);
 int backvote_bins_launch(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
                          uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
                          int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, const Geom* geom,
-                         cudaStream_t stream, double res_host);
+                         cudaStream_t stream, double res_host, int row0 = 0);
 int vote_finalize_launch(const unsigned long long* acc, float* grid, int cells, const Geom* geom, int only_mode,
                          cudaStream_t stream);
 int64_t routed_pool_bytes(int64_t n_pairs, int n_rots);

@@ -18,6 +18,8 @@
 
 namespace cppf {
 
+bool dense_rows_ok(const void* idx, int n_points, int64_t n_pairs, int row0);    // encode_tc.cu
+
 constexpr int kSelectBlockBytes = 2048;  // = kCompactBlock * kCompactItems of vote.cu (cppf_compact_count)
 constexpr int kSelectBlock = kSelectBlockBytes;
 
@@ -39,6 +41,7 @@ struct VotePParams {
     const Geom* geom;          // optional: device-side geometry overrides corner / dims / upper bounds
     int max_cells;             // capacity of the shared-memory grid of this launch
     int rep_stride;            // 0, or the offset (in cells) of a second replica of the grid used by the odd lanes
+    int row0;                  // dense mode: first row of the block of the pair matrix (n_pairs / n_points rows) this launch covers
     int slab_planes;           // 0: every CTA holds the whole grid.  > 0 ("slab passes", grids of up to gridDim slabs): CTA b
                                // holds the x-slab (b % n_slabs) of slab_planes base planes (+ 1 overlap plane), walks the
                                // pairs of part (b / n_slabs) and keeps only the candidates whose floor(g.x) it owns --
@@ -165,16 +168,17 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
     // batch takes another 9 % off the same-cell replays of the splat (tools/sim_vote_banks.py: 4.0 -> 3.65 per ATOMS).
     const bool tiled = prm.idx == nullptr;
     const int tiles_x = (prm.n_points + kTileB - 1) / kTileB;
-    const long long n_batches = tiled ? (long long)((prm.n_points + kTileA - 1) / kTileA) * tiles_x
+    const int n_rows = tiled ? (int)(prm.n_pairs / prm.n_points) : 0;      // rows [row0, row0 + n_rows) of the pair matrix
+    const long long n_batches = tiled ? (long long)((n_rows + kTileA - 1) / kTileA) * tiles_x
                                       : (prm.n_pairs + kVoteBatch - 1) / kVoteBatch;
-    auto pair_index = [&](long long batch, int local) -> long long {      // -1: no such pair
+    auto pair_index = [&](long long batch, int local) -> long long {      // position in this launch's pair arrays; -1: none
         if (!tiled) {
             const long long q = batch * kVoteBatch + local;
             return q < prm.n_pairs ? q : -1;
         }
         const int tr = (int)(batch / tiles_x), tc = (int)(batch - (long long)tr * tiles_x);
-        const int a = tr * kTileA + (local / kTileB), b = tc * kTileB + (local % kTileB);
-        return (a < prm.n_points && b < prm.n_points) ? (long long)a * prm.n_points + b : -1;
+        const int r = tr * kTileA + (local / kTileB), b = tc * kTileB + (local % kTileB);
+        return (r < n_rows && b < prm.n_points) ? (long long)r * prm.n_points + b : -1;
     };
 
     for (long long batch = part; batch < n_batches; batch += parts) {
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(kVoteThreads, 1) vote_private_kernel(const Vot
             if (item < total) {
                 const long long p = pair_index(batch, s_perm[item]);
                 int ia, ib;
-                pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
+                pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib, prm.row0);
                 float mu, nu;
                 if (BINS) {
                     const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
@@ -378,6 +382,7 @@ struct BackvotePParams {
     long long n_pairs;
     int n_rots, gx, gy, gz;
     const Geom* geom;                // optional: device-side geometry overrides corner / dims / bounds
+    int row0;                        // dense mode: first row of the block of the pair matrix this launch covers
     double res_host;                 // the resolution as the DOUBLE the host multiplies the winning cell with (nocs/inference.py:209:
                                      // `corners[0] + cand * cfg.res`, a Python float); (double)(float)res differs from it in the 9th digit
 };
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(CPPF_BV_THREADS, CPPF_BV_MIN_BLOCKS) backvote_
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < prm.n_pairs;
          p += (long long)gridDim.x * blockDim.x) {
         int ia, ib;
-        pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
+        pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib, prm.row0);
         const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
         const float mu = s_lut[bn.x], nu = s_lut[32 + bn.y];
         const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
@@ -647,6 +652,7 @@ struct RotHistParams {
     unsigned long long offset_seed;
     float thr;
     float ywin;                  // half-width of the y window (>= 2: scan every bin)
+    int row0;                    // dense mode: first row of the block of the pair matrix the pair positions refer to
 };
 
 constexpr int kRotHistPairs = 64;
@@ -707,7 +713,7 @@ __global__ void __launch_bounds__(kRotHistThreads) rot_hist_kernel(const RotHist
             const long long p = prm.pos ? prm.pos[prm.pos_is_sample ? j : r]
                                         : select_survivor(prm.mask, prm.block_offsets, prm.n_blocks, prm.n_pairs, r);
             int ia, ib;
-            pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib);
+            pair_ab<IDX64>(prm.idx, p, prm.n_points, ia, ib, prm.row0);
             const uchar4 bn = __ldg(reinterpret_cast<const uchar4*>(prm.bins) + p);
             const float rot = __ldg(prm.lut + (prm.which == 0 ? 64 + bn.z : 100 + bn.w));
             const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
@@ -788,6 +794,7 @@ struct StatsParams {
     int n_points;
     long long n_pairs;
     int vec4;                    // dense pairs through the mask with 16-byte aligned buffers and n_points % 4 == 0
+    int row0;                    // dense mode: first row of the block of the pair matrix the pair positions refer to
 };
 
 template <bool IDX64>
@@ -827,7 +834,7 @@ __global__ void __launch_bounds__(256, CPPF_STATS_MIN_BLOCKS) survivor_stats_ker
             if (m4 == 0u) continue;
             const long long p0 = q << 2;
             int ia, ib;
-            pair_ab<IDX64>(nullptr, p0, prm.n_points, ia, ib);
+            pair_ab<IDX64>(nullptr, p0, prm.n_points, ia, ib, prm.row0);
             const f3 a = ld3(prm.points, ia), n = ld3(prm.nrm, ia);
             const float4* pb = reinterpret_cast<const float4*>(prm.points + 3 * (long long)ib);       // ib % 4 == 0: 16-byte aligned
             const float4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
@@ -853,7 +860,7 @@ __global__ void __launch_bounds__(256, CPPF_STATS_MIN_BLOCKS) survivor_stats_ker
         for (int u = 0; u < 4; ++u) {
             if (p[u] < 0) continue;
             int ia, ib;
-            pair_ab<IDX64>(prm.idx, p[u], prm.n_points, ia, ib);
+            pair_ab<IDX64>(prm.idx, p[u], prm.n_points, ia, ib, prm.row0);
             const f3 a = ld3(prm.points, ia), b = ld3(prm.points, ib);
             const f3 ab = a - b;
             const float inv = sqrtf(dot3(ab, ab)) + 1e-7f;                     // :288-289 (float32 numpy)
@@ -911,7 +918,7 @@ namespace cppf {
 int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, const void* idx,
                      int idx_is_64, float* grid, void* scratch, const float* corner, float res, int n_points,
                      int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive, const Geom* geom, int max_cells,
-                     cudaStream_t stream, int slab_cells, long long total_cells) {
+                     cudaStream_t stream, int slab_cells, long long total_cells, int row0) {
     if (n_pairs <= 0) return 0;                     // empty pair list: nothing to vote (pointers may be null)
     const bool slabs = slab_cells > 0;
     long long cells = geom ? (long long)(slabs ? slab_cells : max_cells) : (long long)gx * gy * gz;
@@ -934,7 +941,7 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
         return (int)cudaErrorInvalidValue;
     if ((mu_nu == nullptr) == (bins == nullptr)) return (int)cudaErrorInvalidValue;
     if (bins != nullptr && lut == nullptr) return (int)cudaErrorInvalidValue;
-    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
+    if (!dense_rows_ok(idx, n_points, n_pairs, row0)) return (int)cudaErrorInvalidValue;
     if (n_pairs <= 0) return 0;
     int terr = 0;
     const float2* rot_tab = rot_table_device(stream, &terr);
@@ -968,7 +975,7 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
     }
     VotePParams prm{rot_tab, points, mu_nu, bins, lut, idx, reinterpret_cast<unsigned long long*>(scratch), corner, res,
                     (float)(1.0 / (double)res), lo, hx, hy, hz, vote_bound_below(lo, res), dhx, dhy, dhz, n_points,
-                    (long long)n_pairs, n_rots, gx, gy, gz, adaptive, geom, (int)cells, 0, pps, n_slabs};
+                    (long long)n_pairs, n_rots, gx, gy, gz, adaptive, geom, (int)cells, 0, row0, pps, n_slabs};
     // second replica 8 banks away from the first, when both fit
     long long rep_stride = ((cells + 31) & ~31ll) + 8;
     if ((size_t)(rep_stride + cells) * 4 + vote_private_fixed_smem() + 1024 > (size_t)225 * 1024) rep_stride = 0;
@@ -1005,16 +1012,16 @@ int vote_finalize_launch(const unsigned long long* acc, float* grid, int cells, 
 int backvote_bins_launch(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
                          uint8_t* out_mask, const float* corner, const int64_t* argmax_flat, float res, float tol,
                          int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, const Geom* geom,
-                         cudaStream_t stream, double res_host) {
+                         cudaStream_t stream, double res_host, int row0) {
     if (n_pairs <= 0) return 0;
     if (n_rots > kMaxRotsP || n_rots <= 0) return (int)cudaErrorInvalidValue;
-    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
+    if (!dense_rows_ok(idx, n_points, n_pairs, row0)) return (int)cudaErrorInvalidValue;
     int terr = 0;
     const float2* rot_tab = rot_table_device(stream, &terr);
     if (terr) return terr;
     BackvotePParams prm{rot_tab, points, bins, lut, idx, out_mask, corner, reinterpret_cast<const long long*>(argmax_flat), res,
                         (float)(1.0 / (double)res), tol, (float)(gx - 1), (float)(gy - 1), (float)(gz - 1), n_points,
-                        (long long)n_pairs, n_rots, gx, gy, gz, geom, res_host > 0.0 ? res_host : (double)res};
+                        (long long)n_pairs, n_rots, gx, gy, gz, geom, row0, res_host > 0.0 ? res_host : (double)res};
     long long blocks = (n_pairs + CPPF_BV_THREADS - 1) / CPPF_BV_THREADS;
     const long long cap = (long long)sm_count() * CPPF_BV_BLOCKS_PER_SM;
     if (blocks > cap) blocks = cap;
@@ -1029,8 +1036,16 @@ extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uin
                               const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
                               int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
                               void* stream_) {
+    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     return vote_fast_launch(points, mu_nu, bins, lut, idx, idx_is_64, grid, scratch, corner, res, n_points, n_pairs, n_rots,
-                            gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, 0, 0);
+                            gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, 0, 0, 0);
+}
+
+extern "C" int cppf_vote_fast_rows(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, int row0,
+                                   float* grid, void* scratch, const float* corner, float res, int n_points, int64_t n_pairs,
+                                   int n_rots, int gx, int gy, int gz, int adaptive, void* stream_) {
+    return vote_fast_launch(points, mu_nu, bins, lut, nullptr, 0, grid, scratch, corner, res, n_points, n_pairs, n_rots, gx, gy,
+                            gz, adaptive, nullptr, 0, (cudaStream_t)stream_, 0, 0, row0);
 }
 
 extern "C" int cppf_vote_finalize(const void* acc, float* grid, int64_t cells, void* stream_) {
@@ -1051,23 +1066,32 @@ extern "C" int cppf_vote_slabs(const float* points, const float* mu_nu, const ui
                                const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
                                int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
                                void* stream_) {
+    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     return vote_fast_launch(points, mu_nu, bins, lut, idx, idx_is_64, grid, scratch, corner, res, n_points, n_pairs, n_rots,
-                            gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, cppf_vote_private_max_cells(), 0);
+                            gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, cppf_vote_private_max_cells(), 0, 0);
 }
 
 extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, const float* lut, const void* idx,
                                   int idx_is_64, uint8_t* out_mask, const float* corner, const int64_t* argmax_flat,
                                   float res, float tol, double res_host, int n_points, int64_t n_pairs, int n_rots, int gx,
                                   int gy, int gz, void* stream_) {
+    if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     return backvote_bins_launch(points, bins, lut, idx, idx_is_64, out_mask, corner, argmax_flat, res, tol, n_points, n_pairs,
-                                n_rots, gx, gy, gz, nullptr, (cudaStream_t)stream_, res_host);
+                                n_rots, gx, gy, gz, nullptr, (cudaStream_t)stream_, res_host, 0);
+}
+
+extern "C" int cppf_backvote_bins_rows(const float* points, const uint8_t* bins, const float* lut, int row0, uint8_t* out_mask,
+                                       const float* corner, const int64_t* argmax_flat, float res, float tol, double res_host,
+                                       int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, void* stream_) {
+    return backvote_bins_launch(points, bins, lut, nullptr, 0, out_mask, corner, argmax_flat, res, tol, n_points, n_pairs, n_rots,
+                                gx, gy, gz, nullptr, (cudaStream_t)stream_, res_host, row0);
 }
 
 namespace cppf {
 int rot_hist_launch(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
                     const int64_t* pos, const uint8_t* mask, const int64_t* block_offsets, int64_t n_pairs, const int64_t* count,
                     const float* sphere, float* counts, int n_points, int n_rots, int n_bins, int which, int64_t max_samples,
-                    uint64_t offset_seed, float thr, cudaStream_t stream, int pos_is_sample = 0) {
+                    uint64_t offset_seed, float thr, cudaStream_t stream, int pos_is_sample = 0, int row0 = 0) {
     if (n_rots > kMaxRotsP || n_rots <= 0 || max_samples <= 0 || n_bins <= 0) return (int)cudaErrorInvalidValue;
     if (pos == nullptr && (mask == nullptr || block_offsets == nullptr)) return (int)cudaErrorInvalidValue;
     int terr = 0;
@@ -1079,7 +1103,7 @@ int rot_hist_launch(const float* points, const uint8_t* bins, const float* lut, 
     RotHistParams prm{rot_tab, points, bins, lut, idx, reinterpret_cast<const long long*>(pos), pos_is_sample, mask,
                       reinterpret_cast<const long long*>(block_offsets), n_blocks, (long long)n_pairs,
                       reinterpret_cast<const long long*>(count), sphere, counts, n_points, n_rots, n_bins, which,
-                      (long long)max_samples, offset_seed, thr, ywin};
+                      (long long)max_samples, offset_seed, thr, ywin, row0};
     const long long blocks = (max_samples + kRotHistPairs - 1) / kRotHistPairs;
     if (blocks > 0x7FFFFFFF) return (int)cudaErrorInvalidValue;
     const size_t smem = (size_t)n_bins * 20;
@@ -1094,14 +1118,14 @@ int rot_hist_launch(const float* points, const uint8_t* bins, const float* lut, 
 int survivor_stats_launch(const float* points, const float* nrm, const float* tail, const void* idx, int idx_is_64,
                           const int64_t* pos, const uint8_t* mask, const int64_t* count, const float* sphere,
                           const int64_t* best_up, const int64_t* best_right, double* out, int n_points, int64_t n_pairs,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int row0 = 0) {
     if (pos == nullptr && mask == nullptr) return (int)cudaErrorInvalidValue;
     CPPF_RETURN_IF(cudaMemsetAsync(out, 0, 6 * sizeof(double), stream));
     const bool aligned = (((uintptr_t)points | (uintptr_t)tail | (uintptr_t)mask) & 15u) == 0;
     const int vec4 = (pos == nullptr && idx == nullptr && (n_points & 3) == 0 && aligned) ? 1 : 0;
     StatsParams prm{points, nrm, tail, idx, reinterpret_cast<const long long*>(pos), mask,
                     reinterpret_cast<const long long*>(count), sphere, reinterpret_cast<const long long*>(best_up),
-                    reinterpret_cast<const long long*>(best_right), out, n_points, (long long)n_pairs, vec4};
+                    reinterpret_cast<const long long*>(best_right), out, n_points, (long long)n_pairs, vec4, row0};
     const int blocks = sm_count() * CPPF_STATS_BLOCKS_PER_SM;
     if (idx_is_64) survivor_stats_kernel<true><<<blocks, 256, 0, stream>>>(prm);
     else survivor_stats_kernel<false><<<blocks, 256, 0, stream>>>(prm);
@@ -1117,6 +1141,14 @@ extern "C" int cppf_rot_hist(const float* points, const uint8_t* bins, const flo
     if (pos == nullptr) return (int)cudaErrorInvalidValue;
     return rot_hist_launch(points, bins, lut, idx, idx_is_64, pos, nullptr, nullptr, 0, count, sphere, counts, n_points, n_rots,
                            n_bins, which, max_samples, offset_seed, thr, (cudaStream_t)stream_);
+}
+
+extern "C" int cppf_rot_hist_rows(const float* points, const uint8_t* bins, const float* lut, int row0, const int64_t* pos,
+                                  const int64_t* count, const float* sphere, float* counts, int n_points, int n_rots, int n_bins,
+                                  int which, int64_t max_samples, uint64_t offset_seed, float thr, void* stream_) {
+    if (pos == nullptr || row0 < 0 || row0 >= n_points) return (int)cudaErrorInvalidValue;
+    return rot_hist_launch(points, bins, lut, nullptr, 0, pos, nullptr, nullptr, 0, count, sphere, counts, n_points, n_rots,
+                           n_bins, which, max_samples, offset_seed, thr, (cudaStream_t)stream_, 0, row0);
 }
 
 extern "C" int cppf_rot_hist_mask(const float* points, const uint8_t* bins, const float* lut, const void* idx, int idx_is_64,
@@ -1147,6 +1179,14 @@ extern "C" int cppf_survivor_stats(const float* points, const float* nrm, const 
     if (pos == nullptr) return (int)cudaErrorInvalidValue;
     return survivor_stats_launch(points, nrm, tail, idx, idx_is_64, pos, nullptr, count, sphere, best_up, best_right, out,
                                  n_points, n_pairs, (cudaStream_t)stream_);
+}
+
+extern "C" int cppf_survivor_stats_rows(const float* points, const float* nrm, const float* tail, int row0, const int64_t* pos,
+                                        const int64_t* count, const float* sphere, const int64_t* best_up,
+                                        const int64_t* best_right, double* out, int n_points, int64_t n_pairs, void* stream_) {
+    if (pos == nullptr || !dense_rows_ok(nullptr, n_points, n_pairs, row0)) return (int)cudaErrorInvalidValue;
+    return survivor_stats_launch(points, nrm, tail, nullptr, 0, pos, nullptr, count, sphere, best_up, best_right, out, n_points,
+                                 n_pairs, (cudaStream_t)stream_, row0);
 }
 
 extern "C" int cppf_survivor_stats_mask(const float* points, const float* nrm, const float* tail, const void* idx,

@@ -11,8 +11,10 @@ and the path gets three small exchange steps, each a sum:
   2. the orientation histogram(s) (480 integer-valued float32 counts per direction);
   3. the survivor statistics (6 float64 sums: log-scale x3, count, aux-sign scores).
 
-Between the exchanges every rank runs the same kernels as the single-GPU staged path on its own pairs
-(indexed mode, int32 pair list of the block).  The steps are written as a generator that yields each
+Between the exchanges every rank runs the same kernels as the single-GPU staged path on its own pairs: in dense
+ROW-BLOCK mode (the ``cppf_*_rows`` entry points enumerate rows [lo, hi) of the pair matrix in-kernel, keeping the
+row-aligned MMA tiles and the tiled vote batches of the dense path and drawing the same Philox stream as a
+full-matrix launch) when the grid fits the shared-memory vote kernel, else over an int32 pair list of the block.  The steps are written as a generator that yields each
 tensor to be summed, so the same code runs under ``torch.distributed`` (``estimate_rowsplit``; NCCL on the
 box, one process per GPU) and in a single process that plays all ranks in lockstep
 (``estimate_rowsplit_local``: the parity test on one GPU).
@@ -70,14 +72,21 @@ def _steps(est, pc, nrm, seed, uniforms, inject_bins, rank, world, out):
     dims = voting.grid_dims(pc, corner, cfg.res)                                            # nocs/inference.py:194-195
     cells = dims[0] * dims[1] * dims[2]
     lo, hi = row_block(n, world, rank)
-    idxs = _cached_block_pairs(n, lo, hi, dev)
     sl = slice(lo * n, hi * n)
     feat = est.point_features(pc, nrm)
     table = est.ppf.tc_preproject(feat) if est.encoder_impl == "tc" else est.ppf.preproject(feat)
     heads = fast.HEAD_TR | fast.HEAD_UP | fast.HEAD_TAIL | (fast.HEAD_RIGHT if cfg.regress_right else 0)
+    # Dense row-block mode (the `_rows` entry points: the kernels enumerate rows [lo, hi) of the pair matrix themselves, with
+    # every dense-mode shortcut and no pair list in HBM) whenever the grid fits the shared-memory vote kernel and the
+    # tcgen05 encoder runs; otherwise an explicit int32 pair list of the block (1 GB at N = 16 k, world 2).
+    dense_rows = (est.encoder_impl == "tc" and cfg.num_rots <= 72 and fast.vote_fits_private(dims) and hi > lo)
+    rows = (lo, hi) if dense_rows else None
+    row0 = lo if dense_rows else None
+    idxs = None if dense_rows else _cached_block_pairs(n, lo, hi, dev)
+    # the Philox stream is keyed by the pair's index in the whole matrix (dense rows): every world size draws the same bins
     bins, tail = fast.encode_sample(est.ppf, pc, nrm, table, idxs, heads=heads,
                                     uniforms=uniforms[sl] if uniforms is not None else None,
-                                    seed=int(seed) * 1000003 + rank, impl=est.encoder_impl)
+                                    seed=int(seed) if dense_rows else int(seed) * 1000003 + rank, impl=est.encoder_impl, rows=rows)
     if inject_bins is not None:
         bins[:, :inject_bins.shape[1]] = inject_bins[sl]
     grid = torch.zeros(dims, dtype=torch.float32, device=dev)
@@ -87,7 +96,7 @@ def _steps(est, pc, nrm, seed, uniforms, inject_bins, rank, world, out):
         if fast.vote_fits_private(dims):
             acc = torch.zeros(cells, dtype=torch.int64, device=dev)
             fast.vote_fast(pc, idxs, junk, corner, cfg.res, bins=bins, lut=est.lut, n_rots=cfg.num_rots,
-                           adaptive=cfg.adaptive_voting, scratch=acc)
+                           adaptive=cfg.adaptive_voting, scratch=acc, rows=rows)
         else:
             nb = _lib.lib().cppf_vote_routed_scratch_bytes(idxs.shape[0], cfg.num_rots, *dims)
             scratch = torch.zeros((nb + 7) // 8, dtype=torch.int64, device=dev)
@@ -104,17 +113,18 @@ def _steps(est, pc, nrm, seed, uniforms, inject_bins, rank, world, out):
         voting.ppf_vote(pc, mu_nu, idxs, grid, corner, cfg.res, cfg.num_rots, cfg.adaptive_voting)
         yield grid
     flat = voting.grid_argmax(grid)
-    mask = fast.backvote_bins(pc, bins, est.lut, idxs, dims, corner, flat, cfg.res, 3 * cfg.res, cfg.num_rots)
+    mask = fast.backvote_bins(pc, bins, est.lut, idxs, dims, corner, flat, cfg.res, 3 * cfg.res, cfg.num_rots, rows=rows)
     _, cnt, pos = voting.compact_pairs(mask, idxs, n, want_pos=True, want_idx=False)
     n_dirs = 2 if cfg.regress_right else 1
     quota = -(-int(cfg.rot_subsample) // world) if cfg.rot_subsample else (1 << 40)
     counts = torch.zeros((n_dirs, est.sphere.shape[0]), dtype=torch.float32, device=dev)
     for j in range(n_dirs):
         fast.rot_hist(pc, bins, est.lut, idxs, pos, cnt, est.sphere, which=j, n_rots=cfg.num_rots, max_samples=quota,
-                      offset_seed=(seed * 7919 + j) * 64 + rank, thr=est.cos_thr, counts=counts[j])
+                      offset_seed=(seed * 7919 + j) * 64 + rank, thr=est.cos_thr, counts=counts[j], row0=row0)
     yield counts                                                    # exchange 2: orientation histograms
     bests = [voting.grid_argmax(counts[j]) for j in range(n_dirs)]
-    stats = fast.survivor_stats(pc, nrm, tail, idxs, pos, cnt, est.sphere, bests[0], bests[1] if cfg.regress_right else None)
+    stats = fast.survivor_stats(pc, nrm, tail, idxs, pos, cnt, est.sphere, bests[0], bests[1] if cfg.regress_right else None,
+                                row0=row0)
     yield stats                                                     # exchange 3: survivor statistics
     rec = torch.cat([flat.double()] + [b.double() for b in bests] + [stats, corner.double()])
     out.update(record=rec, n_dirs=n_dirs, grid=grid, bins=bins, mask=mask, rows=(lo, hi), dims=dims)

@@ -377,6 +377,31 @@ int cppf_gaussian3d(const float* grid, float* out, float* tmp, int gx, int gy, i
 int cppf_scene_proposals(float* grid, int gx, int gy, int gz, float thresh, int margin, float rel_stop, int max_props,
                          float* h_out, void* scratch, void* stream);
 
+/* ==== one object over several GPUs: a ROW BLOCK of the dense pair matrix (second axis) ==========
+ * The `_rows` forms of the dense (idx == NULL) entry points enumerate the pairs (a, b) with a in [row0, row0 + n_pairs /
+ * n_points) and every b, in row-major order: pair p of the launch is (row0 + p / n_points, p % n_points), and bins / tail /
+ * mask / pos are indexed by that LOCAL p (n_pairs entries).  They keep every dense-mode shortcut (row-aligned MMA tiles with
+ * the a-side table row as a row constant, tiled vote batches, no index list in HBM).  The Philox stream of
+ * cppf_encode_sample_tc_rows is keyed by the pair's index in the WHOLE matrix, so the row blocks of all ranks together draw
+ * exactly what one full-matrix launch draws.  cppf_vote_fast_rows leaves its exact integer sums in `scratch` like
+ * cppf_vote_fast (all_reduce them, then cppf_vote_finalize). */
+int cppf_encode_sample_tc_rows(const float* pc, const float* nrm, const float* table, const float* tc_blob,
+                               const void* idx, int idx_is_64, int n_points, int64_t n_pairs, int row0,
+                               const float* uniforms, uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_t,
+                               void* stream);
+int cppf_vote_fast_rows(const float* points, const float* mu_nu, const uint8_t* bins, const float* lut, int row0,
+                        float* grid, void* scratch, const float* corner, float res, int n_points, int64_t n_pairs,
+                        int n_rots, int gx, int gy, int gz, int adaptive, void* stream);
+int cppf_backvote_bins_rows(const float* points, const uint8_t* bins, const float* lut, int row0, uint8_t* out_mask,
+                            const float* corner, const int64_t* argmax_flat, float res, float tol, double res_host,
+                            int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, void* stream);
+int cppf_rot_hist_rows(const float* points, const uint8_t* bins, const float* lut, int row0, const int64_t* pos,
+                       const int64_t* count, const float* sphere, float* counts, int n_points, int n_rots, int n_bins,
+                       int which, int64_t max_samples, uint64_t offset_seed, float thr, void* stream);
+int cppf_survivor_stats_rows(const float* points, const float* nrm, const float* tail, int row0, const int64_t* pos,
+                             const int64_t* count, const float* sphere, const int64_t* best_up, const int64_t* best_right,
+                             double* out, int n_points, int64_t n_pairs, void* stream);
+
 /* ==== measurement aids (bench.py's roofline block; never on the pose path) =====================================
  * cppf_vote_count: the ALGORITHMIC work of one centre-vote launch over these inputs, counted on the device with the
  * reference's own acceptance test (models/voting.py:21-39).  out3 (device, 3 x uint64): [0] rotation steps walked

@@ -37,8 +37,8 @@ def test_row_split_in_lockstep_equals_the_whole_pair_list(world, regress_right):
     n = 333                                            # rows do not divide evenly
     est = _estimator(regress_right=regress_right)
     pc, nrm, u, inj = _inputs(n)
-    whole = est.estimate_fused(pc, nrm, seed=0, idxs=rowsplit.block_pairs(n, 0, n, DEV), uniforms=u, inject_bins=inj,
-                               return_debug=True)
+    # the whole pair matrix in ONE dense launch vs its row blocks (cppf_*_rows: the same row-aligned tiles, in-kernel)
+    whole = est.estimate_fused(pc, nrm, seed=0, idxs=None, uniforms=u, inject_bins=inj, return_debug=True)
     split = rowsplit.estimate_rowsplit_local(est, pc, nrm, world, seed=0, uniforms=u, inject_bins=inj, return_debug=True)
     assert torch.equal(split["bins"], whole["bins"])
     assert torch.equal(split["grid"], whole["grid"])                    # exact integer sums, one rounding
@@ -50,6 +50,24 @@ def test_row_split_in_lockstep_equals_the_whole_pair_list(world, regress_right):
     np.testing.assert_allclose(split["RT"], whole["RT"], rtol=1e-6, atol=1e-9)
     one = rowsplit.estimate_rowsplit(est, pc, nrm, seed=0, uniforms=u, inject_bins=inj)      # no process group: world 1
     assert one["argmax_flat"] == whole["argmax_flat"] and one["n_survivors"] == whole["n_survivors"]
+    # no injected uniforms: the Philox stream is keyed by the pair's index in the WHOLE matrix, so the row blocks of any
+    # world size draw exactly the bins of the single dense launch
+    whole_s = est.estimate_fused(pc, nrm, seed=77, idxs=None, return_debug=True)
+    split_s = rowsplit.estimate_rowsplit_local(est, pc, nrm, world, seed=77, return_debug=True)
+    assert torch.equal(split_s["bins"], whole_s["bins"]) and torch.equal(split_s["grid"], whole_s["grid"])
+    assert split_s["argmax_flat"] == whole_s["argmax_flat"] and torch.equal(split_s["mask"], whole_s["mask"])
+
+
+def test_row_split_falls_back_to_a_pair_list_for_routed_grids():
+    """A 64^3 grid does not fit the shared-memory vote kernel: the row blocks then run over an explicit pair list and the
+    routed-slab vote, and still reproduce the single-GPU grid bit for bit."""
+    n = 200
+    est = _estimator()
+    pc, nrm = synth.synth_cylinder_grid64(n, 3)
+    u = torch.rand(n * n, 4, generator=torch.Generator().manual_seed(8)).to(DEV)
+    whole = est.estimate_fused(pc, nrm, seed=0, idxs=rowsplit.block_pairs(n, 0, n, DEV), uniforms=u, return_debug=True)
+    split = rowsplit.estimate_rowsplit_local(est, pc, nrm, 2, seed=0, uniforms=u, return_debug=True)
+    assert torch.equal(split["grid"], whole["grid"]) and split["argmax_flat"] == whole["argmax_flat"]
 
 
 def _free_port():
@@ -88,8 +106,7 @@ def test_row_split_over_two_gpus_nccl():
         assert p.exitcode == 0
     est = _estimator()
     pc, nrm, u, inj = _inputs(n)
-    whole = est.estimate_fused(pc, nrm, seed=0, idxs=rowsplit.block_pairs(n, 0, n, DEV), uniforms=u, inject_bins=inj,
-                               return_debug=True)
+    whole = est.estimate_fused(pc, nrm, seed=0, idxs=None, uniforms=u, inject_bins=inj, return_debug=True)
     for _, flat, surv, bests, RT, grid in results:
         assert flat == whole["argmax_flat"] and surv == whole["n_survivors"] and bests == whole["best_bins"]
         np.testing.assert_array_equal(grid, whole["grid"].cpu().numpy())
