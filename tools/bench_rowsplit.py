@@ -75,9 +75,10 @@ def main():
                 "pairs_per_sec": n * n / (ms * 1e-3), "single_gpu_one_call_ms": single, "speedup_vs_single": single / ms,
                 "same_argmax_as_single": bool(pose["argmax_flat"] == ref["argmax_flat"]),
                 "T_split": [float(v) for v in pose["T_host"]], "T_single": [float(v) for v in ref["T_host"]],
-                "note": "row blocks in indexed mode (int32 pair list per rank); exchanges: u64 vote grid, orientation "
-                        "histogram, survivor statistics (3 all_reduce); bins differ from the dense run only in the sampled "
-                        "right/aux heads (different Philox counters), votes are injected trained-like bins"}
+                "same_survivors_as_single": bool(pose["n_survivors"] == ref["n_survivors"]),
+                "note": "dense row-block mode (cppf_*_rows: in-kernel enumeration of the rank's rows, no pair list); exchanges: "
+                        "u64 vote grid, orientation histogram, survivor statistics (3 all_reduce); the Philox stream is keyed "
+                        "by the pair's index in the whole matrix, votes are injected trained-like bins"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
