@@ -78,6 +78,9 @@ def parse():
                          "come from the random-init network's own samples (cheap: most candidates fall outside the grid)")
     ap.add_argument("--encoder", default="tc", choices=["tc", "simt"],
                     help="fused path's pair encoder: tc = tcgen05 tensor cores (3xTF32), simt = fp32 FFMA warp tiles")
+    ap.add_argument("--streams", type=int, default=3,
+                    help="fused path: worker streams of the batched entry (cppf_pose_batch) the timed steps are enqueued through; "
+                         "1 = one cppf_pose_fused call per object on one stream")
     ap.add_argument("--path", default="fused", choices=["fused", "twopass"],
                     help="fused: encode+sample / privatised vote kernels; twopass: materialised logits like the reference")
     return ap.parse_args()
@@ -89,6 +92,8 @@ def workload_config(args):
             "n_points": args.n_points, "pairs_per_object": args.n_points ** 2, "objects_per_step_per_rank": 1,
             "out_dim": 141, "parallelism": f"objects sharded over {args.gpus} rank(s), one NCCL all_gather of pose records",
             "path": args.path, "votes": args.votes, "encoder": args.encoder,
+            "entry": (f"cppf_pose_batch: the K timed objects in one call, {args.streams} worker streams" if args.path == "fused" and args.streams > 1
+                      else "one cppf_pose_fused call per object, one stream"),
             "weights": "torch.manual_seed(0) default init of the reference architecture (no checkpoints exist offline)",
             "l2_policy": "per-step working set (bins + tail logits of 16.7M pairs = 403 MB, + 17 MB survivor mask) exceeds the "
                          "126 MB L2; each step is a different cloud"}
@@ -332,7 +337,7 @@ def main():
         return
 
     from cppf_b200 import _lib, model, shard, synth
-    from cppf_b200.pipeline import PoseConfig, PoseEstimator
+    from cppf_b200.pipeline import PoseConfig, PoseEstimator, enqueue_batch
 
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local)
@@ -386,7 +391,7 @@ def main():
         L.cppf_timing_reserve(timing, max(args.steps, 200))
     stage_names = [L.cppf_timing_stage_name(i).decode() for i in range(L.cppf_timing_stages())]
 
-    def run(leg, votes_injected=True):
+    def run(leg, votes_injected=True, batched=False):
         """leg 'hbm': clouds already on the device; leg 'e2e': pinned host buffers in, pose record out.
         The fused path enqueues every step with ONE library call (cppf_pose_fused) and never waits for the GPU
         inside the loop: the records come back through pinned buffers and are read after the last enqueue."""
@@ -405,20 +410,36 @@ def main():
             r = step(src[0], src[1], seed=s)
             if args.path == "fused":
                 r.result()
+        if batched:                     # warm the worker streams / workspaces of the batch entry too
+            w_items = [(est, (resident[s] if leg == "hbm" else pinned[s])[0], (resident[s] if leg == "hbm" else pinned[s])[1], s)
+                       for s in range(min(args.warmup, 3))]
+            enqueue_batch(w_items, n_streams=args.streams, n_threads=args.streams,
+                          inject_bins=[inject[s] if votes_injected else None for s in range(len(w_items))],
+                          capacities=[(cells[s], 0) for s in range(len(w_items))]).results(on_error="none")
         timers.clear()
         if timing:
             L.cppf_timing_collect(timing, (C.c_float * len(stage_names))())      # drop the warm-up marks
-        est.timing = timing
+        est.timing = None if batched else timing
         barrier()
         l0 = _lib.launch_count()
         t0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pend = []
-        for s in range(args.warmup, n_obj):
-            src = resident[s] if leg == "hbm" else pinned[s]
-            pend.append(step(src[0], src[1], seed=s))
-        records = [(p.result() if args.path == "fused" else p)["record"] for p in pend]
+        if batched:
+            # the K timed steps as ONE library call (cppf_pose_batch): the objects are fanned out over a few worker streams,
+            # so the dozen small kernels of one object run beside the large kernels of the next
+            items = [(est, (resident[s] if leg == "hbm" else pinned[s])[0], (resident[s] if leg == "hbm" else pinned[s])[1], s)
+                     for s in range(args.warmup, n_obj)]
+            pb = enqueue_batch(items, n_streams=args.streams, n_threads=args.streams,
+                               inject_bins=[inject[s] if votes_injected else None for s in range(args.warmup, n_obj)],
+                               capacities=[(cells[s], 0) for s in range(args.warmup, n_obj)])
+            records = list(pb.records17())
+        else:
+            pend = []
+            for s in range(args.warmup, n_obj):
+                src = resident[s] if leg == "hbm" else pinned[s]
+                pend.append(step(src[0], src[1], seed=s))
+            records = [(p.result() if args.path == "fused" else p)["record"] for p in pend]
         rec = np.stack(records)
         ids = [rank * args.steps + i for i in range(args.steps)]
         shard.gather_records(ids, rec, world * args.steps, device=dev)    # the one collective: pose hypotheses
@@ -445,12 +466,16 @@ def main():
                     stage_ms[name] = {"avg_ms": sum(durs) / len(durs), "launches": len(durs)}
         return float(t.item()), launches, clocks, stage_ms
 
-    ms_hbm, launches, window, timers = run("hbm")
+    use_batch = args.path == "fused" and args.streams > 1
+    ms_hbm, launches, window, timers = run("hbm", batched=use_batch)
     clocks = sampler.stop(*window) if sampler else None
-    ms_e2e, _, _, _ = run("e2e")
+    ms_e2e, _, _, _ = run("e2e", batched=use_batch)
+    ms_inst = ms_hbm
+    if use_batch:       # per-kernel times: a separate pass over the same objects, one stream, CUDA events around every stage
+        ms_inst, _, _, timers = run("hbm", batched=False)
     ms_net = None
     if args.votes == "trained_like" and args.path == "fused" and not args.no_variants:
-        ms_net, _, _, _ = run("hbm", votes_injected=False)
+        ms_net, _, _, _ = run("hbm", votes_injected=False, batched=use_batch)
     sampled = None
     if args.path == "fused" and not args.no_variants:
         # The reference's own inference regime (nocs/inference.py:120-129,177): 100 000 random pairs per object, clouds in
@@ -483,6 +508,16 @@ def main():
             if best is None or statistics.median(reps) < best[0]:
                 best = (statistics.median(reps), reps, statistics.median(host), n_str, n_thr)
         ms_1, reps, host_us, n_str, n_thr = best
+        # host cost of the enqueue alone: a batch small enough (12 objects, ~300 launches) that the launch queue never
+        # fills, issued to an idle GPU -- the call returns long before the kernels finish
+        free_us = []
+        for _ in range(5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pend = enqueue_batch(items[:12], n_streams=4, n_threads=4)
+            free_us.append((time.perf_counter() - t0) * 1e6 / 12)
+            pend.records17()
+        host_free_us = statistics.median(free_us)
         # per-object calls on one stream (round 1's path) for comparison, and the stage breakdown of one object
         def enq(s_):
             return est_s.enqueue_fused(pinned[s_ % n_obj][0], pinned[s_ % n_obj][1], seed=s_, max_cells=cells[s_ % n_obj])
@@ -509,7 +544,8 @@ def main():
             stage_s = {nm: round(acc[i] / max(calls, 1), 4) for i, nm in enumerate(stage_names)}
         sampled = {"objects_per_sec_per_gpu": n_s / (ms_1 * 1e-3), "pairs_per_sec_per_gpu": n_s * 100000 / (ms_1 * 1e-3),
                    "ms_per_object": ms_1 / n_s, "ms_per_object_repeats": [r / n_s for r in reps],
-                   "host_enqueue_us_per_object": host_us, "n_streams": n_str, "n_threads": n_thr, "sweep": sweep,
+                   "host_enqueue_us_per_object": host_free_us, "host_enqueue_us_per_object_queue_full": host_us,
+                   "n_streams": n_str, "n_threads": n_thr, "sweep": sweep,
                    "per_object_calls_one_stream": {"objects_per_sec": n_s / (ms_loop * 1e-3), "ms_per_object": ms_loop / n_s},
                    "stage_ms": stage_s, "pairs_per_object": 100000, "objects_per_batch": n_s,
                    "note": "reference regime: P = 100 000 sampled pairs (nocs/inference.py:177), host clouds in, pose records "
@@ -673,7 +709,13 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "objects_per_sec": world * args.steps / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_detail": detail, "kernels": kern,
-                "cpu_baseline": cpu, "ncu_constants_dropped_as_stale": ncu_stale}
+                "cpu_baseline": cpu, "ncu_constants_dropped_as_stale": ncu_stale,
+                "kernels_pass": {"ms_per_step": ms_inst / args.steps, "streams": 1,
+                                 "note": "`kernels`, `roofline` and `roofline_detail` come from a pass over the same K objects "
+                                         "enqueued one cppf_pose_fused call at a time on ONE stream with CUDA events around every "
+                                         "stage (under the multi-stream batch entry the kernels of neighbouring objects overlap "
+                                         "and per-kernel event times mean nothing); a kernel's share of the step is its avg_ms "
+                                         "over this pass's ms_per_step"} if use_batch else None}
         if ms_net is not None:
             line["variant_network_votes"] = {"value": total_pairs / (ms_net * 1e-3), "unit": UNIT,
                                              "ms_per_step": ms_net / args.steps,

@@ -192,7 +192,7 @@ extern "C" int cppf_peak_global_red(int gx, int gy, int gz, int reps, double* g_
     float* grid = nullptr;
     CPPF_RETURN_IF(cudaMalloc(&grid, (size_t)cells * 4));
     CPPF_RETURN_IF(cudaMemsetAsync(grid, 0, (size_t)cells * 4, stream));
-    const int iters = 512, blocks = sm_count() * 8, threads = 256;
+    const int iters = 96, blocks = sm_count() * 8, threads = 256;
     float ms = 0.f;
     const int err = best_ms([&] {
         global_red_kernel<<<blocks, threads, 0, stream>>>(grid, cells, iters, gz, gy * gz);

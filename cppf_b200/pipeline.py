@@ -537,6 +537,21 @@ class PoseEstimator:
 
 
 _ARGS_DTYPE = None
+_PINNED = {}              # (device index, tag) -> [pinned tensor, event of its last use]: cudaHostAlloc costs milliseconds
+
+
+def _pinned(dev, tag, shape, dtype):
+    """A cached page-locked host buffer of at least `shape` elements (grow-only).  Before it is handed out again the
+    previous user's stream work is waited for (the buffer is the source / target of an asynchronous copy)."""
+    key = (dev.index or 0, tag)
+    need = int(np.prod(shape))
+    ent = _PINNED.get(key)
+    if ent is None or ent[0].numel() < need or ent[0].dtype != dtype:
+        ent = _PINNED[key] = [torch.empty(max(need, 1), dtype=dtype, pin_memory=True), None]
+    if ent[1] is not None:
+        ent[1].synchronize()
+    return ent, ent[0][:need].view(*shape)
+
 
 
 def _args_dtype():
@@ -594,12 +609,15 @@ class PendingBatch:
 
 
 @torch.no_grad()
-def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None):
+def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None, inject_bins=None, capacities=None):
     """The object loop of nocs/inference.py:120-129 as ONE library call (cppf_pose_batch).
     items = [(estimator, pc, normals, seed), ...]: float32 [N_i,3] clouds, host (numpy / pinned torch) or CUDA; objects may
     belong to different categories (estimators).  Host clouds are packed into one pinned block and copied with ONE
     host->device copy; the point pairs of nocs/inference.py:177 are drawn on the device (cfg.n_pairs > 0; 0 = all N^2
-    pairs); all records come back with ONE device->host copy.  -> PendingBatch."""
+    pairs); all records come back with ONE device->host copy.  inject_bins: optional list (one uint8 CUDA tensor [P_i, c]
+    or None per object) overwriting the sampled bins (benchmark aid, see enqueue_fused).  capacities: optional list of
+    (max_cells, routed_max_cells) per object (see grid_capacity; deriving them from a CUDA-resident cloud costs a device->host
+    copy per object).  -> PendingBatch."""
     if not items:
         raise ValueError("empty batch")
     dev = items[0][0].device
@@ -614,7 +632,7 @@ def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None):
     keep = []
     ptr_pc, ptr_nrm = np.zeros(n_obj, np.uint64), np.zeros(n_obj, np.uint64)
     if host_rows:
-        stage = torch.empty((2 * host_rows, 3), dtype=torch.float32, pin_memory=True)
+        stage_ent, stage = _pinned(dev, "clouds", (2 * host_rows, 3), torch.float32)
         sn = stage.numpy()
         off = 0
         offs = []
@@ -627,7 +645,9 @@ def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None):
             offs.append(off)
             off += 2 * n
         dstage = stage.to(dev, non_blocking=True)
-        keep += [stage, dstage]
+        stage_ent[1] = torch.cuda.Event()
+        stage_ent[1].record()
+        keep += [dstage]
         base = dstage.data_ptr()
         for i, (o, n) in enumerate(zip(offs, ns)):
             if o >= 0:
@@ -639,8 +659,8 @@ def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None):
             ptr_pc[i], ptr_nrm[i] = pcd.data_ptr(), nd.data_ptr()
     # ---- grid capacities (nocs/inference.py:194-195) and pair counts
     caps = []
-    for (est, pc, nrm, _), d in zip(items, on_dev):
-        cap = est.grid_capacity(pc)
+    for k_, ((est, pc, nrm, _), d) in enumerate(zip(items, on_dev)):
+        cap = capacities[k_] if capacities is not None else est.grid_capacity(pc)
         if cap is None:
             raise RuntimeError("vote grid too large for cppf_pose_batch; use estimate_fused(staged=True) for this object")
         if not est._onecall_ok():
@@ -679,6 +699,12 @@ def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None):
     wsp = np.array([w.data_ptr() for w in ws], np.uint64)
     wsb = np.array([w.numel() for w in ws], np.int64)
     a["workspace"], a["workspace_bytes"] = wsp[np.arange(n_obj) % n_streams], wsb[np.arange(n_obj) % n_streams]
+    if inject_bins is not None:
+        for i, t in enumerate(inject_bins):
+            if t is not None:
+                assert t.dtype == torch.uint8 and t.is_contiguous() and t.shape[0] == int(pairs[i])
+                a["inject_bins"][i], a["inject_cols"][i] = t.data_ptr(), t.shape[1]
+        keep.append(list(inject_bins))
     groups = {}
     for i, it in enumerate(items):
         groups.setdefault(id(it[0]), (it[0], []))[1].append(i)
@@ -696,7 +722,9 @@ def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None):
     with torch.cuda.device(dev):
         _lib.check(L.cppf_pose_batch(a.ctypes.data, n_obj, n_streams, n_threads, torch.cuda.current_stream(dev).cuda_stream),
                    "cppf_pose_batch")
-    host = torch.empty((n_obj, 16), dtype=torch.float64, pin_memory=True)
+    # page-locked target of the one D2H copy, sized in steps of 256 objects so that torch's caching host allocator hands the
+    # block of an earlier batch back instead of calling cudaHostAlloc (milliseconds) for every new batch size
+    host = torch.empty((-(-n_obj // 256) * 256, 16), dtype=torch.float64, pin_memory=True)[:n_obj]
     host.copy_(rec, non_blocking=True)
     done = torch.cuda.Event()
     done.record()
