@@ -13,8 +13,14 @@ const float2* rot_table_device(cudaStream_t stream, int* err);   // vote.cu: (co
 // x-slabs of the routed vote (vote_routed.cu): as many planes per slab as fit `cap` u32 cells, minus the overlap
 // plane of the x+1 corners.  Shared by the host plan and the device-side geometry kernel (pose.cu).
 constexpr int kMaxSlabs = 8;
+// Strides of a slab in shared memory.  The slab is private to its CTA, so its rows and planes can be padded: with the
+// natural strides of a 64^3 grid (gz = 64, gy * gz = 4096, both multiples of the 32 banks) the bank of a cell is fz mod 32
+// alone, the candidates a warp splats together are close in z, and an ATOMS took 5.3 wavefronts instead of the 3.6 of
+// random banks.  Odd strides make every unit step in x or y move the bank by an odd amount.
+__host__ __device__ inline int slab_row_stride(int gz) { return gz | 1; }
+__host__ __device__ inline int slab_plane_stride(int gy, int gz) { return (gy * slab_row_stride(gz)) | 1; }
 __host__ __device__ inline bool routed_plan_hd(int gx, int gy, int gz, long long cap, int* pps, int* n_slabs) {
-    const long long gyz = (long long)gy * gz;
+    const long long gyz = (long long)slab_plane_stride(gy, gz);
     const long long planes = cap / gyz - 1;
     if (planes < 1 || gx > 1024) return false;
     *pps = (int)(planes < gx ? planes : gx);

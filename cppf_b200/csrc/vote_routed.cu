@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
     int gx = prm.gx, gy = prm.gy, gzd = prm.gz, pps = prm.planes_per_slab, n_slabs = prm.n_slabs;
     if (prm.geom != nullptr) {
         const Geom g = *prm.geom;
-        if (g.status != 0 || g.mode != 1 || (g.planes_per_slab + 1) * g.gy * g.gz > prm.max_slab_cells) return;
+        if (g.status != 0 || g.mode != 1 || (g.planes_per_slab + 1) * slab_plane_stride(g.gy, g.gz) > prm.max_slab_cells) return;
         gx = g.gx; gy = g.gy; gzd = g.gz; pps = g.planes_per_slab; n_slabs = g.n_slabs;
     }
     if (threadIdx.x == 0) {
@@ -365,10 +365,17 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
     const int slab = s_slab, j = s_j, m = s_m;
     if (slab < 0) return;
     const int gyz = gy * gzd, gz = gzd;
+    const int rs = slab_row_stride(gz), ps = slab_plane_stride(gy, gz);        // padded strides of the slab in shared memory
     const int x0 = slab * pps;
     const int x1 = min(gx, x0 + pps + 1);                          // + the overlap plane of the x+1 corners
-    const int cells = (x1 - x0) * gyz;
+    const int cells = (x1 - x0) * ps;                               // padded cells (the padding stays zero)
     const unsigned s_grid_addr = (unsigned)__cvta_generic_to_shared(s_grid);
+    // padded slab index -> flat index of the cell in the global grid, or -1 for a padding word
+    auto global_cell = [&](int i) -> long long {
+        const int x = i / ps, r = i - x * ps;
+        const int y = r / rs, z = r - y * rs;
+        return (y < gy && z < gz) ? (long long)(x0 + x) * gyz + (long long)y * gz + z : -1ll;
+    };
     for (int i = threadIdx.x; i < cells; i += blockDim.x) s_grid[i] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
                 for (int i = threadIdx.x; i < cells; i += blockDim.x) {
                     const unsigned v = s_grid[i];
                     if (v >= kSplatFlushAt) {
-                        atomicAdd(prm.acc + (long long)x0 * gyz + i, (unsigned long long)v);
+                        atomicAdd(prm.acc + global_cell(i), (unsigned long long)v);
                         s_grid[i] = 0u;
                     }
                 }
@@ -423,9 +430,16 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
 #pragma unroll
                         for (int q = 0; q < 4; ++q) nx[q] = __ldg(ch + (part + 1) * 128 + q * 32 + lane);
                     }
+                    // Lane l takes its four entries in the order (q + l) mod 4: the 32 entries splatted by one instruction then
+                    // come from four different 32-entry runs of the chunk (8 lanes each).  Consecutive entries of a chunk are
+                    // candidates of ONE route32 call -- the same 32 pairs at the same rotation step, which reach the vote peak
+                    // together -- and splatting them side by side cost 5.3 wavefronts per ATOMS (same-cell collisions).
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (g[q].x == g[q].x) splat_fixed(s_grid_addr, g[q].x - fx0, g[q].y, g[q].z, gyz, gz);   // NaN = padding
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = (q + lane) & 3;
+                        const float4 e = k == 0 ? g[0] : (k == 1 ? g[1] : (k == 2 ? g[2] : g[3]));
+                        if (e.x == e.x) splat_fixed(s_grid_addr, e.x - fx0, e.y, e.z, ps, rs);                   // NaN = padding
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) g[q] = nx[q];
                 }
@@ -435,7 +449,7 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
         const unsigned v = s_grid[i];
-        if (v) atomicAdd(prm.acc + (long long)x0 * gyz + i, (unsigned long long)v);
+        if (v) atomicAdd(prm.acc + global_cell(i), (unsigned long long)v);
     }
 }
 
@@ -451,7 +465,7 @@ long long slab_cap_cells() { return ((long long)220 * 1024) / 4; }      // u32 c
 
 static bool routed_plan(int gx, int gy, int gz, RoutedPlan* pl) {
     const long long gyz = (long long)gy * gz;
-    const long long planes = slab_cap_cells() / gyz - 1;                 // minus the overlap plane
+    const long long planes = slab_cap_cells() / slab_plane_stride(gy, gz) - 1;    // minus the overlap plane
     if (planes < 1 || gx > 1024) return false;
     pl->planes_per_slab = (int)(planes < gx ? planes : gx);
     pl->n_slabs = (gx + pl->planes_per_slab - 1) / pl->planes_per_slab;
@@ -512,7 +526,7 @@ int vote_routed_launch(const float* points, const float* mu_nu, const uint8_t* b
     else route = idx_is_64 ? route_kernel<true, false> : route_kernel<false, false>;
     const size_t rsmem = route_smem();
     CPPF_RETURN_IF(cudaFuncSetAttribute(route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-    const long long slab_cells = geom ? slab_cap_cells() : (long long)(pl.planes_per_slab + 1) * gy * gz;
+    const long long slab_cells = geom ? slab_cap_cells() : (long long)(pl.planes_per_slab + 1) * slab_plane_stride(gy, gz);
     const size_t ssmem = (size_t)slab_cells * 4;
     CPPF_RETURN_IF(cudaFuncSetAttribute(slab_splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
     const int64_t total_batches = idx == nullptr

@@ -136,3 +136,33 @@ def test_degenerate_and_empty_inputs():
     assert float(grid.abs().sum()) == 0.0
     with pytest.raises(RuntimeError):                     # fewer points than neighbours: the kNN refuses (k > N)
         est.estimate_fused(pc[:40], nrm[:40], seed=0)
+
+
+def test_vote_count_and_peaks_measurement_aids():
+    """bench.py's roofline inputs are measured, not pasted: cppf_vote_count must count exactly the candidates the reference's
+    acceptance test (models/voting.py:21-39) lets through -- checked against the number of atomic adds the reference kernel
+    itself performs (the grid's total mass: every in-bounds candidate adds exactly 1 when prob = 1) -- and the peak
+    microbenchmarks must return sane rates."""
+    import ctypes as C
+    from cppf_b200 import _lib, fast, voting
+    n, p = 700, 60000
+    pc, _ = synth.synth_bottle(n, 4)
+    idxs = synth.sample_pairs(n, p, 4).astype(np.int32)
+    tr = synth.trained_like_tr(pc, idxs)
+    corner, dims = synth.vote_grid_geometry(pc, 4e-3)
+    t = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(DEV, dt)
+    out = torch.zeros(3, dtype=torch.int64, device=DEV)
+    L = _lib.lib()
+    sp = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.cppf_vote_count(t(pc).data_ptr(), t(tr).data_ptr(), None, None, t(idxs, torch.int32).data_ptr(), 0,
+                                 t(corner).data_ptr(), 4e-3, n, p, 72, dims[0], dims[1], dims[2], 1, out.data_ptr(), sp), "count")
+    steps, inb, live = [int(v) for v in out.cpu()]
+    grid = torch.zeros(dims, device=DEV)
+    voting.ppf_vote(t(pc), t(tr), t(idxs, torch.int32), grid, t(corner), 4e-3, 72, True)
+    assert abs(float(grid.double().sum()) - inb) < 1e-3 * inb + 1          # trilinear weights of a candidate sum to 1
+    assert live == int((idxs[:, 0] != idxs[:, 1]).sum()) and steps >= inb > 0
+    pk = (C.c_double * 3)()
+    _lib.check(L.cppf_peak_shared_atomics(dims[0], dims[1], dims[2], 0, 2, C.byref(pk, 0), sp), "peak")
+    _lib.check(L.cppf_peak_shared_atomics(dims[0], dims[1], dims[2], 1, 2, C.byref(pk, 8), sp), "peak")
+    _lib.check(L.cppf_peak_global_red(dims[0], dims[1], dims[2], 2, C.byref(pk, 16), sp), "peak")
+    assert pk[1] > pk[0] > pk[2] > 1.0            # conflict-free > random-bank shared > global fp32 reductions (G atomics/s)

@@ -101,3 +101,29 @@ def test_estimate_scene_finds_both_objects():
         assert len(lab) > 300 and (lab == lab[0]).all()                     # the instance mask stays on one object
         assert abs(abs(f["up"][1]) - 1) < 0.05                               # bottles stand along y
         np.testing.assert_allclose(f["scales"] * np.linalg.norm(np.float32([0.1, 0.3, 0.1])), [0.1, 0.3, 0.1], rtol=1e-5)
+
+
+def test_estimate_scene_runs_with_the_real_regression_head_encoder():
+    """scene mode must run with cppf_b200.model.PPFEncoder(out_dim=9) itself -- its forward_with_idx returns an
+    unbatched [P, 9] tensor like the reference's (models/model.py:117-137).  Random-init weights vote at random, so only the
+    plumbing is asserted: the flow runs end to end (votes, smoothing, proposals, per-proposal refinement with a low
+    threshold) and returns well-formed proposals."""
+    res = 8e-3
+    pc1, n1 = synth.synth_bottle(700, 0)
+    pc = torch.from_numpy(pc1 + np.float32([0.0, 0.0, 0.8])).to(DEV)
+    nrm = torch.from_numpy(n1).to(DEV)
+    torch.manual_seed(0)
+    pe = model.PointEncoder(k=60, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(DEV).eval()
+    head = model.PPFEncoder(ppffcs=[84, 32, 32, 16], out_dim=9).to(DEV).eval()
+    idx = torch.randint(0, 700, (50000, 2), device=DEV, dtype=torch.int32)
+    with torch.no_grad():
+        preds = head.forward_with_idx(pc, nrm, pe.encode_fused(pc, nrm), idx)
+    assert preds.shape == (50000, 9)                                        # unbatched, like the reference
+    with torch.no_grad():
+        head.final.bias[:2] = torch.tensor([0.0, 0.03], device=DEV)          # votes land inside the scene grid
+    found = scene.estimate_scene(pe, head, pc, nrm, res=res, scale_mean=(0.05, 0.15, 0.05), n_pairs=200000, thresh=0.5,
+                                 margin=3, min_contrib=1, seed=1)
+    assert isinstance(found, list) and len(found) >= 1
+    for f in found:
+        assert np.isfinite(f["RT"]).all() and np.isfinite(f["scales"]).all() and f["n_pairs"] > 0
+        assert abs(np.linalg.norm(f["up"]) - 1) < 1e-6
