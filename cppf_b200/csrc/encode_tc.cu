@@ -688,6 +688,7 @@ extern "C" int cppf_encode_sample_tc_rows(const float* pc, const float* nrm, con
 extern "C" int cppf_encode_sample_tc(const float* pc, const float* nrm, const float* table, const float* tc_blob,
                                      const void* idx, int idx_is_64, int n_points, int64_t n_pairs, const float* uniforms,
                                      uint64_t seed, int heads, uint8_t* bins, float* tail, float* dbg_t, void* stream) {
+    if (n_pairs <= 0) return 0;
     if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     return cppf_encode_sample_tc_rows(pc, nrm, table, tc_blob, idx, idx_is_64, n_points, n_pairs, 0, uniforms, seed, heads, bins,
                                       tail, dbg_t, stream);

@@ -1036,6 +1036,7 @@ extern "C" int cppf_vote_fast(const float* points, const float* mu_nu, const uin
                               const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
                               int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
                               void* stream_) {
+    if (n_pairs <= 0) return 0;
     if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     return vote_fast_launch(points, mu_nu, bins, lut, idx, idx_is_64, grid, scratch, corner, res, n_points, n_pairs, n_rots,
                             gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, 0, 0, 0);
@@ -1066,6 +1067,7 @@ extern "C" int cppf_vote_slabs(const float* points, const float* mu_nu, const ui
                                const void* idx, int idx_is_64, float* grid, void* scratch, const float* corner, float res,
                                int n_points, int64_t n_pairs, int n_rots, int gx, int gy, int gz, int adaptive,
                                void* stream_) {
+    if (n_pairs <= 0) return 0;
     if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     return vote_fast_launch(points, mu_nu, bins, lut, idx, idx_is_64, grid, scratch, corner, res, n_points, n_pairs, n_rots,
                             gx, gy, gz, adaptive, nullptr, 0, (cudaStream_t)stream_, cppf_vote_private_max_cells(), 0, 0);
@@ -1075,6 +1077,7 @@ extern "C" int cppf_backvote_bins(const float* points, const uint8_t* bins, cons
                                   int idx_is_64, uint8_t* out_mask, const float* corner, const int64_t* argmax_flat,
                                   float res, float tol, double res_host, int n_points, int64_t n_pairs, int n_rots, int gx,
                                   int gy, int gz, void* stream_) {
+    if (n_pairs <= 0) return 0;
     if (idx == nullptr && n_pairs != (int64_t)n_points * n_points) return (int)cudaErrorInvalidValue;
     return backvote_bins_launch(points, bins, lut, idx, idx_is_64, out_mask, corner, argmax_flat, res, tol, n_points, n_pairs,
                                 n_rots, gx, gy, gz, nullptr, (cudaStream_t)stream_, res_host, 0);

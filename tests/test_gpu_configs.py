@@ -154,11 +154,12 @@ def test_vote_count_and_peaks_measurement_aids():
     out = torch.zeros(3, dtype=torch.int64, device=DEV)
     L = _lib.lib()
     sp = torch.cuda.current_stream().cuda_stream
-    _lib.check(L.cppf_vote_count(t(pc).data_ptr(), t(tr).data_ptr(), None, None, t(idxs, torch.int32).data_ptr(), 0,
-                                 t(corner).data_ptr(), 4e-3, n, p, 72, dims[0], dims[1], dims[2], 1, out.data_ptr(), sp), "count")
+    d_pc, d_tr, d_idx, d_corner = t(pc), t(tr), t(idxs, torch.int32), t(corner)      # kept alive across the launches
+    _lib.check(L.cppf_vote_count(d_pc.data_ptr(), d_tr.data_ptr(), None, None, d_idx.data_ptr(), 0, d_corner.data_ptr(), 4e-3,
+                                 n, p, 72, dims[0], dims[1], dims[2], 1, out.data_ptr(), sp), "count")
     steps, inb, live = [int(v) for v in out.cpu()]
     grid = torch.zeros(dims, device=DEV)
-    voting.ppf_vote(t(pc), t(tr), t(idxs, torch.int32), grid, t(corner), 4e-3, 72, True)
+    voting.ppf_vote(d_pc, d_tr, d_idx, grid, d_corner, 4e-3, 72, True)
     assert abs(float(grid.double().sum()) - inb) < 1e-3 * inb + 1          # trilinear weights of a candidate sum to 1
     assert live == int((idxs[:, 0] != idxs[:, 1]).sum()) and steps >= inb > 0
     pk = (C.c_double * 3)()
