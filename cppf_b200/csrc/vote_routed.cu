@@ -445,6 +445,9 @@ __global__ void __launch_bounds__(kSplatThreads, 1) slab_splat_kernel(const Spla
                 }
             }
         }
+        // every warp is done with s_list / s_count of this round before the next round rewrites them (racecheck, round 2:
+        // a warp still between the barrier above and its read of s_count could see the next round's reset)
+        __syncthreads();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
