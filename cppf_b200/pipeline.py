@@ -631,17 +631,22 @@ def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None, i
     host_rows = int(sum(n for n, d in zip(ns, on_dev) if not d))
     keep = []
     ptr_pc, ptr_nrm = np.zeros(n_obj, np.uint64), np.zeros(n_obj, np.uint64)
+    lo_hi = np.zeros((n_obj, 2, 3), np.float32)                      # bounding boxes of the host clouds (nocs/inference.py:194)
     if host_rows:
         stage_ent, stage = _pinned(dev, "clouds", (2 * host_rows, 3), torch.float32)
         sn = stage.numpy()
         off = 0
         offs = []
-        for (est, pc, nrm, _), d, n in zip(items, on_dev, ns):
+        for k_, ((est, pc, nrm, _), d, n) in enumerate(zip(items, on_dev, ns)):
             if d:
                 offs.append(-1)
                 continue
-            sn[off:off + n] = pc.numpy() if isinstance(pc, torch.Tensor) else pc
+            blk = sn[off:off + n]
+            blk[:] = pc.numpy() if isinstance(pc, torch.Tensor) else pc
             sn[off + n:off + 2 * n] = nrm.numpy() if isinstance(nrm, torch.Tensor) else nrm
+            if capacities is None:
+                bt = np.ascontiguousarray(blk.T)                 # [3, N]: a reduction along axis 0 of [N, 3] is ~25x slower
+                lo_hi[k_, 0], lo_hi[k_, 1] = bt.min(1), bt.max(1)
             offs.append(off)
             off += 2 * n
         dstage = stage.to(dev, non_blocking=True)
@@ -658,28 +663,44 @@ def enqueue_batch(items, n_streams: int = 4, n_threads: int = 4, n_pairs=None, i
             keep += [pcd, nd]
             ptr_pc[i], ptr_nrm[i] = pcd.data_ptr(), nd.data_ptr()
     # ---- grid capacities (nocs/inference.py:194-195) and pair counts
-    caps = []
-    for k_, ((est, pc, nrm, _), d) in enumerate(zip(items, on_dev)):
-        cap = capacities[k_] if capacities is not None else est.grid_capacity(pc)
-        if cap is None:
-            raise RuntimeError("vote grid too large for cppf_pose_batch; use estimate_fused(staged=True) for this object")
-        if not est._onecall_ok():
-            raise RuntimeError("cppf_pose_batch needs the tcgen05 encoder and the reference PointEncoder / head configuration")
-        caps.append(cap)
+    if not all(it[0]._onecall_ok() for it in {id(it[0]): it for it in items}.values()):
+        raise RuntimeError("cppf_pose_batch needs the tcgen05 encoder and the reference PointEncoder / head configuration")
+    if capacities is not None:
+        caps = [tuple(c) for c in capacities]
+    else:
+        # host clouds: grid dims for the whole batch at once (float32 like numpy at :195); CUDA clouds: one round trip each
+        res_v = np.array([it[0].cfg.res for it in items], np.float64)
+        dims_v = ((lo_hi[:, 1] - lo_hi[:, 0]) / res_v[:, None].astype(np.float32)).astype(np.int32) + 1
+        cells_v = dims_v.astype(np.int64).prod(1)
+        priv_max = L.cppf_vote_private_max_cells()
+        caps = []
+        for k_, ((est, pc, nrm, _), d) in enumerate(zip(items, on_dev)):
+            if d:
+                cap = est.grid_capacity(pc)
+            elif cells_v[k_] <= priv_max:
+                cap = (int(cells_v[k_]), 0)
+            else:
+                cap = (1, int(cells_v[k_])) if fast.vote_routed_supported(tuple(int(v) for v in dims_v[k_])) else None
+            if cap is None:
+                raise RuntimeError("vote grid too large for cppf_pose_batch; use estimate_fused(staged=True) for this object")
+            caps.append(cap)
     caps = np.asarray(caps, np.int64)
     pairs = np.array([(it[0].cfg.n_pairs if n_pairs is None else n_pairs) for it in items], np.int64)
     dense = pairs <= 0
     pairs = np.where(dense, ns * ns, pairs)
     # ---- one workspace per worker stream, sized for the largest object it serves
     ws = []
+    ws_bytes = {}
     for s_ in range(n_streams):
         rows = np.arange(s_, n_obj, n_streams)
         nb = 0
         for i in rows:
             cfg = items[i][0].cfg
-            nb = max(nb, L.cppf_pose_workspace_bytes(int(ns[i]), 0 if dense[i] else int(pairs[i]), cfg.knn, int(caps[i, 0]),
-                                                     int(caps[i, 1]), cfg.num_rots, items[i][0].sphere.shape[0],
-                                                     int(cfg.rot_subsample or 0)))
+            key = (int(ns[i]), 0 if dense[i] else int(pairs[i]), cfg.knn, int(caps[i, 0]), int(caps[i, 1]), cfg.num_rots,
+                   items[i][0].sphere.shape[0], int(cfg.rot_subsample or 0))
+            if key not in ws_bytes:
+                ws_bytes[key] = L.cppf_pose_workspace_bytes(*key)
+            nb = max(nb, ws_bytes[key])
         slot = ("batch", dev.index or 0, s_)
         w = _WORKSPACES.get(slot)
         if w is None or w.numel() < nb:
@@ -738,8 +759,12 @@ def estimate_many(items, sync: bool = True, batched: bool = True, n_streams: int
     batched=False: one cppf_pose_fused call per object on the current stream, pairs drawn by torch.randint.
     Either way every object is enqueued before the first record is read.  Returns the list of pose dicts (sync=True),
     or a PendingBatch / list of PendingPose."""
-    if batched and all(it[0]._onecall_ok() and it[0].grid_capacity(it[1]) is not None for it in items):
-        pend = enqueue_batch(items, n_streams=n_streams, n_threads=n_threads)
-        return pend.results() if sync else pend
+    if batched and all(it[0]._onecall_ok() for it in items):
+        try:
+            pend = enqueue_batch(items, n_streams=n_streams, n_threads=n_threads)
+            return pend.results() if sync else pend
+        except RuntimeError as e:           # a vote grid too large for the one-call path: per-object calls (staged fallback)
+            if "too large" not in str(e):
+                raise
     pend = [est.estimate_fused(pc, nrm, seed=seed, sync=False) for est, pc, nrm, seed in items]
     return [p.result() for p in pend] if sync else pend

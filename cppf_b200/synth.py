@@ -57,7 +57,8 @@ def dense_pairs(n: int) -> np.ndarray:
 
 def vote_grid_geometry(pc: np.ndarray, res: float):
     """nocs/inference.py:194-195: corner = min, grid = int((max-min)/res)+1 per axis."""
-    lo, hi = np.min(pc, 0), np.max(pc, 0)
+    t = np.ascontiguousarray(np.asarray(pc).T)           # [3, N]: numpy reduces a [N, 3] array along axis 0 ~25x slower
+    lo, hi = t.min(1), t.max(1)
     dims = ((hi - lo) / res).astype(np.int32) + 1
     return lo.astype(np.float32), tuple(int(d) for d in dims)
 
