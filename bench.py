@@ -490,7 +490,7 @@ def main():
         barrier()
         sweep = {}
         best = None
-        for n_str, n_thr in ((1, 1), (2, 2), (4, 4), (8, 4)):
+        for n_str, n_thr in ((1, 1), (2, 2), (4, 4), (8, 4), (8, 8)):
             reps, host = [], []
             for _ in range(3):
                 torch.cuda.synchronize()
@@ -524,14 +524,16 @@ def main():
         for s_ in range(3):
             enq(s_).result()
         barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        pend = [enq(s_) for s_ in range(n_s)]
-        for q in pend:
-            q.result()
-        a1.record()
-        barrier()
-        ms_loop = a0.elapsed_time(a1)
+        ms_loop = None
+        for _ in range(3):              # the first pass grows torch's caching allocator (240 objects' pair lists alive at once)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            pend = [enq(s_) for s_ in range(n_s)]
+            for q in pend:
+                q.result()
+            a1.record()
+            barrier()
+            ms_loop = a0.elapsed_time(a1) if ms_loop is None else min(ms_loop, a0.elapsed_time(a1))
         stage_s = {}
         if timing:                      # stage breakdown from a separate short run (event records slow short objects down)
             L.cppf_timing_collect(timing, (C.c_float * len(stage_names))())
