@@ -7,6 +7,19 @@ namespace cppf {
 
 // process-wide launch counter behind cppf_launch_count() (defined in abi.cu)
 void count_launch(int n = 1);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) takes the context lock and costs microseconds, and the object loop
+// launches six kernels that need more than 48 KB: the limit of a kernel is raised once per device (and again only if a
+// later launch needs more), not before every launch.  Defined in abi.cu.
+int raise_dynamic_smem(const void* kernel, int bytes);
+// True while cppf_pose_fused is enqueueing an object on this host thread: it clears every accumulator of its workspace
+// (vote scratch, argmax keys, sphere counts, statistics) with ONE memset and initialises the global-max scratch in its
+// geometry kernel, so the launchers below skip their own small memsets / init kernels (6 driver calls per object).
+// Standalone calls through the C ABI never see it set.  Defined in abi.cu.
+extern thread_local bool t_workspace_prepared;
+struct PreparedWorkspaceScope {
+    PreparedWorkspaceScope() { t_workspace_prepared = true; }
+    ~PreparedWorkspaceScope() { t_workspace_prepared = false; }
+};
 
 #define CPPF_RETURN_IF(err_expr)                         \
     do {                                                 \

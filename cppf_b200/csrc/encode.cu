@@ -171,7 +171,7 @@ extern "C" int cppf_ppf_encode(const float* pc, const float* nrm, const float* t
     long long ctas = (n_tiles + kEncWarps - 1) / kEncWarps;
     if (ctas > sm_count()) ctas = sm_count();
     auto kern = idx_is_64 ? ppf_encode_kernel<true> : ppf_encode_kernel<false>;
-    CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)kern, (int)smem));
     kern<<<(int)ctas, kEncWarps * 32, smem, (cudaStream_t)stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     return 0;

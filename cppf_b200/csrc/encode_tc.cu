@@ -675,11 +675,18 @@ extern "C" int cppf_encode_sample_tc_rows(const float* pc, const float* nrm, con
     const long long n_tiles = dense ? (n_pairs / n_points) * ((n_points + tc::kTile - 1) / tc::kTile)
                                     : (n_pairs + tc::kTile - 1) / tc::kTile;
     long long ctas = (n_tiles + tc::kGroups - 1) / tc::kGroups;
-    if (ctas > sm_count()) ctas = sm_count();
+    if (ctas > sm_count()) {
+        // the kernel runs in rounds of kGroups tiles per CTA: the fewest CTAs that keep the round count of a full grid finish
+        // at the same time and leave the other SMs to whatever else is in flight (the object loop overlaps several objects:
+        // 100 000 pairs = 782 tiles = 2 rounds on 98 CTAs instead of 1.3 rounds on 148)
+        const long long rounds = (n_tiles + (long long)sm_count() * tc::kGroups - 1) / ((long long)sm_count() * tc::kGroups);
+        ctas = (n_tiles + rounds * tc::kGroups - 1) / (rounds * tc::kGroups);
+        if (ctas > sm_count()) ctas = sm_count();
+    }
     void (*kern)(const tc::Params);
     if (dense) kern = tc::encode_sample_tc_kernel<false, true>;
     else kern = idx_is_64 ? tc::encode_sample_tc_kernel<true, false> : tc::encode_sample_tc_kernel<false, false>;
-    CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)kern, tc::kSmemBytes));
     kern<<<(int)ctas, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     return 0;

@@ -219,7 +219,7 @@ extern "C" int cppf_encode_sample(const float* pc, const float* nrm, const float
     long long ctas = (n_tiles + kFusedWarps - 1) / kFusedWarps;
     if (ctas > sm_count()) ctas = sm_count();
     auto kern = idx_is_64 ? encode_sample_kernel<true> : encode_sample_kernel<false>;
-    CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)kern, (int)smem));
     kern<<<(int)ctas, kFusedWarps * 32, smem, (cudaStream_t)stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     return 0;

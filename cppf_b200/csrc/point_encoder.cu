@@ -477,7 +477,7 @@ extern "C" int cppf_knn(const float* pc, int n_points, int k, int64_t* out_idx, 
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
     const size_t smem = (size_t)pe::kKnnWarps * (pe::kKnnBins + 2 * pe::kKnnCand) * sizeof(unsigned);
-    CPPF_RETURN_IF(cudaFuncSetAttribute(pe::knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)pe::knn_kernel, (int)smem));
     pe::knn_kernel<<<blocks, pe::kKnnWarps * 32, smem, (cudaStream_t)stream>>>(pc, n_points, k,
                                                                                 reinterpret_cast<long long*>(out_idx));
     CPPF_LAUNCH_CHECK();
@@ -489,13 +489,15 @@ extern "C" int cppf_point_encode(const float* pc, const float* nrm, const int64_
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_points <= 0) return 0;
     if (k <= 0 || k > 64) return (int)cudaErrorInvalidValue;
-    pe::glob_init_kernel<<<1, 32, 0, stream>>>(glob_scratch);
-    CPPF_LAUNCH_CHECK();
+    if (!t_workspace_prepared) {                  // cppf_pose_fused: the geometry kernel wrote the -inf already
+        pe::glob_init_kernel<<<1, 32, 0, stream>>>(glob_scratch);
+        CPPF_LAUNCH_CHECK();
+    }
     pe::Params prm{pc, nrm, reinterpret_cast<const long long*>(nbrs), pe_blob, feat, glob_scratch, n_points, k};
     const size_t smem = sizeof(float) * ((size_t)pe::kBlobFloats + (size_t)pe::kWarps * pe::kWarpFloats);
     int blocks = (n_points + pe::kWarps - 1) / pe::kWarps;
     if (blocks > sm_count()) blocks = sm_count();
-    CPPF_RETURN_IF(cudaFuncSetAttribute(pe::point_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)pe::point_encode_kernel, (int)smem));
     pe::point_encode_kernel<<<blocks, pe::kWarps * 32, smem, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     pe::point_glob_kernel<<<(n_points * 8 + 255) / 256, 256, 0, stream>>>(feat, glob_scratch, n_points);

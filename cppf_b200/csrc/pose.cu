@@ -43,7 +43,9 @@ int grid_argmax_launch(const float* grid, int64_t n_cells, const int* n_cells_de
 
 // ---- geometry: nocs/inference.py:194-195 in float32 like numpy (pc is float32, `res` a weak Python scalar)
 __global__ void __launch_bounds__(1024) geom_kernel(const float* __restrict__ pc, int n_points, float res, int max_cells,
-                                                    int routed_max_cells, int slab_cap_cells, Geom* __restrict__ out) {
+                                                    int routed_max_cells, int slab_cap_cells, Geom* __restrict__ out,
+                                                    float* __restrict__ glob) {
+    if (threadIdx.x < 8) glob[threadIdx.x] = -INFINITY;       // running global max of the point encoder (glob_init_kernel)
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = threadIdx.x; i < n_points; i += blockDim.x) {
         const f3 p = ld3(pc, i);
@@ -173,6 +175,7 @@ struct Workspace {
     size_t pool_bytes;
     int2* idx_gen;              // pairs drawn on the device (sample_pairs): [n_pairs] when the object is not dense
     size_t bytes;
+    size_t zero_bytes;                 // grid .. count: the accumulators cleared at the start of an object
 };
 
 static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int max_cells, int routed_max_cells, int n_rots,
@@ -198,6 +201,7 @@ static Workspace carve(void* base, int n_points, int64_t n_pairs, int knn, int m
     w.best = c.take<long long>(2);
     w.stats = c.take<double>(6);
     w.count = c.take<long long>(1);
+    w.zero_bytes = (size_t)(reinterpret_cast<unsigned char*>(w.count + 1) - reinterpret_cast<unsigned char*>(w.grid));
     w.pool_bytes = routed_max_cells > 0 ? (size_t)routed_pool_bytes(n_pairs, n_rots) : 0;
     w.pool = c.take<unsigned char>(w.pool_bytes);
     w.idx_gen = c.take<int2>(dense ? 0 : (size_t)n_pairs);
@@ -314,8 +318,12 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
         CPPF_LAUNCH_CHECK();
     }
     geom_kernel<<<1, 1024, 0, stream>>>(a->pc, n, a->res, a->max_cells, a->routed_max_cells, (int)slab_cap_cells(),
-                                        w.geom);
+                                        w.geom, w.glob);
     CPPF_LAUNCH_CHECK();
+    // every accumulator of the object (vote grid, its u64 scratch, argmax keys, sphere counts, statistics, survivor count)
+    // lies in one contiguous tail of the workspace: one memset instead of six
+    CPPF_RETURN_IF(cudaMemsetAsync(w.grid, 0, w.zero_bytes, stream));
+    const PreparedWorkspaceScope prepared;
     CPPF_TRY(mark());
     CPPF_TRY(cppf_knn(a->pc, n, a->knn, reinterpret_cast<int64_t*>(w.nbrs), stream));
     CPPF_TRY(cppf_point_encode(a->pc, a->nrm, reinterpret_cast<const int64_t*>(w.nbrs), a->pe_blob, w.feat, w.glob, n, a->knn,
@@ -332,7 +340,6 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
         CPPF_LAUNCH_CHECK();
     }
     CPPF_TRY(mark());
-    CPPF_RETURN_IF(cudaMemsetAsync(w.grid, 0, (size_t)cap_cells * 4, stream));
     CPPF_TRY(vote_fast_launch(a->pc, nullptr, w.bins, a->lut, idx, idx_is_64, w.grid, w.acc, nullptr, a->res, n, n_pairs,
                               a->n_rots, 0, 0, 0, a->adaptive, w.geom, a->max_cells, stream));
     if (a->routed_max_cells > 0) {      // grids of up to 8 shared-memory slabs: the kernels return at once unless geom->mode == 1
@@ -351,7 +358,6 @@ extern "C" int cppf_pose_fused(const cppf_pose_args* a, void* stream_) {
     // survivors stay addressed through the mask: per-block counts + scan instead of a materialised list (:230-231)
     CPPF_TRY(cppf_compact_count(w.mask, n_pairs, reinterpret_cast<int64_t*>(w.count), w.compact_scratch, stream));
     CPPF_TRY(mark());
-    CPPF_RETURN_IF(cudaMemsetAsync(w.counts, 0, (size_t)a->n_sphere * 2 * sizeof(float), stream));
     const int64_t max_samples = a->rot_subsample > 0 ? a->rot_subsample : n_pairs;
     for (int j = 0; j < n_dirs; ++j) {
         CPPF_TRY(cppf_rot_hist_mask(a->pc, w.bins, a->lut, idx, idx_is_64, w.mask,

@@ -586,7 +586,7 @@ namespace cppf {
 int grid_argmax_launch(const float* grid, int64_t n_cells, const int* n_cells_dev, int64_t* out_index, float* out_value,
                        cudaStream_t stream) {
     if (n_cells <= 0 || n_cells > 0xFFFFFFFFll) return (int)cudaErrorInvalidValue;
-    CPPF_RETURN_IF(cudaMemsetAsync(out_index, 0, sizeof(int64_t), stream));
+    if (!t_workspace_prepared) CPPF_RETURN_IF(cudaMemsetAsync(out_index, 0, sizeof(int64_t), stream));
     grid_argmax_kernel<<<blocks_for(n_cells, 256, 4), 256, 0, stream>>>(grid, (long long)n_cells,
                                                                        reinterpret_cast<unsigned long long*>(out_index),
                                                                        n_cells_dev);

@@ -946,7 +946,7 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
     int terr = 0;
     const float2* rot_tab = rot_table_device(stream, &terr);
     if (terr) return terr;
-    CPPF_RETURN_IF(cudaMemsetAsync(scratch, 0, (size_t)total_cells * 8, stream));
+    if (!t_workspace_prepared) CPPF_RETURN_IF(cudaMemsetAsync(scratch, 0, (size_t)total_cells * 8, stream));
 #if CPPF_VOTE_CONST_TAB
     {   // once per device: copy the table into this module's constant bank; the first call waits for the copy so that a
         // concurrent first call on another stream cannot run ahead of it
@@ -993,7 +993,7 @@ int vote_fast_launch(const float* points, const float* mu_nu, const uint8_t* bin
         if (bins) kern = idx_is_64 ? vote_private_kernel<true, true, false> : vote_private_kernel<false, true, false>;
         else kern = idx_is_64 ? vote_private_kernel<true, false, false> : vote_private_kernel<false, false, false>;
     }
-    CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)kern, (int)smem));
     kern<<<(int)blocks, threads, smem, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     vote_finalize_kernel<<<(int)((total_cells + 255) / 256), 256, 0, stream>>>(
@@ -1112,7 +1112,7 @@ int rot_hist_launch(const float* points, const uint8_t* bins, const float* lut, 
     const size_t smem = (size_t)n_bins * 20;
     if (smem > 160 * 1024) return (int)cudaErrorInvalidValue;
     auto kern = idx_is_64 ? rot_hist_kernel<true> : rot_hist_kernel<false>;
-    if (smem > 40 * 1024) CPPF_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)kern, (int)smem));
     kern<<<(int)blocks, kRotHistThreads, smem, stream>>>(prm);
     CPPF_LAUNCH_CHECK();
     return 0;
@@ -1123,7 +1123,7 @@ int survivor_stats_launch(const float* points, const float* nrm, const float* ta
                           const int64_t* best_up, const int64_t* best_right, double* out, int n_points, int64_t n_pairs,
                           cudaStream_t stream, int row0 = 0) {
     if (pos == nullptr && mask == nullptr) return (int)cudaErrorInvalidValue;
-    CPPF_RETURN_IF(cudaMemsetAsync(out, 0, 6 * sizeof(double), stream));
+    if (!t_workspace_prepared) CPPF_RETURN_IF(cudaMemsetAsync(out, 0, 6 * sizeof(double), stream));
     const bool aligned = (((uintptr_t)points | (uintptr_t)tail | (uintptr_t)mask) & 15u) == 0;
     const int vec4 = (pos == nullptr && idx == nullptr && (n_points & 3) == 0 && aligned) ? 1 : 0;
     StatsParams prm{points, nrm, tail, idx, reinterpret_cast<const long long*>(pos), mask,

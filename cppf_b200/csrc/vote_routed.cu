@@ -528,10 +528,10 @@ int vote_routed_launch(const float* points, const float* mu_nu, const uint8_t* b
     if (bins) route = idx_is_64 ? route_kernel<true, true> : route_kernel<false, true>;
     else route = idx_is_64 ? route_kernel<true, false> : route_kernel<false, false>;
     const size_t rsmem = route_smem();
-    CPPF_RETURN_IF(cudaFuncSetAttribute(route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)route, (int)rsmem));
     const long long slab_cells = geom ? slab_cap_cells() : (long long)(pl.planes_per_slab + 1) * slab_plane_stride(gy, gz);
     const size_t ssmem = (size_t)slab_cells * 4;
-    CPPF_RETURN_IF(cudaFuncSetAttribute(slab_splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)slab_splat_kernel, (int)ssmem));
     const int64_t total_batches = idx == nullptr
                                       ? (int64_t)((n_points + kRTileA - 1) / kRTileA) * ((n_points + kRTileB - 1) / kRTileB)
                                       : (n_pairs + kRouteBatch - 1) / kRouteBatch;
