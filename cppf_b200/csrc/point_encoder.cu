@@ -15,10 +15,12 @@
 //                         max over all points (sprin.py:74-83, ordered-int atomic max: exact and order-free).
 //   cppf_point_glob     : writes the 8 global-max columns into every row of feat[N, 40].
 #include "encode.cuh"
+#include "tc_common.cuh"
 
 #include "../../include/cppf_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace cppf {
 namespace pe {
@@ -281,6 +283,269 @@ __global__ void __launch_bounds__(kWarps * 32, 1) point_encode_kernel(const Para
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same convolution on the 5th-generation tensor cores (tcgen05 + TMEM, building blocks of tc_common.cuh).
+//
+//   * a tile is 128 rows = TWO points x 64 neighbour slots (k <= 64; slots >= k are zero rows); thread t of a 128-thread
+//     group owns row t = TMEM lane t through the whole kernel MLP, so LayerNorm (a per-row statistic) needs no shuffle;
+//   * every Linear is D[128 x N] (TMEM, fp32) = A[128 x K] . W^T in 3xTF32 (hi.hi + hi.lo + lo.hi), its bias put into the
+//     accumulators by a ones-operand MMA; the epilogue of a layer (TMEM -> registers, LayerNorm, ReLU, tf32 split) writes the
+//     next layer's A operand.  Linear(64, 32) runs as two K = 32 halves through the same 32 KB A buffer, so that four
+//     groups (four tiles in flight per SM, one group's epilogue under the others' MMAs) fit beside the weights;
+//   * the MMA operands (hi / lo split, canonical layout) are packed by the host behind the FFMA section of the blob
+//     (cppf_b200/model.py: pack_pe_weights) and staged with one straight copy;
+//   * the rank-32 contraction over a point's neighbours (sprin.py:98) goes through the group's A buffer, free again after
+//     the last MMA: every row parks its 32 kernel values there and 128 threads sum (rank, feature) columns over 64 rows;
+//     the 64 -> 32 output Linear + LayerNorm + GlobalInfoProp run on one warp per point as in the FFMA kernel.
+// 245 760 rows (N = 4096, k = 60) -> 1920 tiles, 67 MMAs of shape 128 x N x 8 each.
+namespace tcpe {
+using namespace tc;
+constexpr int kGroups = 4;
+constexpr int kThreads = kGroups * kTile;
+constexpr int kSlots = 64;                       // neighbour slots per point in a tile
+// shared-memory operand section (floats): B operands [K/4][N][4], hi block then lo block
+constexpr int oW1 = 0;                           // N = 32, K = 8 (k = 6, 7 zero)
+constexpr int oW2 = oW1 + 2 * 32 * 8;            // N = 64, K = 32
+constexpr int oW3a = oW2 + 2 * 64 * 32;          // N = 32, K = 32: input columns 0..31 of Linear(64, 32)
+constexpr int oW3b = oW3a + 2 * 32 * 32;         //                 input columns 32..63
+constexpr int oW4 = oW3b + 2 * 32 * 32;
+constexpr int oW5 = oW4 + 2 * 32 * 32;
+constexpr int oV1 = oW5 + 2 * 32 * 32;           // bias operands [N x 8]: k = 0 hi, k = 4 lo
+constexpr int oV2 = oV1 + 32 * 8;
+constexpr int oV3 = oV2 + 64 * 8;
+constexpr int oV4 = oV3 + 32 * 8;
+constexpr int oV5 = oV4 + 32 * 8;
+constexpr int oLN = oV5 + 32 * 8;                // gamma1 beta1 | gamma2 beta2 | gamma3 beta3 | gamma4 beta4
+constexpr int oG1 = oLN, oE1 = oG1 + 32, oG2 = oE1 + 32, oE2 = oG2 + 64, oG3 = oE2 + 64, oE3 = oG3 + 32, oG4 = oE3 + 32,
+              oE4 = oG4 + 32;
+constexpr int oOut = oE4 + 32;                   // outnet ... GlobalInfoProp, verbatim from the blob (kWo .. kBlobFloats)
+constexpr int kOutFloats = kBlobFloats - kWo;
+constexpr int kSmemFloats = oOut + kOutFloats;
+constexpr int kSmemBytes = kSmemFloats * 4 + kOnesBytes + kGroups * kGroupBytes;
+constexpr int kTmemColsPerGroup = 64;
+// scratch inside a group's A buffer (floats), used between the last MMA of a tile and the first store of the next
+constexpr int kSS = 33;                          // row stride of the parked kernel values: (row + rank) mod 32 banks
+constexpr int sNF = kTile * kSS;                 // [128][2] neighbour features
+constexpr int sCT = 6144;                        // [2][64] contraction, in plane 4 of the lo half: the first two K planes of
+                                                 // either half are the ones the next tile's step 0 writes
+static_assert(sNF + 2 * kTile <= sCT && (sCT + 128) * 4 <= kGroupBytes, "scratch fits the A buffer");
+static_assert(sCT * 4 >= kABytes + 2 * kAPlane, "contraction result clear of the next tile's K = 8 operand");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+static_assert(kBlobFloats % 4 == 0 && kSmemFloats % 4 == 0, "float4 staging");
+
+// LayerNorm + ReLU of NF values of this thread's row (sprin.py:67-68), then the row's K chunks of the next A operand
+template <int NF>
+__device__ __forceinline__ void ln_relu(float (&v)[NF], const float* __restrict__ gamma, const float* __restrict__ beta) {
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) mean += v[j];
+    mean *= 1.f / NF;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+        v[j] -= mean;
+        var = fmaf(v[j], v[j], var);
+    }
+    const float rstd = rsqrtf(var * (1.f / NF) + kLnEps);
+#pragma unroll
+    for (int j = 0; j < NF; j += 4) {
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + j), bt = *reinterpret_cast<const float4*>(beta + j);
+        v[j] = fmaxf(fmaf(v[j] * rstd, gm.x, bt.x), 0.f);
+        v[j + 1] = fmaxf(fmaf(v[j + 1] * rstd, gm.y, bt.y), 0.f);
+        v[j + 2] = fmaxf(fmaf(v[j + 2] * rstd, gm.z, bt.z), 0.f);
+        v[j + 3] = fmaxf(fmaf(v[j + 3] * rstd, gm.w, bt.w), 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) point_encode_tc_kernel(const Params prm) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar[kGroups];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_red[kGroups][4][3];
+    float* sWf = reinterpret_cast<float*>(smem);
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction (see encode_tc.cu)
+    const int lane = tid & 31;
+    const int g = warp >> 2, tg = tid & 127, wg = warp & 3;
+    unsigned char* s_ones = smem + kSmemFloats * 4;
+    unsigned char* a_hi = s_ones + kOnesBytes + g * kGroupBytes;
+    float* scratch = reinterpret_cast<float*>(a_hi);
+
+    {   // operands -> shared memory (packed by the host behind the FFMA section of the blob), TMEM allocation, barriers
+        const float4* src = reinterpret_cast<const float4*>(prm.blob + kBlobFloats);
+        float4* dst = reinterpret_cast<float4*>(sWf);
+        for (int i = tid; i < kSmemFloats / 4; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < kOnesBytes / 16; i += kThreads)                 // k = 0 and k = 4 of every row are 1
+            reinterpret_cast<float4*>(s_ones)[i] = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                         "r"(kGroups * kTmemColsPerGroup)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        if (tid < kGroups) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[tid])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const uint32_t tm = s_tmem + g * kTmemColsPerGroup;
+    const uint32_t tml = tm + ((uint32_t)(wg * 32) << 16);                    // this warp's lane quarter for tcgen05.ld
+    const uint32_t bar = smem_u32(&s_bar[g]);
+    const uint32_t sA = smem_u32(a_hi), sAl = sA + kABytes;
+    const uint32_t sW = smem_u32(sWf);
+    const uint32_t sOnes = smem_u32(s_ones);
+    const bool lead_warp = wg == 0;
+    uint32_t phase = 0;
+    const float* sOutW = sWf + oOut;                                          // offsets below relative to kWo
+    const int ps = tg >> 6, slot = tg & (kSlots - 1);
+    const float inv_k = 1.f / (float)prm.k;
+    const int n_tiles = (prm.n_points + 1) / 2;
+    float tmax = -INFINITY;                                                   // warps 0, 1 of a group, lanes 0..7
+
+    // The neighbour data of a tile is fetched one tile ahead (index early in the previous tile, the two gathers it feeds in
+    // the middle of it): an SM configured with 200 KB of shared memory has next to no L1, and the index -> point chain is
+    // two L2 round trips at the head of every tile otherwise.
+    const int t_stride = gridDim.x * kGroups;
+    long long id_n = 0;
+    f3 ctr_n = {0.f, 0.f, 0.f}, ncn_n = ctr_n, nb_n = ctr_n, nn_n = ctr_n;
+    auto fetch_id = [&](int tile) {
+        const int n = 2 * tile + ps;
+        id_n = (tile < n_tiles && n < prm.n_points && slot < prm.k) ? __ldg(prm.nbrs + (long long)n * prm.k + slot) : 0;
+    };
+    auto fetch_pts = [&](int tile) {
+        const int n = 2 * tile + ps;
+        const int nc_ = (tile < n_tiles && n < prm.n_points) ? n : 0;
+        ctr_n = ld3(prm.pc, nc_); ncn_n = ld3(prm.nrm, nc_);
+        nb_n = ld3(prm.pc, id_n); nn_n = ld3(prm.nrm, id_n);
+    };
+    int tile = blockIdx.x * kGroups + g;
+    fetch_id(tile);
+    fetch_pts(tile);
+    for (; tile < n_tiles; tile += t_stride) {
+        const int n = 2 * tile + ps;
+        const bool have_pt = n < prm.n_points;
+        const bool ok = have_pt && slot < prm.k;
+        const f3 ctr = ctr_n, ncn = ncn_n, nb = nb_n, nn = nn_n;
+        fetch_id(tile + t_stride);
+        {   // mean of the point's k neighbours (sprin.py:51): two warps per point
+            const float sx = warp_sum(ok ? nb.x : 0.f), sy = warp_sum(ok ? nb.y : 0.f), sz = warp_sum(ok ? nb.z : 0.f);
+            if (lane == 0) {
+                s_red[g][wg][0] = sx; s_red[g][wg][1] = sy; s_red[g][wg][2] = sz;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+        }
+        f3 mean;
+        mean.x = (s_red[g][2 * ps][0] + s_red[g][2 * ps + 1][0]) * inv_k;
+        mean.y = (s_red[g][2 * ps][1] + s_red[g][2 * ps + 1][1]) * inv_k;
+        mean.z = (s_red[g][2 * ps][2] + s_red[g][2 * ps + 1][2]) * inv_k;
+        float nf0 = 0.f, nf1 = 0.f;
+        {   // rifeat (sprin.py:52-60) and the two neighbour features (models/model.py:49-53)
+            const f3 l1 = mean - nb, l2 = nb - ctr, l3 = ctr - mean;
+            const float n1 = len3(l1), n2 = len3(l2), n3 = len3(l3);
+            const float r3 = dot3(l1, l2) / (n1 * n2 + 1e-7f), r4 = dot3(l2, l3) / (n2 * n3 + 1e-7f),
+                        r5 = dot3(l3, l1) / (n3 * n1 + 1e-7f);
+            if (ok) {
+                st_chunk(a_hi, 0, tg, n1, n2, n3, r3);
+                st_chunk(a_hi, 1, tg, r4, r5, 0.f, 0.f);
+                nf0 = n2;                                                     // |p_k - p|
+                nf1 = dot3(nn, ncn);                                          // n_k . n
+            } else {
+                st_chunk(a_hi, 0, tg, 0.f, 0.f, 0.f, 0.f);
+                st_chunk(a_hi, 1, tg, 0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float x[32], y[32];
+        // ---- Linear(6, 32) -> LN -> ReLU
+        CPPF_TC_STEP((issue_bias<32>(tm, sOnes, sW + oV1 * 4), issue3<32, 8, true>(tm, sA, sAl, sW + oW1 * 4)));
+        tmem_ld32(tml, x);
+        ln_relu<32>(x, sWf + oG1, sWf + oE1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st_chunk(a_hi, q, tg, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        // ---- Linear(32, 64) -> LN -> ReLU
+        CPPF_TC_STEP((issue_bias<64>(tm, sOnes, sW + oV2 * 4), issue3<64, 32, true>(tm, sA, sAl, sW + oW2 * 4)));
+        {
+            float z[64];
+            tmem_ld32(tml, x);
+            tmem_ld32(tml + 32, y);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                z[q] = x[q];
+                z[32 + q] = y[q];
+            }
+            ln_relu<64>(z, sWf + oG2, sWf + oE2);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                x[q] = z[q];
+                y[q] = z[32 + q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st_chunk(a_hi, q, tg, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        // ---- Linear(64, 32) in two K = 32 halves -> LN -> ReLU
+        CPPF_TC_STEP((issue_bias<32>(tm, sOnes, sW + oV3 * 4), issue3<32, 32, true>(tm, sA, sAl, sW + oW3a * 4)));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st_chunk(a_hi, q, tg, y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+        fetch_pts(tile + t_stride);
+        CPPF_TC_STEP((issue3<32, 32, true>(tm, sA, sAl, sW + oW3b * 4)));
+        tmem_ld32(tml, x);
+        ln_relu<32>(x, sWf + oG3, sWf + oE3);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st_chunk(a_hi, q, tg, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        // ---- Linear(32, 32) -> LN -> ReLU
+        CPPF_TC_STEP((issue_bias<32>(tm, sOnes, sW + oV4 * 4), issue3<32, 32, true>(tm, sA, sAl, sW + oW4 * 4)));
+        tmem_ld32(tml, x);
+        ln_relu<32>(x, sWf + oG4, sWf + oE4);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st_chunk(a_hi, q, tg, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        // ---- Linear(32, 32): the rank-32 kernel of each neighbour
+        CPPF_TC_STEP((issue_bias<32>(tm, sOnes, sW + oV5 * 4), issue3<32, 32, true>(tm, sA, sAl, sW + oW5 * 4)));
+        tmem_ld32(tml, x);
+        // ---- einsum('bnkr,bnki->bnri') (sprin.py:98) through the A buffer (every MMA that read it has completed)
+#pragma unroll
+        for (int r = 0; r < 32; ++r) scratch[tg * kSS + r] = x[r];
+        *reinterpret_cast<float2*>(scratch + sNF + 2 * tg) = make_float2(nf0, nf1);
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+        {
+            const int r = slot >> 1, i = slot & 1;                            // this thread's (rank, neighbour feature) of point ps
+            const float* kv = scratch + (ps * kSlots) * kSS + r;
+            const float* nf = scratch + sNF + 2 * (ps * kSlots) + i;
+            float c = 0.f;
+#pragma unroll 8
+            for (int row = 0; row < kSlots; ++row) c = fmaf(kv[row * kSS], nf[2 * row], c);
+            scratch[sCT + ps * 64 + slot] = c;                                // flatten(-2): index r * 2 + i
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+        if (wg < 2) {                        // warp wg of the group finishes point wg of the tile: lane = output column
+            const int np = 2 * tile + wg;
+            const float* ct = scratch + sCT + wg * 64;
+            float o = sOutW[(kBo - kWo) + lane];                              // outnet Linear(64, 32)   (sprin.py:99)
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) o = fmaf(ct[k], sOutW[k * 32 + lane], o);
+            const float m = warp_sum(o) * (1.f / 32.f);                       // LayerNorm(32) across the lanes (sprin.py:100-101)
+            const float d = o - m;
+            const float var = warp_sum(d * d) * (1.f / 32.f);
+            const float yv = fmaf(d * rsqrtf(var + kLnEps), sOutW[(kGo - kWo) + lane], sOutW[(kEo - kWo) + lane]);
+            if (np < prm.n_points) prm.feat[(long long)np * 40 + lane] = yv;
+            float t = lane < 8 ? sOutW[(kBa - kWo) + lane] : 0.f;             // GlobalInfoProp (sprin.py:80-82)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float yk = __shfl_sync(0xffffffffu, yv, k);
+                if (lane < 8) t = fmaf(yk, sOutW[(kWa - kWo) + k * 8 + lane], t);
+            }
+            if (np < prm.n_points) tmax = (t > tmax || t != t) ? t : tmax;    // NaN sticks, like torch.max
+        }
+    }
+    if (wg < 2 && lane < 8 && tmax != -INFINITY) atomic_max_float(prm.glob + lane, tmax);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(kGroups * kTmemColsPerGroup)
+                     : "memory");
+}
+}  // namespace tcpe
+
 __global__ void __launch_bounds__(256) point_glob_kernel(float* __restrict__ feat, const float* __restrict__ glob, int n_points) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_points * 8) feat[(long long)(i >> 3) * 40 + 32 + (i & 7)] = glob[i & 7];
@@ -468,7 +733,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
 
 using namespace cppf;
 
-extern "C" int cppf_pe_blob_floats(void) { return pe::kBlobFloats; }
+extern "C" int cppf_pe_blob_floats(void) { return pe::kBlobFloats + pe::tcpe::kSmemFloats; }
 
 extern "C" int cppf_knn(const float* pc, int n_points, int k, int64_t* out_idx, void* stream) {
     if (n_points <= 0) return 0;
@@ -494,12 +759,26 @@ extern "C" int cppf_point_encode(const float* pc, const float* nrm, const int64_
         CPPF_LAUNCH_CHECK();
     }
     pe::Params prm{pc, nrm, reinterpret_cast<const long long*>(nbrs), pe_blob, feat, glob_scratch, n_points, k};
-    const size_t smem = sizeof(float) * ((size_t)pe::kBlobFloats + (size_t)pe::kWarps * pe::kWarpFloats);
-    int blocks = (n_points + pe::kWarps - 1) / pe::kWarps;
-    if (blocks > sm_count()) blocks = sm_count();
-    CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)pe::point_encode_kernel, (int)smem));
-    pe::point_encode_kernel<<<blocks, pe::kWarps * 32, smem, stream>>>(prm);
-    CPPF_LAUNCH_CHECK();
+    // CPPF_PE_IMPL=simt selects the FFMA kernel (kept as the cross-check of the tensor-core one)
+    const char* impl_env = getenv("CPPF_PE_IMPL");                // read per call so that a test can compare the two kernels
+    const bool simt = impl_env != nullptr && impl_env[0] == 's';
+    if (!simt) {
+        const long long n_tiles = ((long long)n_points + 1) / 2;
+        const long long per_round = (long long)sm_count() * pe::tcpe::kGroups;
+        const long long rounds = (n_tiles + per_round - 1) / per_round;
+        long long ctas = (n_tiles + rounds * pe::tcpe::kGroups - 1) / (rounds * pe::tcpe::kGroups);   // fewest CTAs for that many rounds
+        if (ctas > sm_count()) ctas = sm_count();
+        CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)pe::tcpe::point_encode_tc_kernel, pe::tcpe::kSmemBytes));
+        pe::tcpe::point_encode_tc_kernel<<<(int)ctas, pe::tcpe::kThreads, pe::tcpe::kSmemBytes, stream>>>(prm);
+        CPPF_LAUNCH_CHECK();
+    } else {
+        const size_t smem = sizeof(float) * ((size_t)pe::kBlobFloats + (size_t)pe::kWarps * pe::kWarpFloats);
+        int blocks = (n_points + pe::kWarps - 1) / pe::kWarps;
+        if (blocks > sm_count()) blocks = sm_count();
+        CPPF_RETURN_IF((cudaError_t)raise_dynamic_smem((const void*)pe::point_encode_kernel, (int)smem));
+        pe::point_encode_kernel<<<blocks, pe::kWarps * 32, smem, stream>>>(prm);
+        CPPF_LAUNCH_CHECK();
+    }
     pe::point_glob_kernel<<<(n_points * 8 + 255) / 256, 256, 0, stream>>>(feat, glob_scratch, n_points);
     CPPF_LAUNCH_CHECK();
     return 0;

@@ -387,8 +387,19 @@ def pack_pe_weights(sd) -> np.ndarray:
     wo = g("spconvs.0.outnet.weight")
     if wo.shape != (32, 64) or "spconvs.0.layer_norm.weight" not in sd or g("aggrs.0.linear.weight").shape != (8, 32):
         raise NotImplementedError("fused point encoder needs num_nbr_feats=2, out_dim=32 with layer_norm")
-    parts += [wo.T, g("spconvs.0.outnet.bias"), g("spconvs.0.layer_norm.weight"), g("spconvs.0.layer_norm.bias"),
-              g("aggrs.0.linear.weight").T, g("aggrs.0.linear.bias")]
+    tail = [wo.T, g("spconvs.0.outnet.bias"), g("spconvs.0.layer_norm.weight"), g("spconvs.0.layer_norm.bias"),
+            g("aggrs.0.linear.weight").T, g("aggrs.0.linear.bias")]
+    parts += tail
+    # second section: the same layers as tcgen05 operands (point_encode_tc_kernel, tcpe::o* offsets): canonical K-major hi / lo
+    # weights -- Linear(64, 32) as two K = 32 halves --, biases as ones-operand rows, LayerNorm vectors, then the tail again
+    ws = [g(f"spconvs.0.kernel.{seq}.weight") for seq in (0, 3, 6, 9, 12)]
+    bs = [g(f"spconvs.0.kernel.{seq}.bias") for seq in (0, 3, 6, 9, 12)]
+    parts += _canon_hi_lo(ws[0], 32, 8) + _canon_hi_lo(ws[1], 64, 32) + _canon_hi_lo(ws[2][:, :32], 32, 32)
+    parts += _canon_hi_lo(ws[2][:, 32:], 32, 32) + _canon_hi_lo(ws[3], 32, 32) + _canon_hi_lo(ws[4], 32, 32)
+    parts += [_row_constant_operand(b, b.shape[0]) for b in bs]
+    for seq in (1, 4, 7, 10):
+        parts += [g(f"spconvs.0.kernel.{seq}.weight"), g(f"spconvs.0.kernel.{seq}.bias")]
+    parts += tail
     blob = np.concatenate([np.ascontiguousarray(q, dtype=np.float32).reshape(-1) for q in parts])
     assert blob.size == _lib.lib().cppf_pe_blob_floats(), blob.size
     return blob

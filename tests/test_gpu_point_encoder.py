@@ -99,3 +99,25 @@ def test_knn_boundary_bin_overflow_falls_back_to_radix_select():
     idx = torch.sort(pe.knn(t), dim=1)[0].cpu().numpy()
     assert idx[0].tolist() == list(range(60))                    # 10 at d=0, then the 50 lowest-index coincident points
     assert idx[300].tolist() == list(range(10, 70))              # a coincident point: 60 lowest indices among its 500 twins
+
+
+@pytest.mark.parametrize("n,k,seed", [(4096, 60, 0), (1001, 60, 1), (257, 64, 2), (90, 7, 3), (1, 1, 4)])
+def test_tensor_core_kernel_equals_ffma_kernel(n, k, seed, monkeypatch):
+    """point_encode_tc_kernel (tcgen05, 3xTF32, two points per 128-row tile) against point_encode_kernel (fp32 FFMA, one
+    warp per point) on the same neighbour lists: ragged last tile (odd n), k = 64 (no padding rows), k < 32, one point."""
+    torch.manual_seed(seed)
+    pe = model.PointEncoder(k=k, spfcs=[32, 64, 32, 32], num_layers=1, out_dim=32).to(DEV).eval()
+    with torch.no_grad():
+        for p in pe.parameters():
+            p.mul_(1.3)
+    pc, nrm = synth.synth_bottle(max(n, 2), seed)
+    pc, nrm = torch.from_numpy(pc[:n]).to(DEV), torch.from_numpy(nrm[:n]).to(DEV)
+    nbrs = pe.knn(pc)
+    with torch.no_grad():
+        monkeypatch.setenv("CPPF_PE_IMPL", "simt")
+        ffma = pe.encode_fused(pc, nrm, nbrs)
+        monkeypatch.setenv("CPPF_PE_IMPL", "tc")
+        tc = pe.encode_fused(pc, nrm, nbrs)
+        tc2 = pe.encode_fused(pc, nrm, nbrs)
+    assert torch.equal(tc, tc2)                                                  # deterministic (the global max is order-free)
+    np.testing.assert_allclose(tc.cpu().numpy(), ffma.cpu().numpy(), rtol=2e-5, atol=2e-5)
