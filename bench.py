@@ -655,7 +655,7 @@ def main():
         binding = {"encode_sample": "SIMT epilogues between the tcgen05 MMA steps (3xTF32 chain)" if args.encoder == "tc" else "fp32 FMA pipe",
                    "vote": "shared-memory atomic pipe (random-bank replays) and issue slots",
                    "backvote": "fp32 / issue", "ppf_vote": "L2 atomic throughput", "stats": "HBM gather",
-                   "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "FP32/issue (two-sweep kNN select + one-warp-per-point SPRIN MLP)"}
+                   "ppf_encode_pass1": "fp32 FMA pipe", "point_encoder": "kNN: issue / LSU (two-sweep select); SPRIN: SIMT LayerNorm epilogues between the tcgen05 MMA steps (3xTF32, two points per 128-row tile)"}
         detail = {}
         for k, v in kern.items():
             t = v["avg_ms"] * 1e-3

@@ -20,7 +20,7 @@ KERNELS = {
     "vote": ("vote_private_kernel", "cppf_b200/csrc/vote_private.cu"),
     "backvote": ("backvote_bins_kernel", "cppf_b200/csrc/vote_private.cu"),
     "stats": ("survivor_stats_kernel", "cppf_b200/csrc/vote_private.cu"),
-    "point_encoder": ("point_encode_kernel", "cppf_b200/csrc/point_encoder.cu"),
+    "point_encoder": ("point_encode_tc_kernel", "cppf_b200/csrc/point_encoder.cu"),
 }
 METRICS = {
     "gpu__time_duration.sum": "duration_ms_under_ncu",
