@@ -135,7 +135,10 @@ int cppf_findpeak(const float* grid, float* out, int width, int gx, int gy, int 
  * cppf_point_encode replaces PointEncoder.forward_nbrs (models/model.py:63-77) for the reference
  * configuration (spfcs=[32,64,32,32], rank 32, 2 neighbour features, out_dim 32, k <= 64): feat
  * [n_points, 40] = [SPRIN conv + LayerNorm (32) | global max of the 8-column GlobalInfoProp linear].
- * pe_blob: cppf_pe_blob_floats() floats (cppf_b200/model.py:pack_pe_weights); glob_scratch: 8 floats. */
+ * The SPRIN MLP runs on the tensor cores (tcgen05, 3xTF32: fp32-grade results); the environment variable
+ * CPPF_PE_IMPL=simt, read per call, selects the fp32 FFMA kernel kept as its cross-check.
+ * pe_blob: cppf_pe_blob_floats() floats (cppf_b200/model.py:pack_pe_weights: the FFMA section, then the same layers as
+ * tcgen05 operands); 16-byte aligned; glob_scratch: 8 floats. */
 int cppf_pe_blob_floats(void);
 int cppf_knn(const float* pc, int n_points, int k, int64_t* out_idx, void* stream);
 int cppf_point_encode(const float* pc, const float* nrm, const int64_t* nbrs, const float* pe_blob, float* feat,
