@@ -174,3 +174,68 @@ def test_packed_blobs_follow_the_weights():
     b2 = m.tc_blob("cpu")
     assert b2 is not b1 and not torch.equal(b2, b1)
     assert torch.equal(b2, torch.from_numpy(model.pack_tc_weights(m.state_dict())))
+
+
+def test_point_encoder_tensor_core_section_reproduces_reference_features():
+    """CPU: the second section of the PointEncoder blob (model.pack_pe_weights: tcgen05 operands of
+    csrc/point_encoder.cu, namespace tcpe) interpreted in numpy the way point_encode_tc_kernel walks it -- canonical
+    K-major [K/4][N][4] operands as hi + lo, Linear(64, 32) as two K = 32 halves, biases as ones-operand rows (k = 0 hi,
+    k = 4 lo), LayerNorm vectors, output tail -- must reproduce the reference module's features on the golden fixture
+    (models/sprin.py:40-107, models/model.py:63-77)."""
+    d = load_golden("encoder_bottle.npz")
+    sd = split_state(d, "pe/")
+    blob = model.pack_pe_weights(sd)
+    simt = 6 * 32 + 96 + 32 * 64 + 192 + 64 * 32 + 96 + 32 * 32 + 96 + 32 * 32 + 32 + 64 * 32 + 96 + 32 * 8 + 8   # pe::kBlobFloats
+    tc = blob[simt:]
+    o = [0]
+
+    def take(n):
+        v = tc[o[0]:o[0] + n]
+        o[0] += n
+        return v
+
+    def operand(n, k):                                           # -> W[n][k] = hi + lo
+        hi = take(n * k).reshape(k // 4, n, 4).transpose(1, 0, 2).reshape(n, k)
+        lo = take(n * k).reshape(k // 4, n, 4).transpose(1, 0, 2).reshape(n, k)
+        assert np.all((hi.view(np.uint32) & 0x1FFF) == 0)        # tf32: low 13 mantissa bits clear
+        return hi.astype(np.float64) + lo.astype(np.float64)
+
+    w1, w2, w3a, w3b, w4, w5 = operand(32, 8), operand(64, 32), operand(32, 32), operand(32, 32), operand(32, 32), operand(32, 32)
+    assert np.all(w1[:, 6:] == 0)
+
+    def bias(n):
+        v = take(n * 8).reshape(2, n, 4)
+        assert np.all(v[:, :, 1:] == 0)
+        return v[0, :, 0].astype(np.float64) + v[1, :, 0].astype(np.float64)
+
+    b1, b2, b3, b4, b5 = bias(32), bias(64), bias(32), bias(32), bias(32)
+    g1, e1, g2, e2, g3, e3, g4, e4 = take(32), take(32), take(64), take(64), take(32), take(32), take(32), take(32)
+    wo, bo, go, eo = take(64 * 32).reshape(64, 32), take(32), take(32), take(32)
+    wa, ba = take(32 * 8).reshape(32, 8), take(8)
+    assert o[0] == tc.size
+
+    def ln(x, g, e):
+        m = x.mean(-1, keepdims=True)
+        v = ((x - m) ** 2).mean(-1, keepdims=True)
+        return (x - m) / np.sqrt(v + 1e-5) * g + e
+
+    pc, nrm, nbrs = d["pc"].astype(np.float64), d["nrm"].astype(np.float64), d["nbrs"]
+    nb, nn = pc[nbrs], nrm[nbrs]                                 # [N, k, 3]
+    ctr = pc[:, None, :]
+    mean = nb.mean(1, keepdims=True)
+    l1, l2, l3 = mean - nb, nb - ctr, ctr - mean
+    n1, n2, n3 = [np.linalg.norm(v, axis=-1) for v in (l1, l2, l3)]
+    n3 = np.broadcast_to(n3, n1.shape)
+    ri = np.stack([n1, n2, n3, (l1 * l2).sum(-1) / (n1 * n2 + 1e-7), (l2 * l3).sum(-1) / (n2 * n3 + 1e-7),
+                   (l3 * l1).sum(-1) / (n3 * n1 + 1e-7), np.zeros_like(n1), np.zeros_like(n1)], -1)      # K padded to 8
+    x = np.maximum(ln(ri @ w1.T + b1, g1, e1), 0)
+    x = np.maximum(ln(x @ w2.T + b2, g2, e2), 0)
+    x = np.maximum(ln(x[..., :32] @ w3a.T + x[..., 32:] @ w3b.T + b3, g3, e3), 0)
+    x = np.maximum(ln(x @ w4.T + b4, g4, e4), 0)
+    kern = x @ w5.T + b5                                         # [N, k, 32]
+    nf = np.stack([n2, (nn * nrm[:, None, :]).sum(-1)], -1)      # [N, k, 2]
+    ct = np.einsum("nkr,nki->nri", kern, nf).reshape(len(pc), 64)
+    y = ln(ct @ wo + bo, go, eo)
+    glob = (y @ wa + ba).max(0)
+    got = np.concatenate([y, np.broadcast_to(glob, (len(pc), 8))], 1)
+    np.testing.assert_allclose(got, d["feat_nbrs"], rtol=2e-4, atol=2e-5)
